@@ -1,0 +1,67 @@
+// K8 onset-indexed epoch gather (bit-exact copy).
+//
+// out[n, c, 0:L] = src[c, start[n] : start[n]+L].  Works on 32-bit words so float32,
+// float64 and integer sources all take the same path (elem_bytes 4 or 8).  The source
+// window is misaligned by start[n] mod 4 words, the destination row is not: each
+// thread gathers four consecutive words through L1 and issues one 128-bit store when
+// the destination allows it.  HBM-bound: 8 B per gathered element.
+#include "common.cuh"
+
+namespace ecog {
+
+constexpr int kGatherWarps = 8;
+
+// one warp per (event, channel) row; rows are distributed grid-stride
+__global__ void __launch_bounds__(kGatherWarps * 32)
+epoch_gather_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ out, int64_t C,
+                    int64_t ld_words, const int64_t* __restrict__ start, int64_t N, int64_t Lw,
+                    int words_per_elem, bool vec_store) {
+    const int lane = threadIdx.x & 31;
+    const int64_t rows = N * C;
+    for (int64_t r = (int64_t)blockIdx.x * kGatherWarps + (threadIdx.x >> 5); r < rows;
+         r += (int64_t)gridDim.x * kGatherWarps) {
+        const int64_t n = r / C, c = r - n * C;
+        const uint32_t* s = src + c * ld_words + start[n] * words_per_elem;
+        uint32_t* d = out + r * Lw;
+        if (vec_store) {
+            for (int64_t i = 4 * lane; i < Lw; i += 128) {   // Lw % 4 == 0 here
+                uint4 v;
+                v.x = s[i]; v.y = s[i + 1]; v.z = s[i + 2]; v.w = s[i + 3];
+                *reinterpret_cast<uint4*>(d + i) = v;
+            }
+        } else {
+            for (int64_t i = lane; i < Lw; i += 32) d[i] = s[i];
+        }
+    }
+}
+
+}  // namespace ecog
+
+using namespace ecog;
+
+extern "C" int ecog_epoch_gather(const void* d_src, void* d_out, int64_t C, int64_t T, int64_t ld,
+                                 const int64_t* d_start, const int64_t* h_start, int64_t N, int64_t L,
+                                 int32_t elem_bytes, ecog_stream_t stream) {
+    if (elem_bytes != 4 && elem_bytes != 8) return fail(ECOG_E_VALUE, "ecog_epoch_gather: elem_bytes must be 4 or 8");
+    if (C <= 0 || T <= 0 || ld < T || L <= 0 || N < 0)
+        return fail(ECOG_E_VALUE, "ecog_epoch_gather: bad shape");
+    for (int64_t n = 0; n < N; ++n) {
+        if (h_start[n] < 0)
+            return fail(ECOG_E_VALUE, "Epoch %lld starts before the recording (start index %lld).",
+                        (long long)n, (long long)h_start[n]);
+        if (h_start[n] + L > T)
+            return fail(ECOG_E_VALUE,
+                        "Requested sample length exceeds data length. Start: %lld, End: %lld; Data length: %lld.",
+                        (long long)h_start[n], (long long)(h_start[n] + L), (long long)T);
+    }
+    if (N == 0) return ECOG_OK;
+    const int wpe = elem_bytes / 4;
+    const int64_t Lw = L * wpe;
+    const bool vec_store = aligned16(d_out) && (Lw % 4 == 0);
+    int64_t blocks = ceil_div(N * C, kGatherWarps);
+    if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
+    epoch_gather_kernel<<<(unsigned)blocks, kGatherWarps * 32, 0, (cudaStream_t)stream>>>(
+        (const uint32_t*)d_src, (uint32_t*)d_out, C, ld * wpe, d_start, N, Lw, wpe, vec_store);
+    ECOG_TRY(check_launch("epoch_gather"));
+    return ECOG_OK;
+}

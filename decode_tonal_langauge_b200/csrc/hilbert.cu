@@ -1,0 +1,234 @@
+// K4 Gaussian filter-bank analytic envelope ("hilbert" method), block-wise.
+//
+// The reference takes one FFT of the whole record, multiplies by nb Gaussian x
+// analytic-mask kernels and inverse-transforms each (frequency_filter.py:154-184).
+// Every band kernel is a Gaussian in time with sigma_t <= a few tens of ms, so the
+// circular convolution is reproduced exactly (to < 1e-9) by overlap-save on 4096-sample
+// blocks with a `halo` of >= 6.5 sigma_t on each side, wrapped circularly at the
+// record ends.  One CTA (256 threads) processes TWO consecutive blocks of one channel:
+//   - the two real blocks ride as real/imag parts of ONE forward complex FFT and are
+//     separated with the conjugate-symmetry split;
+//   - per band and block: multiply by the gain table, inverse FFT (as conj-forward),
+//     |.| (or real part) accumulated in registers -> mean over bands never leaves the SM.
+// FFT: 4096 = 16 x 16 x 16, each thread holds 16 points in registers, three radix-16
+// passes with two shared-memory exchanges (padded index i + i/16, conflict free).
+// The kernel is FP32-ALU/shared-memory bound (~9 FFTs per 4096 samples), NOT HBM bound:
+// algorithmic traffic is 8 B per sample (read x once + halo, write y once).
+#include "common.cuh"
+
+namespace ecog {
+
+constexpr int kN = ECOG_HILBERT_N;      // 4096
+constexpr int kHT = 256;                // threads
+constexpr int kHalf = kN / 2;
+
+__device__ __forceinline__ int padi(int i) { return i + (i >> 4); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward-DFT quarter turn)
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+// forward 4-point DFT in place: (a0,a1,a2,a3) -> X[0..3]
+__device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mi(csub(a1, a3));
+    a0 = cadd(t0, t2); a2 = csub(t0, t2); a1 = cadd(t1, t3); a3 = csub(t1, t3);
+}
+
+// forward 16-point DFT in place, natural order in and out
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+    const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
+    // stage 1: for each m, DFT4 over q of v[m + 4q]  -> a[m][p] kept at v[m + 4p]
+#pragma unroll
+    for (int m = 0; m < 4; ++m) dft4(v[m], v[m + 4], v[m + 8], v[m + 12]);
+    // twiddle W16^(m p), element (m, p) lives at v[m + 4p]
+    v[1 + 4] = cmul(v[1 + 4], make_float2(C1, -S1));        // m=1,p=1 : W^1
+    v[1 + 8] = cmul(v[1 + 8], make_float2(C2, -C2));        // m=1,p=2 : W^2
+    v[1 + 12] = cmul(v[1 + 12], make_float2(S1, -C1));      // m=1,p=3 : W^3
+    v[2 + 4] = cmul(v[2 + 4], make_float2(C2, -C2));        // m=2,p=1 : W^2
+    v[2 + 8] = mul_mi(v[2 + 8]);                            // m=2,p=2 : W^4 = -i
+    v[2 + 12] = cmul(v[2 + 12], make_float2(-C2, -C2));     // m=2,p=3 : W^6
+    v[3 + 4] = cmul(v[3 + 4], make_float2(S1, -C1));        // m=3,p=1 : W^3
+    v[3 + 8] = cmul(v[3 + 8], make_float2(-C2, -C2));       // m=3,p=2 : W^6
+    v[3 + 12] = cmul(v[3 + 12], make_float2(-C1, S1));      // m=3,p=3 : W^9
+    // stage 2: for each p, DFT4 over m of v[m + 4p] -> X[p + 4r] at v[4p + r]
+#pragma unroll
+    for (int p = 0; p < 4; ++p) dft4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
+    // now v[4p + r] = X[p + 4r]; transpose the 4x4 index to natural order
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int r = p + 1; r < 4; ++r) { float2 t = v[4 * p + r]; v[4 * p + r] = v[4 * r + p]; v[4 * r + p] = t; }
+}
+
+// passes 2 and 3 of the 4096-point forward FFT; pass-1 output must already be in `buf`
+// (index padi(256 k0 + tid)).  Result: v[k2] = X[k0 + 16 k1 + 256 k2] with tid = 16 k0 + k1.
+__device__ __forceinline__ void fft4096_finish(float2 (&v)[16], float2* buf, const float2* __restrict__ tw2, int tid) {
+    __syncthreads();
+    const int k0 = tid >> 4, n0 = tid & 15;
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) v[n1] = buf[padi(256 * k0 + 16 * n1 + n0)];
+    dft16(v);
+#pragma unroll
+    for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], __ldg(&tw2[k1 * kHT + tid]));
+    v[0] = cmul(v[0], __ldg(&tw2[tid]));
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) buf[padi(256 * k0 + 16 * k1 + n0)] = v[k1];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = buf[padi(16 * tid + j)];
+    dft16(v);
+}
+
+// pass 1: v[n2] = x[256 n2 + tid] -> twiddled A[k0] stored at padi(256 k0 + tid)
+__device__ __forceinline__ void fft4096_pass1(float2 (&v)[16], float2* buf, const float2* __restrict__ tw1, int tid) {
+    dft16(v);
+#pragma unroll
+    for (int k0 = 1; k0 < 16; ++k0) v[k0] = cmul(v[k0], __ldg(&tw1[k0 * kHT + tid]));
+#pragma unroll
+    for (int k0 = 0; k0 < 16; ++k0) buf[padi(256 * k0 + tid)] = v[k0];
+}
+
+__global__ void __launch_bounds__(kHT, 2)
+hilbert_env_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t ldx, int64_t ldy,
+                   const float* __restrict__ gain, int nb, int halo, int envelope,
+                   const float2* __restrict__ tw, int64_t nBlocks) {
+    extern __shared__ __align__(16) float2 hsm[];
+    float2* bufA = hsm;                       // [4096 + 256]
+    float2* bufB = hsm + (kN + kN / 16);      // [4096 + 256]
+    const int tid = threadIdx.x;
+    const int64_t ch = blockIdx.y;
+    const int U = kN - 2 * halo;
+    const int64_t b0 = 2 * (int64_t)blockIdx.x, b1 = b0 + 1;
+    const float* xr = x + ch * ldx;
+    const float2* tw1 = tw;                 // [16][256] : W_256^{(tid>>4) k0}
+    const float2* tw2 = tw + 16 * kHT;      // [16][256] : W_4096^{(tid&15)((tid>>4) + 16 k1)}
+
+    float2 v[16];
+    {   // two real blocks as one complex signal, circular halo
+        int64_t s0 = (b0 * U - halo) % T; if (s0 < 0) s0 += T;
+        int64_t s1 = (b1 * U - halo) % T; if (s1 < 0) s1 += T;
+        const bool has1 = b1 < nBlocks;
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) {
+            const int i = 256 * n2 + tid;
+            v[n2].x = xr[(s0 + i) % T];
+            v[n2].y = has1 ? xr[(s1 + i) % T] : 0.f;
+        }
+    }
+    fft4096_pass1(v, bufA, tw1, tid);
+    fft4096_finish(v, bufA, tw2, tid);
+    {   // natural-order spectrum Z[k] -> bufB
+        const int k0 = tid >> 4, k1 = tid & 15;
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) bufB[padi(k0 + 16 * k1 + 256 * k2)] = v[k2];
+    }
+    __syncthreads();
+    // conjugate-symmetry split (factor 1/2 folded into the gain table):
+    //   block0: S0[k] = Z[k] + conj(Z[N-k]),  block1: S1[k] = -i (Z[k] - conj(Z[N-k]))
+    // stored CONJUGATED (the inverse transforms run as conj-forward FFTs)
+#pragma unroll
+    for (int j = 0; j < kHalf / kHT; ++j) {
+        const int k = tid + kHT * j;
+        float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);
+        if (k > 0) {
+            const float2 zk = bufB[padi(k)], zm = bufB[padi(kN - k)];
+            const float2 a = make_float2(zk.x + zm.x, zk.y - zm.y);     // Z[k] + conj(Z[N-k])
+            const float2 d = make_float2(zk.x - zm.x, zk.y + zm.y);     // Z[k] - conj(Z[N-k])
+            s0 = make_float2(a.x, -a.y);                                 // conj(a)
+            s1 = make_float2(d.y, d.x);                                  // conj(-i d) = conj((d.y, -d.x))
+        }
+        bufA[padi(k)] = s0;
+        bufA[padi(kHalf + k)] = s1;
+    }
+    __syncthreads();
+
+    float acc0[16], acc1[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
+
+    for (int band = 0; band < nb; ++band) {
+        const float* g = gain + (size_t)band * kHalf;
+#pragma unroll
+        for (int sel = 0; sel < 2; ++sel) {
+            // analytic spectrum: bins >= N/2 are zero
+#pragma unroll
+            for (int n2 = 0; n2 < 8; ++n2) {
+                const int k = 256 * n2 + tid;
+                const float gk = __ldg(&g[k]);
+                const float2 sv = bufA[padi(sel * kHalf + k)];
+                v[n2] = make_float2(sv.x * gk, sv.y * gk);
+            }
+#pragma unroll
+            for (int n2 = 8; n2 < 16; ++n2) v[n2] = make_float2(0.f, 0.f);
+            __syncthreads();                       // previous transform's pass-3 reads of bufB are done
+            fft4096_pass1(v, bufB, tw1, tid);
+            fft4096_finish(v, bufB, tw2, tid);
+            // v[k2] = conj(z[t]), t = k0 + 16 k1 + 256 k2
+            if (sel == 0) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc0[j] += envelope ? sqrtf(fmaf(v[j].x, v[j].x, v[j].y * v[j].y)) : v[j].x;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc1[j] += envelope ? sqrtf(fmaf(v[j].x, v[j].x, v[j].y * v[j].y)) : v[j].x;
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const int k0 = tid >> 4, k1 = tid & 15;
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) bufB[padi(k0 + 16 * k1 + 256 * k2)] = make_float2(acc0[k2], acc1[k2]);
+    }
+    __syncthreads();
+    float* yr = y + ch * ldy;
+    for (int i = tid; i < U; i += kHT) {
+        const float2 r = bufB[padi(halo + i)];
+        const int64_t t0 = b0 * U + i, t1 = b1 * U + i;
+        if (t0 < T) yr[t0] = r.x;
+        if (b1 < nBlocks && t1 < T) yr[t1] = r.y;
+    }
+}
+
+}  // namespace ecog
+
+using namespace ecog;
+
+extern "C" size_t ecog_hilbert_twiddle_floats(void) { return (size_t)2 * 16 * kHT * 2; }
+
+extern "C" int ecog_hilbert_twiddles(float* h_out) {
+    if (!h_out) return fail(ECOG_E_VALUE, "ecog_hilbert_twiddles: null output");
+    const double PI = 3.14159265358979323846;
+    for (int e = 0; e < 16; ++e)
+        for (int tid = 0; tid < kHT; ++tid) {
+            // pass 1: W_256^{n1 k0}, n1 = tid >> 4, k0 = e
+            double a1 = -2.0 * PI * (double)((tid >> 4) * e) / 256.0;
+            h_out[2 * (e * kHT + tid) + 0] = (float)cos(a1);
+            h_out[2 * (e * kHT + tid) + 1] = (float)sin(a1);
+            // pass 2: W_4096^{n0 (k0 + 16 k1)}, k0 = tid >> 4, n0 = tid & 15, k1 = e
+            double a2 = -2.0 * PI * (double)((tid & 15) * ((tid >> 4) + 16 * e)) / 4096.0;
+            h_out[2 * (16 * kHT + e * kHT + tid) + 0] = (float)cos(a2);
+            h_out[2 * (16 * kHT + e * kHT + tid) + 1] = (float)sin(a2);
+        }
+    return ECOG_OK;
+}
+
+extern "C" int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                                const float* d_gain, int32_t nbands, int32_t halo, int32_t envelope,
+                                const float* d_twiddle, ecog_stream_t stream) {
+    if (C <= 0 || T <= 0 || ldx < T || ldy < T || C > 65535) return fail(ECOG_E_VALUE, "ecog_hilbert_env: bad shape");
+    if (nbands < 1) return fail(ECOG_E_VALUE, "ecog_hilbert_env: no bands");
+    if (halo < 0 || 2 * halo >= kN / 2)
+        return fail(ECOG_E_UNSUPPORTED, "ecog_hilbert_env: halo %d does not fit a %d-sample block", halo, kN);
+    if (d_x == d_y) return fail(ECOG_E_VALUE, "ecog_hilbert_env: in-place operation is not supported");
+    const int U = kN - 2 * halo;
+    const int64_t nBlocks = ceil_div(T, U);
+    dim3 grid((unsigned)ceil_div(nBlocks, 2), (unsigned)C);
+    const size_t smem = (size_t)2 * (kN + kN / 16) * sizeof(float2);
+    ECOG_CUDA(cudaFuncSetAttribute(hilbert_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hilbert_env_kernel<<<grid, kHT, smem, (cudaStream_t)stream>>>(
+        d_x, d_y, T, ldx, ldy, d_gain, nbands, halo, envelope, reinterpret_cast<const float2*>(d_twiddle), nBlocks);
+    return check_launch("hilbert_env");
+}

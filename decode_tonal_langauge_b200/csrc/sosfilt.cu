@@ -1,0 +1,387 @@
+// K3 IIR biquad cascade: zero-phase (filtfilt, odd padding) and causal (sosfilt).
+//
+// Block-parallel linear recurrence.  A row of T samples is cut into chunks of L
+// samples; one thread owns one chunk and runs the float64 DF2T cascade over it.
+//   1. tail  : every full chunk is run from a ZERO state over its last `tail` samples
+//              (the part of the zero-state response that still reaches the chunk end
+//              in float64); the end state g_k is the affine term of the chunk map.
+//   2. scan  : per row, S_{k+1} = A^L S_k + g_k carries the true state across chunks
+//              (A^L is built by the host); S_0 comes from the filtfilt start-up:
+//              zi * ext[0] pushed through the odd-extension pad.
+//   3. main  : every chunk is re-run from its true start state and writes float32.
+// The backward sweep repeats 1-3 on the forward result, in place, time reversed.
+//
+// Data movement: 512 chunks per CTA; 16-sample time tiles of all 512 chunks are
+// staged through shared memory with a 3-deep cp.async ring (64 B per chunk per
+// stage, coalesced), each thread reads its own tile row with conflict-free 128-bit
+// shared loads (row pitch 20 words), results go back through a shared tile and are
+// stored with 128-bit coalesced writes.  Arithmetic is FP64-pipe bound
+// (5 DFMA per biquad per sample + 2 conversions), see DESIGN.md.
+#include "common.cuh"
+
+namespace ecog {
+
+constexpr int kSosThreads = 512;
+constexpr int kSub = 16;              // samples per stage per chunk
+constexpr int kPitch = kSub + 4;      // shared row pitch in floats (conflict-free LDS.128)
+constexpr int kRing = 3;
+
+struct SosCoef {
+    double c[ECOG_MAX_SECTIONS][5];   // b0 b1 b2 a1 a2
+    double zi[ECOG_MAX_SECTIONS][2];
+};
+struct SosMatrix { double m[2 * ECOG_MAX_SECTIONS][2 * ECOG_MAX_SECTIONS]; };
+
+template <int NSEC>
+__device__ __forceinline__ double sos_step(double u, const double (&c)[NSEC][5], double (&s)[NSEC][2]) {
+#pragma unroll
+    for (int j = 0; j < NSEC; ++j) {
+        const double y = fma(c[j][0], u, s[j][0]);
+        s[j][0] = fma(-c[j][3], y, fma(c[j][1], u, s[j][1]));
+        s[j][1] = fma(-c[j][4], y, c[j][2] * u);
+        u = y;
+    }
+    return u;
+}
+
+// WRITE=false: tail pass (zero state, last `tail` samples, end state -> slot k+1)
+// WRITE=true : main pass (state from slot k, float32 output)
+template <int NSEC, bool REV, bool WRITE, bool VEC>
+__global__ void __launch_bounds__(kSosThreads, 1)
+sos_chunk_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, int64_t T,
+                 int64_t ldx, int64_t ldy, int L, int tail, int nChunks, int padlen,
+                 SosCoef coef, double* __restrict__ state, double* __restrict__ padbuf) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* in_tile = reinterpret_cast<float*>(smem_raw);                       // [kRing][512][kPitch]
+    float* out_tile = in_tile + (size_t)kRing * kSosThreads * kPitch;          // [512][kPitch]
+    int64_t* gbase = reinterpret_cast<int64_t*>(out_tile + (size_t)kSosThreads * kPitch);  // [512] row*ld
+    int* cstart = reinterpret_cast<int*>(gbase + kSosThreads);                 // [512] chunk edge (a or b) - may exceed int? no: < 2^31 checked on host
+    int* clen = cstart + kSosThreads;                                          // [512]
+
+    const int tid = threadIdx.x;
+    const int64_t q = (int64_t)blockIdx.x * kSosThreads + tid;
+    const int64_t items = C * nChunks;
+    const bool valid = q < items;
+    const int64_t row = valid ? q / nChunks : 0;
+    const int k = valid ? (int)(q - row * nChunks) : 0;
+    int64_t a, b;
+    if (!REV) { a = (int64_t)k * L; b = a + L < T ? a + L : T; }
+    else      { b = T - (int64_t)k * L; a = b - L > 0 ? b - L : 0; }
+    const bool need = valid && (WRITE || k < nChunks - 1);
+    gbase[tid] = row;
+    cstart[tid] = (int)(REV ? b : a);
+    clen[tid] = need ? (int)(b - a) : 0;
+    __syncthreads();
+
+    double c[NSEC][5], s[NSEC][2];
+#pragma unroll
+    for (int j = 0; j < NSEC; ++j) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) c[j][i] = coef.c[j][i];
+        s[j][0] = 0.0; s[j][1] = 0.0;
+    }
+    if (WRITE && valid) {
+        const double* sp = state + q * (2 * NSEC);
+#pragma unroll
+        for (int j = 0; j < NSEC; ++j) { s[j][0] = sp[2 * j]; s[j][1] = sp[2 * j + 1]; }
+    }
+
+    const int nStages = L / kSub;
+    const int first = WRITE ? 0 : (L - tail) / kSub;
+    const float* src = WRITE && REV ? y : x;          // backward main pass runs in place on y
+    const int64_t lds = WRITE && REV ? ldy : ldx;
+
+    // cooperative stage loader: VEC -> 4 pieces of 16 B per row, else 16 pieces of 4 B
+    auto issue = [&](int stage) {
+        if (stage < nStages) {
+            float* dst = in_tile + (size_t)(stage % kRing) * kSosThreads * kPitch;
+            if (VEC) {
+                for (int i = tid; i < kSosThreads * 4; i += kSosThreads) {
+                    const int r = i >> 2, p = i & 3;
+                    const int len = clen[r];
+                    int64_t off; bool ok;
+                    if (!REV) { int e = stage * kSub + 4 * p; ok = e < len; off = (int64_t)cstart[r] + e; }
+                    else { int e = (stage + 1) * kSub - 4 * p; ok = e <= len; off = (int64_t)cstart[r] - e; }
+                    const float* g = src + gbase[r] * lds + (ok ? off : 0);
+                    cp_async16_zfill(dst + r * kPitch + 4 * p, g, ok);
+                }
+            } else {
+                for (int i = tid; i < kSosThreads * kSub; i += kSosThreads) {
+                    const int r = i / kSub, p = i - r * kSub;
+                    const int len = clen[r];
+                    int64_t off; bool ok;
+                    if (!REV) { int e = stage * kSub + p; ok = e < len; off = (int64_t)cstart[r] + e; }
+                    else { int e = (stage + 1) * kSub - p; ok = e <= len; off = (int64_t)cstart[r] - e; }
+                    const float* g = src + gbase[r] * lds + (ok ? off : 0);
+                    cp_async4_zfill(dst + r * kPitch + p, g, ok);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    for (int st = first; st < first + kRing; ++st) issue(st);
+
+    const int mylen = clen[tid];
+    for (int st = first; st < nStages; ++st) {
+        cp_async_wait<kRing - 1>();
+        __syncthreads();
+        const float* mine = in_tile + (size_t)(st % kRing) * kSosThreads * kPitch + tid * kPitch;
+        float* outp = out_tile + tid * kPitch;
+#pragma unroll
+        for (int v = 0; v < kSub / 4; ++v) {
+            float4 xv, yv;
+            const int base = st * kSub + 4 * v;        // logical sample index within the chunk
+            if (!REV) {
+                xv = *reinterpret_cast<const float4*>(mine + 4 * v);
+            } else {
+                float4 t4 = *reinterpret_cast<const float4*>(mine + (kSub - 4 - 4 * v));
+                xv = make_float4(t4.w, t4.z, t4.y, t4.x);
+            }
+            if (base + 4 <= mylen) {
+                yv.x = (float)sos_step<NSEC>((double)xv.x, c, s);
+                yv.y = (float)sos_step<NSEC>((double)xv.y, c, s);
+                yv.z = (float)sos_step<NSEC>((double)xv.z, c, s);
+                yv.w = (float)sos_step<NSEC>((double)xv.w, c, s);
+            } else {   // ragged chunk end: samples past it are zero filled; freeze the state there
+                yv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (base + 0 < mylen) yv.x = (float)sos_step<NSEC>((double)xv.x, c, s);
+                if (base + 1 < mylen) yv.y = (float)sos_step<NSEC>((double)xv.y, c, s);
+                if (base + 2 < mylen) yv.z = (float)sos_step<NSEC>((double)xv.z, c, s);
+            }
+            if (WRITE) {
+                if (!REV) *reinterpret_cast<float4*>(outp + 4 * v) = yv;
+                else *reinterpret_cast<float4*>(outp + (kSub - 4 - 4 * v)) = make_float4(yv.w, yv.z, yv.y, yv.x);
+            }
+        }
+        __syncthreads();
+        if (WRITE) {
+            if (VEC) {
+                for (int i = tid; i < kSosThreads * 4; i += kSosThreads) {
+                    const int r = i >> 2, p = i & 3;
+                    const int len = clen[r];
+                    int64_t off; bool ok;
+                    if (!REV) { int e = st * kSub + 4 * p; ok = e < len; off = (int64_t)cstart[r] + e; }
+                    else { int e = (st + 1) * kSub - 4 * p; ok = e <= len; off = (int64_t)cstart[r] - e; }
+                    if (ok) {
+                        float4 v4 = *reinterpret_cast<const float4*>(out_tile + r * kPitch + 4 * p);
+                        *reinterpret_cast<float4*>(y + gbase[r] * ldy + off) = v4;
+                    }
+                }
+            } else {
+                for (int i = tid; i < kSosThreads * kSub; i += kSosThreads) {
+                    const int r = i / kSub, p = i - r * kSub;
+                    const int len = clen[r];
+                    int64_t off; bool ok;
+                    if (!REV) { int e = st * kSub + p; ok = e < len; off = (int64_t)cstart[r] + e; }
+                    else { int e = (st + 1) * kSub - p; ok = e <= len; off = (int64_t)cstart[r] - e; }
+                    if (ok) y[gbase[r] * ldy + off] = out_tile[r * kPitch + p];
+                }
+            }
+        }
+        issue(st + kRing);
+    }
+    cp_async_wait<0>();
+
+    if (!WRITE) {
+        if (need) {   // end state of chunk k is the affine term of slot k+1
+            double* sp = state + (q + 1) * (2 * NSEC);
+#pragma unroll
+            for (int j = 0; j < NSEC; ++j) { sp[2 * j] = s[j][0]; sp[2 * j + 1] = s[j][1]; }
+        }
+        return;
+    }
+    // forward main pass: the thread that owns a row's last chunk runs on through the right
+    // odd-extension pad ext[T+i] = 2 x[T-1] - x[T-2-i] (float32, like scipy's odd_ext) and keeps
+    // the filtered pad in float64 for the backward start-up.
+    if (!REV && padlen > 0 && valid && k == nChunks - 1) {
+        const float* xr = x + row * ldx;
+        const float xe = xr[T - 1];
+        double* pb = padbuf + row * padlen;
+        for (int i = 0; i < padlen; ++i) {
+            const float e = 2.0f * xe - xr[T - 2 - i];
+            pb[i] = sos_step<NSEC>((double)e, c, s);
+        }
+    }
+}
+
+// one thread per row: start-up state, then the sequential carry over chunks
+template <int NSEC, bool REV>
+__global__ void sos_scan_kernel(const float* __restrict__ x, int64_t C, int64_t T, int64_t ldx,
+                                int nChunks, int padlen, int zero_phase, SosCoef coef, SosMatrix M,
+                                double* __restrict__ state, const double* __restrict__ padbuf) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= C) return;
+    constexpr int NS = 2 * NSEC;
+    double c[NSEC][5], s[NSEC][2];
+#pragma unroll
+    for (int j = 0; j < NSEC; ++j) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) c[j][i] = coef.c[j][i];
+        s[j][0] = 0.0; s[j][1] = 0.0;
+    }
+    if (zero_phase) {
+        if (!REV) {
+            const float* xr = x + row * ldx;
+            const float x0 = xr[0];
+            const float e0 = 2.0f * x0 - xr[padlen];
+#pragma unroll
+            for (int j = 0; j < NSEC; ++j) { s[j][0] = coef.zi[j][0] * (double)e0; s[j][1] = coef.zi[j][1] * (double)e0; }
+            for (int i = 0; i < padlen; ++i) {
+                const float e = 2.0f * x0 - xr[padlen - i];
+                (void)sos_step<NSEC>((double)e, c, s);
+            }
+        } else {
+            const double* pb = padbuf + row * padlen;
+            const double y0 = pb[padlen - 1];
+#pragma unroll
+            for (int j = 0; j < NSEC; ++j) { s[j][0] = coef.zi[j][0] * y0; s[j][1] = coef.zi[j][1] * y0; }
+            for (int i = padlen - 1; i >= 0; --i) (void)sos_step<NSEC>(pb[i], c, s);
+        }
+    }
+    double v[NS];
+#pragma unroll
+    for (int j = 0; j < NSEC; ++j) { v[2 * j] = s[j][0]; v[2 * j + 1] = s[j][1]; }
+    double* sp = state + row * nChunks * NS;
+    for (int k = 0; k < nChunks; ++k) {
+        double g[NS];
+        if (k + 1 < nChunks) {
+#pragma unroll
+            for (int i = 0; i < NS; ++i) g[i] = sp[(int64_t)(k + 1) * NS + i];
+        }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) sp[(int64_t)k * NS + i] = v[i];
+        if (k + 1 < nChunks) {
+            double nv[NS];
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                double acc = g[i];
+#pragma unroll
+                for (int j = 0; j < NS; ++j) acc = fma(M.m[i][j], v[j], acc);
+                nv[i] = acc;
+            }
+#pragma unroll
+            for (int i = 0; i < NS; ++i) v[i] = nv[i];
+        }
+    }
+}
+
+static size_t sos_smem_bytes() {
+    return ((size_t)(kRing + 1) * kSosThreads * kPitch) * sizeof(float) +
+           (size_t)kSosThreads * (sizeof(int64_t) + 2 * sizeof(int));
+}
+
+template <int NSEC, bool REV, bool WRITE>
+static int launch_chunk(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                        const ecog_sos_plan& p, int nChunks, const SosCoef& coef, double* state,
+                        double* padbuf, bool vec, cudaStream_t st) {
+    const size_t smem = sos_smem_bytes();
+    const unsigned grid = (unsigned)ceil_div(C * nChunks, kSosThreads);
+    if (vec) {
+        auto k = sos_chunk_kernel<NSEC, REV, WRITE, true>;
+        ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kSosThreads, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, coef, state, padbuf);
+    } else {
+        auto k = sos_chunk_kernel<NSEC, REV, WRITE, false>;
+        ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kSosThreads, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, coef, state, padbuf);
+    }
+    return check_launch(WRITE ? "sos_main" : "sos_tail");
+}
+
+template <int NSEC>
+static int run_sos(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                   const ecog_sos_plan& p, const SosCoef& coef, const SosMatrix& M, double* state,
+                   double* padbuf, cudaStream_t st) {
+    const int nChunks = (int)ceil_div(T, p.chunk);
+    const bool vec = aligned16(x) && aligned16(y) && T % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0;
+    const unsigned sgrid = (unsigned)ceil_div(C, 64);
+    // forward sweep: x -> y
+    if (nChunks > 1) ECOG_TRY((launch_chunk<NSEC, false, false>(x, y, C, T, ldx, ldy, p, nChunks, coef, state, padbuf, vec, st)));
+    sos_scan_kernel<NSEC, false><<<sgrid, 64, 0, st>>>(x, C, T, ldx, nChunks, p.padlen, p.zero_phase, coef, M, state, padbuf);
+    ECOG_TRY(check_launch("sos_scan"));
+    ECOG_TRY((launch_chunk<NSEC, false, true>(x, y, C, T, ldx, ldy, p, nChunks, coef, state, padbuf, vec, st)));
+    if (!p.zero_phase) return ECOG_OK;
+    // backward sweep: y -> y in place, time reversed
+    if (nChunks > 1) ECOG_TRY((launch_chunk<NSEC, true, false>(y, y, C, T, ldy, ldy, p, nChunks, coef, state, padbuf, vec, st)));
+    sos_scan_kernel<NSEC, true><<<sgrid, 64, 0, st>>>(y, C, T, ldy, nChunks, p.padlen, p.zero_phase, coef, M, state, padbuf);
+    ECOG_TRY(check_launch("sos_scan"));
+    return launch_chunk<NSEC, true, true>(y, y, C, T, ldy, ldy, p, nChunks, coef, state, padbuf, vec, st);
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace ecog
+
+using namespace ecog;
+
+extern "C" size_t ecog_sos_workspace(const ecog_sos_plan* plan, int64_t C, int64_t T) {
+    if (!plan || plan->chunk <= 0) return 0;
+    const int64_t nChunks = ceil_div(T, plan->chunk);
+    const int nsec_pad = plan->nsec <= 4 ? (plan->nsec == 3 ? 3 : (plan->nsec <= 2 ? plan->nsec : 4))
+                                         : (plan->nsec <= 6 ? 6 : 8);
+    size_t states = align_up((size_t)C * nChunks * 2 * nsec_pad * sizeof(double), 256);
+    size_t pad = align_up((size_t)C * (plan->padlen > 0 ? plan->padlen : 1) * sizeof(double), 256);
+    return states + pad;
+}
+
+extern "C" int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                            const ecog_sos_plan* plan, const double* h_sos, const double* h_zi,
+                            const double* h_M, void* d_workspace, size_t workspace_bytes,
+                            ecog_stream_t stream) {
+    if (!plan || !h_sos) return fail(ECOG_E_VALUE, "ecog_sosfilt: null plan");
+    const ecog_sos_plan& p = *plan;
+    if (C <= 0 || T <= 0 || ldx < T || ldy < T || T >= (int64_t)1 << 31)
+        return fail(ECOG_E_VALUE, "ecog_sosfilt: bad shape C=%lld T=%lld", (long long)C, (long long)T);
+    if (p.nsec < 1 || p.nsec > ECOG_MAX_SECTIONS) return fail(ECOG_E_VALUE, "ecog_sosfilt: nsec=%d out of range", p.nsec);
+    if (p.chunk < kSub || p.chunk % kSub || p.tail < kSub || p.tail % kSub || p.tail > p.chunk)
+        return fail(ECOG_E_VALUE, "ecog_sosfilt: chunk=%d tail=%d must be multiples of %d with tail<=chunk", p.chunk, p.tail, kSub);
+    if (p.zero_phase) {
+        if (!h_zi) return fail(ECOG_E_VALUE, "ecog_sosfilt: zero_phase needs h_zi");
+        if (p.padlen < 1) return fail(ECOG_E_VALUE, "ecog_sosfilt: zero_phase needs padlen >= 1");
+        if (T <= p.padlen)
+            return fail(ECOG_E_VALUE, "The length of the input vector x must be greater than padlen, which is %d.", p.padlen);
+    }
+    const int nChunks = (int)ceil_div(T, p.chunk);
+    if (nChunks > 1 && !h_M) return fail(ECOG_E_VALUE, "ecog_sosfilt: chunked rows need the chunk transition matrix h_M");
+    if (workspace_bytes < ecog_sos_workspace(plan, C, T))
+        return fail(ECOG_E_WORKSPACE, "ecog_sosfilt: workspace %zu < %zu", workspace_bytes, ecog_sos_workspace(plan, C, T));
+
+    // pad the cascade with identity sections up to an instantiated width
+    const int widths[] = {1, 2, 3, 4, 6, 8};
+    int ns = 8;
+    for (int w : widths) if (p.nsec <= w) { ns = w; break; }
+    SosCoef coef;
+    SosMatrix M;
+    memset(&coef, 0, sizeof(coef));
+    memset(&M, 0, sizeof(M));
+    for (int j = 0; j < ns; ++j) {
+        if (j < p.nsec) {
+            const double* r = h_sos + 6 * j;
+            if (r[3] == 0.0) return fail(ECOG_E_VALUE, "ecog_sosfilt: a0 of section %d is zero", j);
+            const double a0 = r[3];
+            coef.c[j][0] = r[0] / a0; coef.c[j][1] = r[1] / a0; coef.c[j][2] = r[2] / a0;
+            coef.c[j][3] = r[4] / a0; coef.c[j][4] = r[5] / a0;
+            if (h_zi) { coef.zi[j][0] = h_zi[2 * j]; coef.zi[j][1] = h_zi[2 * j + 1]; }
+        } else {
+            coef.c[j][0] = 1.0;   // identity section: y = u, state stays zero
+        }
+    }
+    if (h_M) {
+        const int n0 = 2 * p.nsec;
+        for (int i = 0; i < n0; ++i)
+            for (int j = 0; j < n0; ++j) M.m[i][j] = h_M[i * n0 + j];
+    }
+    const size_t states = align_up((size_t)C * nChunks * 2 * ns * sizeof(double), 256);
+    double* state = (double*)d_workspace;
+    double* padbuf = (double*)((char*)d_workspace + states);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (ns) {
+        case 1: return run_sos<1>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, padbuf, st);
+        case 2: return run_sos<2>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, padbuf, st);
+        case 3: return run_sos<3>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, padbuf, st);
+        case 4: return run_sos<4>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, padbuf, st);
+        case 6: return run_sos<6>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, padbuf, st);
+        default: return run_sos<8>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, padbuf, st);
+    }
+}

@@ -1,0 +1,167 @@
+"""Host-side plans and tables for the whole-row FFT resampler (K5) and the block
+Hilbert kernel (K4).  Float64 everywhere, rounded to float32 once.
+
+Resample of a real row of T samples to ``num`` samples (ref: preprocess/signal/downsample.py:21-27,
+scipy.signal.resample): the device computes
+
+  forward : z[j] = x[2j] + i x[2j+1] (N = T/2 complex points), Z = FFT_N(z) as a
+            four-step transform N = n_a * n_b: column pass (length n_a, stride n_b,
+            times W_N^{q c}) stored transposed, then a second column pass (length n_b);
+  repack  : rfft bins X[k] from Z[k], Z[N-k]; truncate / scale / Nyquist rule; fold
+            the half spectrum into G[k] (N' = num/2 complex points);
+  inverse : g = IFFT_{N'}(G) run as a conjugated forward four-step transform;
+            y[2j] = Re g[j], y[2j+1] = Im g[j].
+"""
+from __future__ import annotations
+
+import functools
+from dataclasses import dataclass
+from typing import List, Tuple
+
+import numpy as np
+
+MAX_AXIS = 2800          # longest in-shared-memory FFT: n * (8 + 1) * 8 B <= ~200 KB
+TILE_W = 8
+BIG_SPLIT = 4096         # two-level table for the four-step twiddles W_N^e, e = hi*4096 + lo
+
+
+def factorize(n: int) -> List[int]:
+    """Radix sequence over {4, 2, 3, 5}; raises for other prime factors."""
+    radices = []
+    m = n
+    while m % 4 == 0:
+        radices.append(4)
+        m //= 4
+    for r in (2, 3, 5):
+        while m % r == 0:
+            radices.append(r)
+            m //= r
+    if m != 1:
+        raise NotImplementedError(
+            f"FFT length {n} has a prime factor other than 2, 3, 5 (left {m}); "
+            "non-smooth lengths need Bluestein (SURVEY.md section 8f row f3)")
+    return radices
+
+
+def digit_reversal(n: int, radices: List[int]) -> np.ndarray:
+    """perm[i] = shared-memory row where input sample i must be placed so that the
+    in-place decimation-in-time stages (radices[0] first) leave natural order."""
+    def rec(idx: np.ndarray, length: int, rs: List[int]) -> np.ndarray:
+        if not rs:
+            return np.zeros_like(idx)
+        r = rs[-1]
+        return (idx % r) * (length // r) + rec(idx // r, length // r, rs[:-1])
+    return rec(np.arange(n, dtype=np.int64), n, list(radices)).astype(np.int32)
+
+
+def roots(n: int, sign: float = -1.0) -> np.ndarray:
+    """(n, 2) float32 table of W_n^k = exp(sign * 2 pi i k / n)."""
+    k = np.arange(n, dtype=np.float64)
+    ang = sign * 2.0 * np.pi * k / n
+    return np.stack([np.cos(ang), np.sin(ang)], axis=1).astype(np.float32)
+
+
+def split_size(N: int) -> Tuple[int, int]:
+    """N = n_a * n_b with both factors 2-3-5 smooth, <= MAX_AXIS, n_b a multiple of TILE_W
+    where possible and the pair as balanced as possible.  (n_a, 1) for short rows."""
+    factorize(N)
+    if N <= MAX_AXIS:
+        return N, 1
+    best = None
+    for na in range(2, MAX_AXIS + 1):
+        if N % na:
+            continue
+        nb = N // na
+        if nb > MAX_AXIS:
+            continue
+        score = (0 if nb % TILE_W == 0 else 1, 0 if na % TILE_W == 0 else 1, abs(na - nb))
+        if best is None or score < best[0]:
+            best = (score, na, nb)
+    if best is None:
+        raise NotImplementedError(f"FFT length {N} does not split into two factors <= {MAX_AXIS}")
+    return best[1], best[2]
+
+
+@dataclass(frozen=True)
+class AxisPlan:
+    n: int
+    radices: Tuple[int, ...]
+    perm: np.ndarray        # int32 (n,)
+    tw: np.ndarray          # float32 (n, 2)
+
+
+def axis_plan(n: int) -> AxisPlan:
+    rs = factorize(n) if n > 1 else []
+    return AxisPlan(n, tuple(rs), digit_reversal(n, rs), roots(max(n, 1)))
+
+
+@dataclass(frozen=True)
+class BigPlan:
+    N: int
+    a: AxisPlan             # first (column) pass, length n_a, stride n_b
+    b: AxisPlan             # second pass, length n_b
+    tw_hi: np.ndarray       # float32 (ceil(N / BIG_SPLIT), 2): W_N^{hi * BIG_SPLIT}
+    tw_lo: np.ndarray       # float32 (BIG_SPLIT, 2):          W_N^{lo}
+
+
+def big_plan(N: int) -> BigPlan:
+    na, nb = split_size(N)
+    hi = np.arange(-(-N // BIG_SPLIT), dtype=np.float64) * BIG_SPLIT
+    lo = np.arange(BIG_SPLIT, dtype=np.float64)
+    f = lambda e: np.stack([np.cos(-2 * np.pi * e / N), np.sin(-2 * np.pi * e / N)], axis=1).astype(np.float32)
+    return BigPlan(N, axis_plan(na), axis_plan(nb), f(hi), f(lo))
+
+
+@dataclass(frozen=True)
+class ResamplePlan:
+    T: int
+    num: int
+    fwd: BigPlan
+    inv: BigPlan
+    tw_T: np.ndarray        # float32 (num/2 + 1, 2): W_T^k        (rfft untangle)
+    tw_num: np.ndarray      # float32 (num/2, 2):     W_num^{-k}   (irfft fold)
+
+
+@functools.lru_cache(maxsize=16)
+def resample_plan(T: int, num: int) -> ResamplePlan:
+    if T % 2 or num % 2:
+        raise NotImplementedError(
+            f"FFT resample {T} -> {num}: odd lengths are not implemented yet (SURVEY.md 8f row f3)")
+    if num < 2 or T < 2:
+        raise ValueError("resample needs at least two samples in and out")
+    Nh = num // 2
+    k = np.arange(Nh + 1, dtype=np.float64)
+    tw_T = np.stack([np.cos(-2 * np.pi * k / T), np.sin(-2 * np.pi * k / T)], axis=1).astype(np.float32)
+    k = k[:Nh]
+    tw_num = np.stack([np.cos(2 * np.pi * k / num), np.sin(2 * np.pi * k / num)], axis=1).astype(np.float32)
+    return ResamplePlan(T, num, big_plan(T // 2), big_plan(Nh), tw_T, tw_num)
+
+
+# --------------------------------------------------------------------- Hilbert
+HILBERT_N = 4096
+
+
+def hilbert_gain(cfs: np.ndarray, sds: np.ndarray, fs: float) -> np.ndarray:
+    """(nb, 2048) float32 gain on the 4096-point block grid: Gaussian x analytic factor 2,
+    times 1/2 (conjugate-symmetry split), 1/N (inverse FFT) and 1/nb (mean over bands).
+    ref: frequency_filter.py:158-175,184 -- H[0] = 0."""
+    N = HILBERT_N
+    f = np.arange(N // 2, dtype=np.float64) * fs / N
+    g = np.exp(-0.5 * ((f[None, :] - cfs[:, None]) / sds[:, None]) ** 2)
+    g[:, 0] = 0.0
+    g *= 2.0 * 0.5 / N / len(cfs)
+    return np.ascontiguousarray(g, dtype=np.float32)
+
+
+def hilbert_halo(cfs: np.ndarray, sds: np.ndarray, fs: float, T: int, nsigma: float = 6.5) -> int:
+    """Samples of context each block needs.  Raises NotImplementedError when the bank cannot
+    be evaluated block-wise (kernels too long, or gain not negligible at DC / Nyquist)."""
+    sigma_t = 1.0 / (2.0 * np.pi * sds)                 # seconds, per band
+    halo = int(np.ceil(nsigma * sigma_t.max() * fs))
+    edge = np.maximum(np.exp(-0.5 * (cfs / sds) ** 2), np.exp(-0.5 * ((fs / 2 - cfs) / sds) ** 2))
+    if halo >= HILBERT_N // 4 or edge.max() > 1e-12:
+        raise NotImplementedError(
+            "this Gaussian bank needs the whole-record FFT path (low-frequency or near-Nyquist "
+            f"bands: halo {halo} samples, edge gain {edge.max():.1e}); only the block-wise "
+            "kernel is implemented (SURVEY.md section 8f row f3)")
+    return max(halo, 1)

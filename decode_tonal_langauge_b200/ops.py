@@ -1,0 +1,304 @@
+"""Device operators: thin torch-tensor wrappers over the C ABI (include/ecog_sm100.h).
+
+Every function takes float32 CUDA tensors of shape (C, T) (contiguous rows), enqueues
+on the current torch stream and returns new CUDA tensors.  PyTorch only owns the memory
+and the stream; all arithmetic happens in libecog_sm100.so.  No CPU path exists.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import design as D
+from . import fftplan as FP
+
+lib = nat.lib
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _hptr(a: Optional[np.ndarray]) -> C.c_void_p:
+    return C.c_void_p(0 if a is None else a.ctypes.data)
+
+
+def require_cuda() -> None:
+    if not torch.cuda.is_available():
+        raise RuntimeError("decode_tonal_langauge_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def as_signal(x: torch.Tensor) -> torch.Tensor:
+    """(C, T) float32 CUDA tensor with contiguous rows (row stride may exceed T)."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise TypeError("expected a CUDA tensor")
+    if x.dim() != 2:
+        raise ValueError(f"expected a (channels, time) array, got shape {tuple(x.shape)}")
+    if x.dtype != torch.float32:
+        x = x.to(torch.float32)
+    if x.stride(1) != 1 or (x.shape[0] > 1 and x.stride(0) < x.shape[1]):
+        x = x.contiguous()
+    return x
+
+
+def _ld(x: torch.Tensor) -> int:
+    return int(x.stride(0)) if x.shape[0] > 1 else int(x.shape[1])
+
+
+_workspaces = {}
+
+
+def workspace(nbytes: int, device, tag: str = "default") -> torch.Tensor:
+    """Grow-only scratch buffer per (device, tag); owned by torch, handed to the library."""
+    key = (str(device), tag)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = None
+        _workspaces.pop(key, None)
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf
+
+
+def release_workspaces() -> None:
+    _workspaces.clear()
+
+
+_tables = {}
+
+
+def _dev_table(key, make, device):
+    k = (str(device), key)
+    t = _tables.get(k)
+    if t is None:
+        t = torch.from_numpy(np.ascontiguousarray(make())).to(device)
+        _tables[k] = t
+    return t
+
+
+# ------------------------------------------------------------------------ K1
+def car(x: torch.Tensor, exclude_channels: Sequence[int] = ()) -> torch.Tensor:
+    x = as_signal(x)
+    Cn, T = x.shape
+    w, n_inc = _car_weights(Cn, exclude_channels, x.device)
+    y = torch.empty_like(x, memory_format=torch.contiguous_format)
+    nat.check(lib.ecog_car(_ptr(x), _ptr(y), Cn, T, _ld(x), _ptr(w), 1.0 / n_inc, _stream()))
+    return y
+
+
+def _car_weights(Cn, exclude_channels, device):
+    if not isinstance(exclude_channels, (list, tuple)):
+        raise ValueError("exclude_channels must be a list of integers.")
+    if any(ch < 0 or ch >= Cn for ch in exclude_channels):
+        raise ValueError("exclude_channels contains invalid channel indices.")
+    if len(exclude_channels) == 0:
+        return None, Cn
+    w = np.ones(Cn, dtype=np.float32)
+    w[list(exclude_channels)] = 0.0
+    return torch.from_numpy(w).to(device), int(w.sum())
+
+
+def car_colsum(x: torch.Tensor, weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Phase 1 of the channel-sharded CAR: per-timestep sum over this shard's rows."""
+    x = as_signal(x)
+    Cn, T = x.shape
+    s = torch.empty(T, dtype=torch.float32, device=x.device)
+    nat.check(lib.ecog_car_colsum(_ptr(x), Cn, T, _ld(x), _ptr(weights), _ptr(s), _stream()))
+    return s
+
+
+def car_apply(x: torch.Tensor, colsum: torch.Tensor, n_included: int) -> torch.Tensor:
+    """Phase 2: subtract the (all-reduced) column sum divided by the global included count."""
+    x = as_signal(x)
+    Cn, T = x.shape
+    y = torch.empty_like(x, memory_format=torch.contiguous_format)
+    nat.check(lib.ecog_car_apply(_ptr(x), _ptr(y), Cn, T, _ld(x), _ptr(colsum), 1.0 / n_included, _stream()))
+    return y
+
+
+# ------------------------------------------------------------------------ K2
+def row_stats(x: torch.Tensor, t0: int = 0, t1: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    x = as_signal(x)
+    Cn, T = x.shape
+    t1 = T if t1 is None else t1
+    mean = torch.empty(Cn, dtype=torch.float64, device=x.device)
+    std = torch.empty(Cn, dtype=torch.float64, device=x.device)
+    nbytes = lib.ecog_row_stats_workspace(Cn, T)
+    ws = workspace(nbytes, x.device)
+    nat.check(lib.ecog_row_stats(_ptr(x), Cn, T, _ld(x), int(t0), int(t1), _ptr(mean), _ptr(std),
+                                 _ptr(ws), ws.numel(), _stream()))
+    return mean, std
+
+
+def zscore(x: torch.Tensor, t0: int = 0, t1: Optional[int] = None, nan_to_zero: bool = False) -> torch.Tensor:
+    x = as_signal(x)
+    mean, std = row_stats(x, t0, t1)
+    y = torch.empty_like(x, memory_format=torch.contiguous_format)
+    nat.check(lib.ecog_zscore_apply(_ptr(x), _ptr(y), x.shape[0], x.shape[1], _ld(x), _ptr(mean), _ptr(std),
+                                    1 if nan_to_zero else 0, _stream()))
+    return y
+
+
+# ------------------------------------------------------------------------ K3
+def sosfilt(x: torch.Tensor, dsg: D.SosDesign, chunk: Optional[int] = None,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    x = as_signal(x)
+    Cn, T = x.shape
+    if dsg.zero_phase and T <= dsg.padlen:
+        raise ValueError(f"The length of the input vector x must be greater than padlen, which is {dsg.padlen}.")
+    L = D.choose_chunk(Cn, T, chunk)
+    n_chunks = -(-T // L)
+    if n_chunks > 1:
+        M, tail = D.chunk_ops(dsg, L)
+    else:
+        M, tail = None, L
+    plan = nat.SosPlan(dsg.nsec, 1 if dsg.zero_phase else 0, dsg.padlen, L, tail)
+    nbytes = lib.ecog_sos_workspace(C.byref(plan), Cn, T)
+    ws = workspace(nbytes, x.device)
+    y = out if out is not None else torch.empty_like(x, memory_format=torch.contiguous_format)
+    sos = np.ascontiguousarray(dsg.sos, dtype=np.float64)
+    zi = None if dsg.zi is None else np.ascontiguousarray(dsg.zi, dtype=np.float64)
+    Mh = None if M is None else np.ascontiguousarray(M, dtype=np.float64)
+    nat.check(lib.ecog_sosfilt(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), C.byref(plan), _hptr(sos), _hptr(zi),
+                               _hptr(Mh), _ptr(ws), ws.numel(), _stream()))
+    return y
+
+
+def butter(x: torch.Tensor, freqs, fs, order=4, causal=False, filter_type="bandpass",
+           chunk: Optional[int] = None) -> torch.Tensor:
+    return sosfilt(x, D.butter_design(freqs, fs, order, causal, filter_type), chunk)
+
+
+# ------------------------------------------------------------------------ K4
+def _hilbert_twiddles(device) -> torch.Tensor:
+    def make():
+        tw = np.zeros(lib.ecog_hilbert_twiddle_floats(), dtype=np.float32)
+        nat.check(lib.ecog_hilbert_twiddles(_hptr(tw)))
+        return tw
+    return _dev_table("hilbert_tw", make, device)
+
+
+def hilbert(x: torch.Tensor, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0,
+            filterbank_bias=np.log10(0.39), filterbank_slope=0.5, envelope=True) -> torch.Tensor:
+    x = as_signal(x)
+    Cn, T = x.shape
+    cfs, sds = D.gaussian_bank(freq_ranges, f0, octspace, filterbank_bias, filterbank_slope)
+    if len(cfs) == 0:
+        raise ValueError("the frequency ranges contain no filter-bank centre frequency")
+    halo = FP.hilbert_halo(cfs, sds, float(fs), T)
+    key = ("hilbert_gain", tuple(cfs.tolist()), tuple(sds.tolist()), float(fs))
+    gain = _dev_table(key, lambda: FP.hilbert_gain(cfs, sds, float(fs)), x.device)
+    y = torch.empty((Cn, T), dtype=torch.float32, device=x.device)
+    nat.check(lib.ecog_hilbert_env(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), _ptr(gain), len(cfs), halo,
+                                   1 if envelope else 0, _ptr(_hilbert_twiddles(x.device)), _stream()))
+    return y
+
+
+# ------------------------------------------------------------------------ K5
+def _axis(ap: FP.AxisPlan) -> nat.FftAxis:
+    a = nat.FftAxis()
+    a.n = ap.n
+    a.nstage = len(ap.radices)
+    for i, r in enumerate(ap.radices):
+        a.radix[i] = r
+    return a
+
+
+def fft_resample(x: torch.Tensor, num: int) -> torch.Tensor:
+    x = as_signal(x)
+    Cn, T = x.shape
+    num = int(num)
+    rp = FP.resample_plan(int(T), num)
+    dev = x.device
+    key = ("resample", T, num)
+    t = lambda name, arr: _dev_table(key + (name,), lambda: arr, dev)
+    tables = nat.ResampleTables()
+    keep = []
+    for name, arr in (("perm_fa", rp.fwd.a.perm), ("perm_fb", rp.fwd.b.perm), ("perm_ia", rp.inv.a.perm),
+                      ("perm_ib", rp.inv.b.perm), ("tw_fa", rp.fwd.a.tw), ("tw_fb", rp.fwd.b.tw),
+                      ("tw_ia", rp.inv.a.tw), ("tw_ib", rp.inv.b.tw), ("tw_big_f_hi", rp.fwd.tw_hi),
+                      ("tw_big_f_lo", rp.fwd.tw_lo), ("tw_big_i_hi", rp.inv.tw_hi), ("tw_big_i_lo", rp.inv.tw_lo),
+                      ("tw_T", rp.tw_T), ("tw_num", rp.tw_num)):
+        dt = t(name, arr)
+        keep.append(dt)
+        setattr(tables, name, dt.data_ptr())
+    tables.big_f_split = FP.BIG_SPLIT
+    tables.big_i_split = FP.BIG_SPLIT
+    plan = nat.ResamplePlan()
+    plan.T, plan.num = T, num
+    plan.fa, plan.fb, plan.ia, plan.ib = _axis(rp.fwd.a), _axis(rp.fwd.b), _axis(rp.inv.a), _axis(rp.inv.b)
+    if _ld(x) % 2 or x.data_ptr() % 8:
+        x = x.contiguous()
+    nbytes = lib.ecog_resample_workspace(C.byref(plan), Cn)
+    ws = workspace(nbytes, dev, "fft")
+    y = torch.empty((Cn, num), dtype=torch.float32, device=dev)
+    nat.check(lib.ecog_fft_resample(_ptr(x), _ptr(y), Cn, _ld(x), _ld(y), C.byref(plan), C.byref(tables),
+                                    _ptr(ws), ws.numel(), _stream()))
+    return y
+
+
+# ------------------------------------------------------------------------ K8
+def epoch_gather(src: torch.Tensor, starts: np.ndarray, length: int) -> torch.Tensor:
+    """out[n, c, :] = src[c, starts[n] : starts[n] + length]; bit copy for 4- and 8-byte dtypes."""
+    if not src.is_cuda or src.dim() != 2:
+        raise TypeError("expected a (channels, time) CUDA tensor")
+    if src.element_size() not in (4, 8):
+        raise TypeError(f"epoch_gather supports 4- and 8-byte element types, got {src.dtype}")
+    if src.stride(1) != 1:
+        src = src.contiguous()
+    Cn, T = src.shape
+    starts = np.ascontiguousarray(starts, dtype=np.int64)
+    N = int(starts.shape[0])
+    out = torch.empty((N, Cn, int(length)), dtype=src.dtype, device=src.device)
+    d_start = torch.from_numpy(starts).to(src.device) if N else None
+    nat.check(lib.ecog_epoch_gather(_ptr(src), _ptr(out), Cn, T, _ld(src), _ptr(d_start), _hptr(starts), N,
+                                    int(length), src.element_size(), _stream()))
+    return out
+
+
+# -------------------------------------------------------------------- K9 / K10
+def anova_f(epochs: torch.Tensor, groups: np.ndarray, extra: Optional[torch.Tensor] = None):
+    """One-way ANOVA over events for every (channel, timepoint).
+
+    epochs (Na, C, L) [+ extra (Nb, C, L), concatenated after it]; groups: int array of
+    length Na + Nb with values 0..G-1.  Returns (F, p) as (C, L) float64 CUDA tensors."""
+    def prep(e):
+        if e.dtype != torch.float32:
+            e = e.to(torch.float32)
+        return e.contiguous()
+    epochs = prep(epochs)
+    Na, Cn, L = epochs.shape
+    Nb = 0
+    if extra is not None:
+        extra = prep(extra)
+        Nb = int(extra.shape[0])
+        if tuple(extra.shape[1:]) != (Cn, L):
+            raise ValueError(f"Shape mismatch between recordings: {tuple(epochs.shape[1:])} vs {tuple(extra.shape[1:])}.")
+    groups = np.ascontiguousarray(groups, dtype=np.int32)
+    if groups.shape[0] != Na + Nb:
+        raise ValueError("one group label per event is required")
+    G = int(groups.max()) + 1 if groups.size else 0
+    counts = np.bincount(groups, minlength=max(G, 1)).astype(np.int64)
+    d_groups = torch.from_numpy(groups).to(epochs.device)
+    F = torch.empty((Cn, L), dtype=torch.float64, device=epochs.device)
+    P = torch.empty((Cn, L), dtype=torch.float64, device=epochs.device)
+    nat.check(lib.ecog_anova_f(_ptr(epochs), Na, _ptr(extra), Nb, Cn, L, _ptr(d_groups), _hptr(counts), G,
+                               _ptr(F), _ptr(P), _stream()))
+    return F, P
+
+
+def sig_runlength(p: torch.Tensor, threshold: float) -> torch.Tensor:
+    """Longest run of consecutive p < threshold per channel (int32, (C,))."""
+    p = p.contiguous()
+    Cn, L = p.shape
+    out = torch.empty(Cn, dtype=torch.int32, device=p.device)
+    nat.check(lib.ecog_sig_runlength(_ptr(p), Cn, L, float(threshold), _ptr(out), _stream()))
+    return out

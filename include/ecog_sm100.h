@@ -1,0 +1,166 @@
+/*
+ * libecog_sm100.so -- C ABI of the B200 (sm_100a) ECoG hot path.
+ *
+ * The reference (Daniel-Lin-S/decode_tonal_langauge) has no native layer: its hot
+ * path is numpy/scipy called from Python plug-ins.  The functions below are what a
+ * ctypes binding behind those plug-ins calls instead; each cites the reference
+ * interface (file:line, relative to the reference root) whose arithmetic it replaces.
+ * INTEGRATION.md shows the reference-side stub for every entry point.
+ *
+ * Conventions:
+ *   - every pointer named d_* is DEVICE memory owned by the caller (PyTorch);
+ *     h_* is HOST memory read during the call; the library never allocates,
+ *     frees or synchronises the device and never creates streams;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*);
+ *   - signals are float32, row-major (C channels, T samples) with a row stride
+ *     `ld` in elements; statistics and filter states are float64;
+ *   - return 0 on success or a negative ECOG_E_* code; ecog_last_error() gives
+ *     the thread-local message.  The Python shims map ECOG_E_VALUE to ValueError
+ *     (the reference's own error type for bad parameters) and the rest to
+ *     RuntimeError;
+ *   - no global mutable state: calls are re-entrant across host threads/streams.
+ */
+#ifndef ECOG_SM100_H
+#define ECOG_SM100_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECOG_ABI_VERSION 1
+
+#define ECOG_OK 0
+#define ECOG_E_VALUE (-1)     /* bad argument (reference raises ValueError)          */
+#define ECOG_E_CUDA (-2)      /* CUDA launch / runtime failure                       */
+#define ECOG_E_WORKSPACE (-3) /* workspace too small                                 */
+#define ECOG_E_UNSUPPORTED (-4) /* shape outside what this build implements          */
+
+typedef void* ecog_stream_t;
+
+int ecog_abi_version(void);
+const char* ecog_last_error(void);
+/* number of kernels this library has launched from the calling thread (bench bookkeeping) */
+int64_t ecog_launch_count(void);
+
+/* ------------------------------------------------------------------ K1: CAR
+ * replaces preprocess/signal/car_rereference.py:34-39
+ *   y[c,t] = x[c,t] - (1/n_inc) * sum_c w[c] x[c,t];  d_w (C floats, 0/1) may be NULL.
+ * ecog_car is the single-GPU fused pass.  ecog_car_colsum / ecog_car_apply are the
+ * two-phase form for channel-sharded recordings: the caller all-reduces d_colsum
+ * (T floats) between the two enqueues.                                             */
+int ecog_car(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ld,
+             const float* d_w, double inv_count, ecog_stream_t stream);
+int ecog_car_colsum(const float* d_x, int64_t C, int64_t T, int64_t ld, const float* d_w,
+                    float* d_colsum, ecog_stream_t stream);
+int ecog_car_apply(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ld,
+                   const float* d_colsum, double inv_count, ecog_stream_t stream);
+
+/* -------------------------------------------------------- K2: row statistics
+ * replaces preprocess/signal/channel_zscore.py:22-27 and
+ *          preprocess/signal/zscore_rereference.py:66-68
+ * mean and POPULATION std (ddof=0) of x[c, t0:t1] in float64, then
+ * y = (x - mean) / std over the whole row; nan_to_zero mirrors preserve_nans=False. */
+size_t ecog_row_stats_workspace(int64_t C, int64_t T);
+int ecog_row_stats(const float* d_x, int64_t C, int64_t T, int64_t ld, int64_t t0, int64_t t1,
+                   double* d_mean, double* d_std, void* d_workspace, size_t workspace_bytes,
+                   ecog_stream_t stream);
+int ecog_zscore_apply(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ld,
+                      const double* d_mean, const double* d_std, int nan_to_zero,
+                      ecog_stream_t stream);
+
+/* ---------------------------------------------- K3: IIR biquad cascade (SOS)
+ * replaces preprocess/signal/frequency_filter.py:218-229 (scipy filtfilt / sosfilt).
+ * h_sos: nsec x 6 float64 (b0 b1 b2 a0 a1 a2), host.  zero_phase=1 reproduces
+ * filtfilt(padtype='odd', padlen): h_zi (nsec x 2, host) is the unit-step state in
+ * cascade coordinates, scaled by the first padded sample of each sweep; zero_phase=0
+ * is the causal zero-state sosfilt.  Rows are cut into chunks of `chunk` samples that
+ * are filtered in parallel; h_M (2nsec x 2nsec, row major, host) is the cascade's
+ * state-transition matrix raised to the power `chunk`, used to carry the state across
+ * chunks (may be NULL when T <= chunk).  `tail` = number of trailing samples of a
+ * chunk whose zero-state response still reaches the chunk end in float64
+ * (ceil(log(1e-18)/log(max pole radius)), clamped to chunk).  d_y may alias d_x.     */
+typedef struct {
+    int32_t nsec;        /* biquad sections, 1..ECOG_MAX_SECTIONS                    */
+    int32_t zero_phase;  /* 1 = forward-backward with odd padding, 0 = causal        */
+    int32_t padlen;      /* filtfilt pad (27 for order-4 band filters); 0 if causal   */
+    int32_t chunk;       /* samples per scan chunk, multiple of 16                    */
+    int32_t tail;        /* multiple of 16, <= chunk                                  */
+} ecog_sos_plan;
+#define ECOG_MAX_SECTIONS 8
+size_t ecog_sos_workspace(const ecog_sos_plan* plan, int64_t C, int64_t T);
+int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                 const ecog_sos_plan* plan, const double* h_sos, const double* h_zi,
+                 const double* h_M, void* d_workspace, size_t workspace_bytes,
+                 ecog_stream_t stream);
+
+/* ------------------------------------ K4: Gaussian-Hilbert envelope (block-wise)
+ * replaces preprocess/signal/frequency_filter.py:154-184.
+ * Overlap-save with 4096-point shared-memory FFTs and a circular halo.  d_gain:
+ * nbands x 2048 float32 = Gaussian x analytic mask / (4096 * nbands) sampled on the
+ * block grid (host, float64 -> float32).  d_twiddle: table from ecog_hilbert_twiddles. */
+#define ECOG_HILBERT_N 4096
+size_t ecog_hilbert_twiddle_floats(void);
+int ecog_hilbert_twiddles(float* h_out);   /* host helper: fills the per-thread twiddle table */
+int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                     const float* d_gain, int32_t nbands, int32_t halo, int32_t envelope,
+                     const float* d_twiddle, ecog_stream_t stream);
+
+/* ------------------------------------------------- K5: whole-row FFT resample
+ * replaces preprocess/signal/downsample.py:21-27 (scipy.signal.resample, real input).
+ * Plan arrays are built by the host (decode_tonal_langauge_b200/fftplan.py).          */
+typedef struct {
+    int32_t n;           /* FFT length along the tile axis                           */
+    int32_t nstage;      /* radix stages                                             */
+    int32_t radix[16];   /* product == n, each in {2,3,4,5}                          */
+} ecog_fft_axis;
+typedef struct {
+    int64_t T;           /* input samples per row (even)                             */
+    int64_t num;         /* output samples per row (even)                            */
+    ecog_fft_axis fa, fb;   /* forward: N = T/2 = fa.n * fb.n (column pass, row pass)  */
+    ecog_fft_axis ia, ib;   /* inverse: N' = num/2 = ia.n * ib.n                       */
+} ecog_resample_plan;
+/* device tables, all built on the host in float64 and rounded once:
+ *   d_perm_*  int32 digit-reversal permutations (length = axis n)
+ *   d_tw_*    float2 roots of unity W_n^k (length = axis n)
+ *   d_tw_big_f / d_tw_big_i  float2 four-step twiddle factors, two-level tables
+ *   d_untangle float2 x (num/2 + 1) pairs used by the spectrum repack                 */
+typedef struct {
+    const int32_t *perm_fa, *perm_fb, *perm_ia, *perm_ib;
+    const float *tw_fa, *tw_fb, *tw_ia, *tw_ib;
+    const float *tw_big_f_hi, *tw_big_f_lo, *tw_big_i_hi, *tw_big_i_lo;
+    int32_t big_f_split, big_i_split;
+    const float *tw_T, *tw_num;
+} ecog_resample_tables;
+size_t ecog_resample_workspace(const ecog_resample_plan* plan, int64_t C);
+int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_t ldx, int64_t ldy,
+                      const ecog_resample_plan* plan, const ecog_resample_tables* tables,
+                      void* d_workspace, size_t workspace_bytes, ecog_stream_t stream);
+
+/* ------------------------------------------------------- K8: epoch gather
+ * replaces data_loading/text_align.py:290-304,331-340,380-394.
+ *   out[n, c, 0:L] = src[c, start[n] : start[n]+L]    (bit copy; elem_bytes 4 or 8)
+ * d_start: int64 onset indices computed on the host in float64 (Appendix A6).
+ * Returns ECOG_E_VALUE if any window leaves [0, T) -- checked on the host copy h_start. */
+int ecog_epoch_gather(const void* d_src, void* d_out, int64_t C, int64_t T, int64_t ld,
+                      const int64_t* d_start, const int64_t* h_start, int64_t N, int64_t L,
+                      int32_t elem_bytes, ecog_stream_t stream);
+
+/* --------------------------------------------- K9/K10: ANOVA F + run length
+ * replaces channel_selection/discriminative.py:172-180, channel_selection/active.py:58-76,
+ *          channel_selection/utils.py:4-30,63-75 (scipy.stats.f_oneway, equal_var).
+ * Epochs may come from up to two tensors (ERP then rest, for active.run); d_group
+ * maps every event to 0..G-1.  Outputs F and p = fdtrc(G-1, N-G, F) as (C, L) float64. */
+int ecog_anova_f(const float* d_epochs_a, int64_t Na, const float* d_epochs_b, int64_t Nb,
+                 int64_t C, int64_t L, const int32_t* d_group, const int64_t* h_group_count,
+                 int32_t G, double* d_F, double* d_p, ecog_stream_t stream);
+/* longest run of consecutive p < threshold per channel (NaN compares false) */
+int ecog_sig_runlength(const double* d_p, int64_t C, int64_t L, double threshold,
+                       int32_t* d_maxrun, ecog_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ECOG_SM100_H */

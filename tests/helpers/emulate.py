@@ -1,0 +1,187 @@
+"""numpy models of the device algorithms, driven by the SAME host-built plans/tables the
+kernels consume.  They let the CPU test-suite validate plan logic (chunk carries, FFT
+decompositions, table layouts) without a GPU; the GPU tests then only have to prove the
+kernels implement these simple semantics."""
+from __future__ import annotations
+
+import numpy as np
+from scipy import signal as sp_signal
+
+
+def sos_chunk_scan(x32: np.ndarray, design, chunk: int, M: np.ndarray, tail: int) -> np.ndarray:
+    """Model of csrc/sosfilt.cu for one sweep pair.  x32: (C, T) float32."""
+    sos = design.sos
+    nsec = sos.shape[0]
+    C, T = x32.shape
+    P = design.padlen
+
+    def sweep(u, s0):
+        """u: (T,) float64 main samples; s0: (nsec,2) state at main start -> (y float32, end state)"""
+        n_chunks = -(-T // chunk)
+        g = [None] * n_chunks
+        for k in range(n_chunks - 1):                      # tail pass, zero state
+            seg = u[k * chunk:(k + 1) * chunk][chunk - tail:]
+            _, zf = sp_signal.sosfilt(sos, seg, zi=np.zeros((nsec, 2)))
+            g[k] = zf
+        S = [s0]
+        for k in range(n_chunks - 1):                      # scan
+            S.append((M @ S[k].reshape(-1) + g[k].reshape(-1)).reshape(nsec, 2))
+        y = np.empty(T, dtype=np.float32)
+        zf = s0
+        for k in range(n_chunks):                          # main pass
+            seg = u[k * chunk:(k + 1) * chunk]
+            out, zf = sp_signal.sosfilt(sos, seg, zi=S[k])
+            y[k * chunk:k * chunk + len(seg)] = out.astype(np.float32)
+        return y, zf
+
+    out = np.empty_like(x32)
+    for c in range(C):
+        x = x32[c]
+        if not design.zero_phase:
+            out[c], _ = sweep(x.astype(np.float64), np.zeros((nsec, 2)))
+            continue
+        left = (np.float32(2.0) * x[0] - x[P:0:-1]).astype(np.float32)
+        right = (np.float32(2.0) * x[-1] - x[-2:-(P + 2):-1]).astype(np.float32)
+        s = design.zi * np.float64(left[0])
+        _, s = sp_signal.sosfilt(sos, left.astype(np.float64), zi=s)
+        yf, s_end = sweep(x.astype(np.float64), s)
+        ypad, _ = sp_signal.sosfilt(sos, right.astype(np.float64), zi=s_end)      # float64 pad
+        s = design.zi * ypad[-1]
+        _, s = sp_signal.sosfilt(sos, ypad[::-1], zi=s)
+        yb, _ = sweep(yf[::-1].astype(np.float64), s)
+        out[c] = yb[::-1]
+    return out
+
+
+# ----------------------------------------------------------------------------- FFT models
+def _c(t):  # (n, 2) float32 table -> complex128
+    return t[:, 0].astype(np.float64) + 1j * t[:, 1].astype(np.float64)
+
+
+def tile_fft(cols: np.ndarray, axis_plan) -> np.ndarray:
+    """Model of the in-shared-memory FFT of csrc/fft.cu: cols is (n, W) complex; rows are
+    placed at perm[i], then in-place DIT stages with twiddles read from the W_n table."""
+    n = axis_plan.n
+    tw = _c(axis_plan.tw)
+    buf = np.empty_like(cols, dtype=np.complex128)
+    buf[axis_plan.perm] = cols
+    L_prev = 1
+    for r in axis_plan.radices:
+        L = L_prev * r
+        stride = n // L
+        new = np.empty_like(buf)
+        for g in range(n // L):
+            for j in range(L_prev):
+                base = g * L + j
+                u = np.stack([buf[base + q * L_prev] * tw[(j * q) * stride] for q in range(r)])
+                for p in range(r):
+                    acc = 0
+                    for q in range(r):
+                        acc = acc + u[q] * np.exp(-2j * np.pi * p * q / r)
+                    new[base + p * L_prev] = acc
+        buf = new
+        L_prev = L
+    return buf
+
+
+def big_fft(z: np.ndarray, plan) -> np.ndarray:
+    """Model of the two-pass four-step forward FFT (natural order in and out)."""
+    N, na, nb = plan.N, plan.a.n, plan.b.n
+    hi, lo = _c(plan.tw_hi), _c(plan.tw_lo)
+    S = lo.shape[0]
+    x = z.reshape(na, nb)                                   # j = i * nb + c
+    Y = tile_fft(x, plan.a)                                 # over i -> q, for every column c
+    q = np.arange(na)[:, None]
+    c = np.arange(nb)[None, :]
+    e = q * c
+    Y = Y * hi[e // S] * lo[e % S]
+    inter = np.ascontiguousarray(Y.T)                       # transposed store: [c][q]
+    if nb == 1:
+        return inter.reshape(-1)
+    X = tile_fft(inter, plan.b)                             # over c -> p, for every column q
+    return X.reshape(-1)                                    # k = p * na + q
+
+
+def resample_model(x32: np.ndarray, plan) -> np.ndarray:
+    """Model of ecog_fft_resample for one row (float32 in, float32 out)."""
+    T, num = plan.T, plan.num
+    N, Nh = T // 2, num // 2
+    z = x32[0::2].astype(np.float64) + 1j * x32[1::2].astype(np.float64)
+    Z = big_fft(z, plan.fwd)
+    m = min(num, T)
+    k = np.arange(Nh + 1)
+    Zk = Z[k % N]
+    Zm = np.conj(Z[(N - k) % N])
+    X = 0.5 * (Zk + Zm) - 0.5j * _c(plan.tw_T) * (Zk - Zm)
+    Y = X * (num / T)
+    Y[k > m // 2] = 0
+    if m % 2 == 0 and num != T:
+        Y[m // 2] *= 2.0 if num < T else 0.5
+    Y[0] = Y[0].real
+    Y[Nh] = Y[Nh].real
+    kk = np.arange(Nh)
+    E = 0.5 * (Y[kk] + np.conj(Y[Nh - kk]))
+    O = 0.5 * (Y[kk] - np.conj(Y[Nh - kk])) * _c(plan.tw_num)
+    G = E + 1j * O
+    g = np.conj(big_fft(np.conj(G), plan.inv)) / Nh
+    y = np.empty(num, dtype=np.float32)
+    y[0::2] = g.real
+    y[1::2] = g.imag
+    return y
+
+
+def fft4096_model(z: np.ndarray, tw: np.ndarray) -> np.ndarray:
+    """Model of the 16x16x16 register FFT of csrc/hilbert.cu using the table from
+    ecog_hilbert_twiddles ((2,16,256,2) float32)."""
+    tw = tw.reshape(2, 16, 256, 2).astype(np.float64)
+    tw1 = tw[0, :, :, 0] + 1j * tw[0, :, :, 1]
+    tw2 = tw[1, :, :, 0] + 1j * tw[1, :, :, 1]
+    tid = np.arange(256)
+    buf = np.zeros(4096, dtype=np.complex128)
+    v = z.reshape(16, 256)                                  # v[n2, tid] = z[256 n2 + tid]
+    A = np.fft.fft(v, axis=0) * tw1                         # k0, tid
+    buf[(256 * np.arange(16)[:, None] + tid[None, :])] = A
+    k0, n0 = tid >> 4, tid & 15
+    idx = 256 * k0[None, :] + 16 * np.arange(16)[:, None] + n0[None, :]
+    B = np.fft.fft(buf[idx], axis=0) * tw2                  # k1, tid
+    buf[idx] = B
+    idx3 = 16 * tid[None, :] + np.arange(16)[:, None]
+    Xr = np.fft.fft(buf[idx3], axis=0)                      # k2, tid ; tid = 16 k0 + k1
+    out = np.zeros(4096, dtype=np.complex128)
+    k0, k1 = tid >> 4, tid & 15
+    out[k0[None, :] + 16 * k1[None, :] + 256 * np.arange(16)[:, None]] = Xr
+    return out
+
+
+def hilbert_block_model(x32: np.ndarray, gain: np.ndarray, halo: int, envelope: bool = True) -> np.ndarray:
+    """Model of ecog_hilbert_env for one row: overlap-save blocks with circular halo,
+    two blocks per complex FFT, conj-forward inverse, mean folded into the gain."""
+    N = 4096
+    T = x32.shape[0]
+    U = N - 2 * halo
+    nblk = -(-T // U)
+    y = np.zeros(T, dtype=np.float32)
+    g = gain.astype(np.float64)
+    for b0 in range(0, nblk, 2):
+        i = np.arange(N)
+        a = x32[(b0 * U - halo + i) % T].astype(np.float64)
+        has1 = b0 + 1 < nblk
+        bb = x32[((b0 + 1) * U - halo + i) % T].astype(np.float64) if has1 else np.zeros(N)
+        Z = np.fft.fft(a + 1j * bb)
+        k = np.arange(1, N // 2)
+        S0 = np.zeros(N // 2, dtype=np.complex128)
+        S1 = np.zeros(N // 2, dtype=np.complex128)
+        S0[k] = Z[k] + np.conj(Z[N - k])
+        S1[k] = -1j * (Z[k] - np.conj(Z[N - k]))
+        acc = [np.zeros(N), np.zeros(N)]
+        for band in range(g.shape[0]):
+            for sel, S in enumerate((S0, S1)):
+                Yc = np.zeros(N, dtype=np.complex128)
+                Yc[:N // 2] = np.conj(S) * g[band]
+                zc = np.fft.fft(Yc)
+                acc[sel] += np.abs(zc) if envelope else zc.real
+        for sel in range(2 if has1 else 1):
+            t = (b0 + sel) * U + np.arange(U)
+            ok = t < T
+            y[t[ok]] = acc[sel][halo + np.arange(U)][ok].astype(np.float32)
+    return y

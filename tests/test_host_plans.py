@@ -1,0 +1,124 @@
+"""CPU tests of the host-built plans and tables through numpy models of the kernels
+(tests/helpers/emulate.py).  No GPU and no compute calls into the library."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from decode_tonal_langauge_b200 import design as D
+from decode_tonal_langauge_b200 import fftplan as FP
+from oracle import steps as S
+from helpers import emulate as EM
+from conftest import max_rel
+
+
+@pytest.mark.parametrize("n", [1, 2, 5, 12, 60, 64, 225, 1000, 1800])
+def test_tile_fft_model(n):
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((n, 3)) + 1j * rng.standard_normal((n, 3))
+    got = EM.tile_fft(x, FP.axis_plan(n))
+    ref = np.fft.fft(x, axis=0)
+    assert np.max(np.abs(got - ref)) < 2e-6 * max(1.0, np.max(np.abs(ref)))
+
+
+def test_factorize_rejects_non_smooth():
+    with pytest.raises(NotImplementedError):
+        FP.factorize(2 * 915527)
+    assert np.prod(FP.factorize(3600000)) == 3600000
+
+
+@pytest.mark.parametrize("N", [6000, 9000, 36000])
+def test_big_fft_model(N):
+    rng = np.random.default_rng(N)
+    z = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+    plan = FP.big_plan(N)
+    assert plan.a.n * plan.b.n == N and plan.a.n <= FP.MAX_AXIS and plan.b.n <= FP.MAX_AXIS
+    got = EM.big_fft(z, plan)
+    ref = np.fft.fft(z)
+    assert np.max(np.abs(got - ref)) < 5e-6 * np.max(np.abs(ref))
+
+
+def test_split_sizes_for_baseline_configs():
+    for T in (1_200_000, 3_600_000, 7_200_000, 10_800_000):
+        for N in (T // 2, T // 10 if T % 3 else T // 15):
+            na, nb = FP.split_size(N)
+            assert na * nb == N and max(na, nb) <= FP.MAX_AXIS
+
+
+@pytest.mark.parametrize("T,num", [(12000, 2400), (12000, 3600), (16000, 16000), (6000, 9000), (24000, 4800)])
+def test_resample_model_vs_oracle(T, num):
+    rng = np.random.default_rng(T + num)
+    x = rng.standard_normal(T).astype(np.float32) * 30
+    got = EM.resample_model(x, FP.resample_plan(T, num))
+    ref = S.fft_resample(x[None].astype(np.float64), num)[0]
+    assert max_rel(got, ref) < 2e-6
+
+
+def test_resample_odd_lengths_are_declared_unsupported():
+    with pytest.raises(NotImplementedError):
+        FP.resample_plan(9001, 1800)
+
+
+def test_hilbert_models(golden):
+    from decode_tonal_langauge_b200 import _native as nat
+    n = nat.lib.ecog_hilbert_twiddle_floats()
+    tw = np.zeros(n, dtype=np.float32)
+    assert nat.lib.ecog_hilbert_twiddles(tw.ctypes.data_as(ctypes.c_void_p)) == 0
+    rng = np.random.default_rng(0)
+    z = rng.standard_normal(4096) + 1j * rng.standard_normal(4096)
+    got = EM.fft4096_model(z, tw)
+    assert np.max(np.abs(got - np.fft.fft(z))) < 2e-5
+
+    g = golden("steps")
+    x, fs = g["x"], float(g["fs"])
+    cfs, sds = D.gaussian_bank([70.0, 150.0])
+    assert len(cfs) == 8 and abs(cfs[0] - 73.728) < 1e-3
+    halo = FP.hilbert_halo(cfs, sds, fs, x.shape[1])
+    gain = FP.hilbert_gain(cfs, sds, fs)
+    y = np.stack([EM.hilbert_block_model(r, gain, halo, True) for r in x])
+    assert max_rel(y, g["hilbert_env"]) < 1e-6
+    y = np.stack([EM.hilbert_block_model(r, gain, halo, False) for r in x])
+    assert max_rel(y, g["hilbert_real"]) < 1e-6
+    cfs2, sds2 = D.gaussian_bank([[30.0, 55.0], [70.0, 150.0]])
+    halo2 = FP.hilbert_halo(cfs2, sds2, fs, x.shape[1])
+    y = np.stack([EM.hilbert_block_model(r, FP.hilbert_gain(cfs2, sds2, fs), halo2, True) for r in x])
+    assert max_rel(y, g["hilbert_two_ranges"]) < 1e-6
+    with pytest.raises(NotImplementedError):
+        c3, s3 = D.gaussian_bank([0.5, 4.0])
+        FP.hilbert_halo(c3, s3, fs, x.shape[1])
+
+
+@pytest.mark.parametrize("key,freqs,btype,tol", [
+    ("notch", [58, 62], "bandstop", None),
+    ("bandpass", [70, 150], "bandpass", 1e-6),
+    ("lowpass", 200.0, "lowpass", 1e-6),
+    ("highpass", 1.0, "highpass", 1e-6),
+])
+def test_sos_design_and_chunk_scan_model(golden, key, freqs, btype, tol):
+    g = golden("steps")
+    x, fs = g["x"], float(g["fs"])
+    d = D.butter_design(freqs, fs, 4, False, btype)
+    for chunk in (1024, 4096, 16384):
+        M, tail = D.chunk_ops(d, chunk)
+        y = EM.sos_chunk_scan(x, d, chunk, M, tail)
+        if tol is not None:
+            assert max_rel(y, g[key]) < tol
+        else:   # ill-conditioned design: the long-double rule of SURVEY.md section 8c
+            truth = S.filtfilt_pad(d.b, d.a, x, dtype=np.longdouble)
+            assert max_rel(y, truth) <= max(1e-5, max_rel(g[key], truth))
+
+
+def test_causal_design_matches_reference(golden):
+    g = golden("steps")
+    x, fs = g["x"], float(g["fs"])
+    d = D.butter_design([70, 150], fs, 4, True, "bandpass")
+    M, tail = D.chunk_ops(d, 2048)
+    y = EM.sos_chunk_scan(x, d, 2048, M, tail)
+    assert max_rel(y, g["causal"]) < 1e-6
+
+
+def test_choose_chunk_fills_one_wave():
+    L = D.choose_chunk(256, 7_200_000)
+    n_chunks = -(-7_200_000 // L)
+    assert L % 16 == 0 and 256 * n_chunks <= 148 * 512
+    assert D.choose_chunk(4, 12000) >= 1024
