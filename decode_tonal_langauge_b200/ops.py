@@ -173,8 +173,9 @@ def sosfilt(x: torch.Tensor, dsg: D.SosDesign, chunk: Optional[int] = None,
 
 
 def butter(x: torch.Tensor, freqs, fs, order=4, causal=False, filter_type="bandpass",
-           chunk: Optional[int] = None) -> torch.Tensor:
-    return sosfilt(x, D.butter_design(freqs, fs, order, causal, filter_type), chunk)
+           chunk: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ref: frequency_filter.py:187-229 (butter_filter keyword names kept)."""
+    return sosfilt(x, D.butter_design(freqs, fs, order, causal, filter_type), chunk, out=out)
 
 
 # ------------------------------------------------------------------------ K4
@@ -187,7 +188,9 @@ def _hilbert_twiddles(device) -> torch.Tensor:
 
 
 def hilbert(x: torch.Tensor, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0,
-            filterbank_bias=np.log10(0.39), filterbank_slope=0.5, envelope=True) -> torch.Tensor:
+            filterbank_bias=np.log10(0.39), filterbank_slope=0.5, envelope=True,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """ref: frequency_filter.py:80-184 (hilbert_filter keyword names kept)."""
     x = as_signal(x)
     Cn, T = x.shape
     cfs, sds = D.gaussian_bank(freq_ranges, f0, octspace, filterbank_bias, filterbank_slope)
@@ -196,10 +199,19 @@ def hilbert(x: torch.Tensor, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0,
     halo = FP.hilbert_halo(cfs, sds, float(fs), T)
     key = ("hilbert_gain", tuple(cfs.tolist()), tuple(sds.tolist()), float(fs))
     gain = _dev_table(key, lambda: FP.hilbert_gain(cfs, sds, float(fs)), x.device)
-    y = torch.empty((Cn, T), dtype=torch.float32, device=x.device)
+    y = out if out is not None else torch.empty((Cn, T), dtype=torch.float32, device=x.device)
     nat.check(lib.ecog_hilbert_env(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), _ptr(gain), len(cfs), halo,
                                    1 if envelope else 0, _ptr(_hilbert_twiddles(x.device)), _stream()))
     return y
+
+
+# ------------------------------------------------------------------ K6 / K7
+def fir_bank(x: torch.Tensor, fs, order: int, center_frequencies, out: Optional[torch.Tensor] = None):
+    raise NotImplementedError("the 'fir' band method is not implemented yet (SURVEY.md section 8f row f3)")
+
+
+def rolling_zscore(x: torch.Tensor, window: int, nan_to_zero: bool = False):
+    raise NotImplementedError("rolling_zscore is not implemented yet (SURVEY.md section 8f row f3)")
 
 
 # ------------------------------------------------------------------------ K5

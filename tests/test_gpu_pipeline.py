@@ -1,0 +1,205 @@
+"""Plug-in level parity on the B200: step ``run(data, params)`` modules, the step runner
+(chains EX and FULL6), epoch extraction and channel selection against the golden fixtures
+written by the real reference."""
+from argparse import Namespace
+
+import numpy as np
+import pytest
+
+from conftest import max_rel
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def test_step_modules_numpy_contract(golden):
+    from decode_tonal_langauge_b200 import steps as S
+    g = golden("steps")
+    x, fs = g["x"], int(g["fs"])
+    p = Namespace(signal_freq=fs, downsample_freq=400)
+    y = S.downsample(x, p)
+    assert isinstance(y, np.ndarray) and y.dtype == np.float32 and p.signal_freq == 400
+    assert max_rel(y, g["downsample"]) < TOL
+    p = Namespace(signal_freq=fs, bands=[
+        {"method": "hilbert", "params": {"freq_ranges": [70.0, 150.0], "envelope": True}},
+        {"method": "butter", "params": {"freqs": [0.3, 100], "filter_type": "bandpass"}}])
+    y = S.frequency_filter(x, p)
+    assert y.dtype == np.float64 and y.shape == g["two_bands"].shape
+    assert max_rel(y, g["two_bands"]) < TOL
+    p = Namespace(signal_freq=fs)
+    y = S.car_rereference(x, p)
+    assert p.exclude_channels == [] and y.dtype == np.float32 and max_rel(y, g["car"]) < 2e-6
+    assert max_rel(S.channel_zscore(x, Namespace(signal_freq=fs)), g["channel_zscore"]) < 2e-6
+    y = S.zscore_rereference(x, Namespace(signal_freq=fs, rereference_interval=[0.5, 3.0]))
+    assert max_rel(y, g["zscore_rereference"]) < 2e-6
+    # float64 input is accepted like the reference and keeps its dtype where the reference does
+    assert S.car_rereference(x.astype(np.float64), Namespace(signal_freq=fs)).dtype == np.float64
+
+
+def test_step_errors_match_reference_types(golden):
+    from decode_tonal_langauge_b200 import steps as S
+    x = golden("steps")["x"]
+    with pytest.raises(ValueError):
+        S.frequency_filter(x, Namespace(signal_freq=2000))
+    with pytest.raises(ValueError):
+        S.frequency_filter(x, Namespace(signal_freq=2000, bands=[{"method": "hilbert", "params": {}}]))
+    with pytest.raises(ValueError):
+        S.frequency_filter(x, Namespace(signal_freq=2000, bands=[{"method": "butter", "params": {}}]))
+    with pytest.raises(ValueError):
+        S.car_rereference(x, Namespace(exclude_channels=(1,)))
+    with pytest.raises(ValueError):
+        S.car_rereference(x, Namespace(exclude_channels=[99]))
+    with pytest.raises(ValueError):
+        S.zscore_rereference(x, Namespace(signal_freq=2000))
+    with pytest.raises(ValueError):
+        S.zscore_rereference(x, Namespace(signal_freq=2000, rereference_interval=[2.0, 1.0]))
+    with pytest.raises(ValueError):
+        S.zscore_rereference(x, Namespace(signal_freq=2000, rereference_interval=[0.0, 100.0]))
+
+
+def test_chains_against_reference(golden):
+    from decode_tonal_langauge_b200.chains import EX_STEPS, FULL6_STEPS
+    from decode_tonal_langauge_b200.preprocessor import preprocess_signal
+    c = golden("chains")
+    x, fs = c["x"], int(c["fs"])
+    p = Namespace(signal_freq=fs)
+    y, f = preprocess_signal(x, FULL6_STEPS, p)
+    assert f == int(c["full6_fs"]) and y.dtype == c["full6"].dtype and y.shape == c["full6"].shape
+    err = max_rel(y, c["full6"])
+    # the notch stage of this chain is the ill-conditioned design of section 8c: the float64
+    # reference carries ~2e-5 of its own round-off into the chain output
+    assert err < 5e-5, err
+    p = Namespace(signal_freq=fs)
+    y, f = preprocess_signal(x, EX_STEPS, p)
+    assert f == int(c["ex_fs"]) and y.shape == c["ex"].shape and y.dtype == c["ex"].dtype
+    assert max_rel(y, c["ex"]) < TOL
+    # device-resident caller: tensors in, tensors out
+    yd, _ = preprocess_signal(torch.from_numpy(x).cuda(), EX_STEPS, Namespace(signal_freq=fs))
+    assert yd.is_cuda and max_rel(yd.cpu().numpy(), c["ex"]) < TOL
+
+
+def test_chain_full6_long_double_rule(golden):
+    """FULL6 against the extended-precision evaluation of the reference's own algorithm."""
+    from oracle import steps as S
+    from oracle import chains as CH
+    from decode_tonal_langauge_b200 import design as D
+    from decode_tonal_langauge_b200.chains import FULL6_STEPS
+    from decode_tonal_langauge_b200.preprocessor import preprocess_signal
+    c = golden("chains")
+    x, fs = c["x"], int(c["fs"])
+    d = D.butter_design([58, 62], fs, 4, False, "bandstop")
+    notch_ld = np.asarray(S.filtfilt_pad(d.b, d.a, x, dtype=np.longdouble), dtype=np.float64)
+    truth, _ = CH.run_chain(notch_ld, fs, FULL6_STEPS[1:])
+    y, _ = preprocess_signal(x, FULL6_STEPS, Namespace(signal_freq=fs))
+    err_gpu, err_ref = max_rel(y, truth), max_rel(c["full6"], truth)
+    assert err_gpu <= max(TOL, err_ref), (err_gpu, err_ref)
+
+
+def test_strict_params_reproduces_reference_collision():
+    from decode_tonal_langauge_b200.chains import FULL6_STEPS
+    from decode_tonal_langauge_b200.preprocessor import preprocess_signal
+    x = np.random.default_rng(0).standard_normal((2, 4000)).astype(np.float32)
+    with pytest.raises(ValueError, match="already exists"):
+        preprocess_signal(x, FULL6_STEPS, Namespace(signal_freq=2000), strict_params=True)
+
+
+def test_epochs_against_reference(golden):
+    from decode_tonal_langauge_b200 import epochs as E
+    e = golden("epochs")
+    intervals, rec = {}, {}
+    for b in (1, 2):
+        intervals[b] = {"start": e[f"b{b}_start"], "tone": e[f"b{b}_tone"],
+                        "syllable": [str(s) for s in e[f"b{b}_syllable"]]}
+        rec[b] = {"ecog": (e[f"b{b}_ecog"], e["ecog_sf"][()]), "audio": (e[f"b{b}_audio"], e["audio_sf"][()])}
+    out = E.extract_epochs(intervals, rec, ["i", "a"], 1.0, (0.0, 5.0))
+    order = [int(str(f)[1]) for f in e["listdir"] if "sound" in str(f)]
+    n = len(e["b1_start"])
+    perm = np.concatenate([np.arange(n) + n * (b - 1) for b in order])
+    assert np.array_equal(out["ecog"][perm], e["ref_ecog"]) and out["ecog"].dtype == e["ref_ecog"].dtype
+    assert np.array_equal(out["audio"][perm], e["ref_audio"])
+    assert np.array_equal(out["syllable"][perm], e["ref_syllable"]) and out["syllable"].dtype == np.int8
+    assert np.array_equal(out["tone"][perm], e["ref_tone"])
+    assert out["ecog_rest"].shape == e["ref_ecog_rest"].shape
+    assert np.array_equal(np.sort(out["ecog_rest"].ravel()), np.sort(e["ref_ecog_rest"].ravel()))
+    with pytest.raises(ValueError, match="exceeds"):
+        E.extract_epochs({1: {"start": np.array([39.5]), "tone": np.array([1]), "syllable": ["i"]}},
+                         {1: rec[1]}, ["i", "a"], 1.0, None)
+    with pytest.raises(ValueError, match="Mismatch"):
+        E.extract_epochs(intervals, {1: rec[1], 2: {"ecog": rec[2]["ecog"]}}, ["i", "a"])
+
+
+def test_extract_ecog_audio_files(golden, tmp_path):
+    from decode_tonal_langauge_b200 import epochs as E
+    e = golden("epochs")
+    intervals = {}
+    for b in (1, 2):
+        np.savez(tmp_path / f"B{b}_ecog.npz", data=e[f"b{b}_ecog"], sf=e["ecog_sf"])
+        np.savez(tmp_path / f"B{b}_sound.npz", data=e[f"b{b}_audio"], sf=e["audio_sf"])
+        intervals[b] = {"start": e[f"b{b}_start"], "tone": e[f"b{b}_tone"],
+                        "syllable": [str(s) for s in e[f"b{b}_syllable"]]}
+    out_path = tmp_path / "subject_1.npz"
+    out = E.extract_ecog_audio(intervals, str(tmp_path), ["i", "a"], 1.0, str(out_path), (0.0, 5.0))
+    saved = np.load(out_path)
+    assert set(saved.keys()) == {"ecog", "ecog_sf", "audio", "audio_sf", "syllable", "tone", "ecog_rest"}
+    assert np.array_equal(saved["ecog"], out["ecog"]) and saved["ecog"].shape == e["ref_ecog"].shape
+    assert np.array_equal(np.sort(saved["ecog"].ravel()), np.sort(e["ref_ecog"].ravel()))
+
+
+def test_selection_against_reference(golden):
+    from decode_tonal_langauge_b200 import selection as SEL
+    s = golden("selection")
+    data = {k: s[k] for k in ("ecog", "ecog_rest", "ecog_sf", "tone", "syllable")}
+    for target in ("tone", "syllable"):
+        for key in ("target", "label"):                          # Appendix B3: both spellings
+            r = SEL.discriminative_run(data, {"p_threshold": 0.01, "active_time_threshold": 0.1, key: target})
+            assert r["selected_channels"] == s[f"disc_{target}_selected"].tolist()
+            assert all(type(c) is int for c in r["selected_channels"]) and r["max_lengths"] == []
+        P, Pr = r["p_values"], s[f"disc_{target}_p"]
+        assert np.array_equal(np.isnan(P), np.isnan(Pr))
+        ok = np.isfinite(Pr) & (Pr > 1e-300)
+        assert np.max(np.abs(np.log10(P[ok]) - np.log10(Pr[ok]))) < 1e-4
+    r = SEL.active_run(data, {"p_threshold": 0.01, "active_time_threshold": 0.1})
+    assert r["selected_channels"] == s["active_selected"].tolist()
+    assert r["max_lengths"] == s["active_max_lengths"].tolist()
+    ok = s["active_p_last"] > 1e-300
+    assert np.max(np.abs(np.log10(r["p_values"][ok]) - np.log10(s["active_p_last"][ok]))) < 1e-4
+    with pytest.raises(KeyError):
+        SEL.discriminative_run(data, {"active_time_threshold": 0.1, "target": "nope"})
+    with pytest.raises(ValueError):
+        SEL.discriminative_run({**data, "tone": data["tone"].astype(np.float64)},
+                               {"active_time_threshold": 0.1, "target": "tone"})
+
+
+def test_full_size_properties():
+    """Size-independent properties at a BASELINE-scale row count (one 60-min row would not
+    finish on the CPU oracle in test time): linearity of the linear steps, CAR idempotence,
+    z-score moments, resample of a band-limited tone."""
+    from decode_tonal_langauge_b200 import ops
+    C, T, fs = 8, 7_200_000, 2000.0
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn((C, T), generator=g, device="cuda") * 30
+    b = torch.randn((C, T), generator=g, device="cuda") * 30
+    fa, fb = ops.butter(a, [70, 150], fs), ops.butter(b, [70, 150], fs)
+    fab = ops.butter(a + 2 * b, [70, 150], fs)
+    scale = fab.abs().max().item()
+    assert (fab - (fa + 2 * fb)).abs().max().item() / scale < 2e-6
+    ca = ops.car(a)
+    assert ca.mean(dim=0).abs().max().item() < 1e-4
+    assert (ops.car(ca) - ca).abs().max().item() < 1e-4
+    z = ops.zscore(fa)
+    assert z.mean(dim=1, dtype=torch.float64).abs().max().item() < 1e-6
+    assert (z.to(torch.float64).std(dim=1, unbiased=False) - 1).abs().max().item() < 1e-6
+    t = torch.arange(T, device="cuda", dtype=torch.float64) / fs
+    tone = torch.sin(2 * np.pi * 37.0 * t).to(torch.float32)[None].repeat(2, 1)     # periodic over the row
+    y = ops.fft_resample(tone, T // 5)
+    t2 = torch.arange(T // 5, device="cuda", dtype=torch.float64) / 400.0
+    assert (y[0].to(torch.float64) - torch.sin(2 * np.pi * 37.0 * t2)).abs().max().item() < 1e-5
+    env = ops.hilbert(tone, fs, [30.0, 45.0])
+    assert env.shape == tone.shape and torch.isfinite(env).all()
