@@ -32,7 +32,16 @@ def test_step_modules_numpy_contract(golden):
         {"method": "butter", "params": {"freqs": [0.3, 100], "filter_type": "bandpass"}}])
     y = S.frequency_filter(x, p)
     assert y.dtype == np.float64 and y.shape == g["two_bands"].shape
-    assert max_rel(y, g["two_bands"]) < TOL
+    C = x.shape[0]
+    assert max_rel(y[:C], g["two_bands"][:C]) < TOL
+    # 0.3-100 Hz at 2 kHz puts poles at radius 0.9996: the reference's float64 direct form is
+    # 0.9 % away from the extended-precision evaluation of its own algorithm (section 8c rule)
+    from oracle import steps as OS
+    from decode_tonal_langauge_b200 import design as D
+    d = D.butter_design([0.3, 100], fs, 4, False, "bandpass")
+    truth = OS.filtfilt_pad(d.b, d.a, x, dtype=np.longdouble)
+    err_gpu, err_ref = max_rel(y[C:], truth), max_rel(g["two_bands"][C:], truth)
+    assert err_gpu <= max(TOL, err_ref) and err_gpu < TOL, (err_gpu, err_ref)
     p = Namespace(signal_freq=fs)
     y = S.car_rereference(x, p)
     assert p.exclude_channels == [] and y.dtype == np.float32 and max_rel(y, g["car"]) < 2e-6
