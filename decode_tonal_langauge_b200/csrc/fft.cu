@@ -8,8 +8,9 @@
 //   pass B : view the intermediate as an (n_b x n_a) matrix, FFT along axis 0 again,
 //            store in place layout -> natural order X[q + n_a p].
 // The in-shared-memory FFT is an in-place mixed-radix (2,3,4,5) decimation-in-time
-// transform; the digit reversal is applied for free when the tile rows are loaded
-// (each row is an independent 64-byte segment).  Root-of-unity tables are built by the host
+// transform; two stages are fused per shared-memory sweep (radix-16/20/25/... "super
+// butterflies" held in registers); the digit reversal is applied for free when the tile
+// rows are loaded (each row is an independent 32/64-byte segment).  Root-of-unity tables are built by the host
 // in float64 and rounded once (decode_tonal_langauge_b200/fftplan.py).
 // The repack kernel turns Z into rfft bins, applies resample's truncation / Nyquist rule and
 // folds the half spectrum for the inverse real transform, which runs as a conjugated forward
@@ -20,14 +21,15 @@
 namespace ecog {
 
 constexpr int kFftThreads = 256;
-constexpr int kW = 8;             // tile width (columns): 64-byte row segments
-constexpr int kWp = kW + 1;       // padded pitch (float2)
 constexpr int kBigShift = 12;     // two-level twiddle split: e = hi * 4096 + lo
 
+// One shared-memory sweep = one or two fused DIT stages done in registers.
 struct AxisDev {
-    int n, nstage;
-    int radix[16], lprev[16], twstride[16];
-    unsigned magic[16];           // ceil(2^32 / lprev): floor(b / lprev) == __umulhi(b, magic) for b < 2^16
+    int n, npass;
+    int ra[16], rb[16];           // radices of the fused stage pair (rb == 1: single stage)
+    int lprev[16];                // sub-transform length before the pass
+    int tws_a[16], tws_b[16];     // table strides n / L_t, n / L_{t+1}
+    unsigned magic[16];           // ceil(2^32 / lprev)
 };
 
 struct PassParams {
@@ -52,84 +54,132 @@ __device__ __forceinline__ float2 caddf(float2 a, float2 b) { return make_float2
 __device__ __forceinline__ float2 csubf(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 __device__ __forceinline__ float2 mulmi(float2 a) { return make_float2(a.y, -a.x); }   // * (-i)
 
+// forward R-point DFT on a[0], a[S], a[2S], ... (register array, compile-time indices)
+template <int R, int S>
+__device__ __forceinline__ void bfly(float2* a) {
+    if (R == 2) {
+        float2 x0 = a[0], x1 = a[S];
+        a[0] = caddf(x0, x1); a[S] = csubf(x0, x1);
+    } else if (R == 3) {
+        const float S3 = 0.86602540378443865f;
+        float2 x0 = a[0], x1 = a[S], x2 = a[2 * S];
+        float2 t1 = caddf(x1, x2);
+        float2 t2 = make_float2(fmaf(-0.5f, t1.x, x0.x), fmaf(-0.5f, t1.y, x0.y));
+        float2 d = csubf(x1, x2);
+        float2 t3 = make_float2(S3 * d.y, -S3 * d.x);                       // -i * S3 * d
+        a[0] = caddf(x0, t1); a[S] = caddf(t2, t3); a[2 * S] = csubf(t2, t3);
+    } else if (R == 4) {
+        float2 x0 = a[0], x1 = a[S], x2 = a[2 * S], x3 = a[3 * S];
+        float2 t0 = caddf(x0, x2), t1 = csubf(x0, x2), t2 = caddf(x1, x3), t3 = mulmi(csubf(x1, x3));
+        a[0] = caddf(t0, t2); a[S] = caddf(t1, t3); a[2 * S] = csubf(t0, t2); a[3 * S] = csubf(t1, t3);
+    } else if (R == 5) {
+        const float C1 = 0.30901699437494742f, C2 = -0.80901699437494742f;
+        const float S1 = 0.95105651629515357f, S2 = 0.58778525229247313f;
+        float2 x0 = a[0], x1 = a[S], x2 = a[2 * S], x3 = a[3 * S], x4 = a[4 * S];
+        float2 t1 = caddf(x1, x4), t2 = caddf(x2, x3), t3 = csubf(x1, x4), t4 = csubf(x2, x3);
+        float2 m1 = make_float2(fmaf(C2, t2.x, fmaf(C1, t1.x, x0.x)), fmaf(C2, t2.y, fmaf(C1, t1.y, x0.y)));
+        float2 m2 = make_float2(fmaf(C1, t2.x, fmaf(C2, t1.x, x0.x)), fmaf(C1, t2.y, fmaf(C2, t1.y, x0.y)));
+        float2 u1 = make_float2(fmaf(S2, t4.x, S1 * t3.x), fmaf(S2, t4.y, S1 * t3.y));
+        float2 u2 = make_float2(fmaf(-S1, t4.x, S2 * t3.x), fmaf(-S1, t4.y, S2 * t3.y));
+        float2 n1 = mulmi(u1), n2 = mulmi(u2);
+        a[0] = make_float2(x0.x + t1.x + t2.x, x0.y + t1.y + t2.y);
+        a[S] = caddf(m1, n1); a[4 * S] = csubf(m1, n1);
+        a[2 * S] = caddf(m2, n2); a[3 * S] = csubf(m2, n2);
+    }
+}
+
+// Two fused DIT stages (radix RA then radix RB) of one column, all in registers.
+//   elements  base + qa*lp + qb*Lt   (Lt = lp*RA),  base = g*Lt*RB + j,  j < lp
+template <int RA, int RB, int WP>
+__device__ __forceinline__ void super_bfly(float2* col, int g, int j, int lp, const float2* __restrict__ tw,
+                                           int tws_a, int tws_b) {
+    const int Lt = lp * RA;
+    float2 a[RA * RB];                       // a[qa * RB + qb]
+    float2* e0 = col + (g * Lt * RB + j) * WP;
+#pragma unroll
+    for (int qb = 0; qb < RB; ++qb)
+#pragma unroll
+        for (int qa = 0; qa < RA; ++qa) a[qa * RB + qb] = e0[(qa * lp + qb * Lt) * WP];
+    if (j) {
+#pragma unroll
+        for (int qa = 1; qa < RA; ++qa) {
+            const float2 w = __ldg(&tw[j * qa * tws_a]);
+#pragma unroll
+            for (int qb = 0; qb < RB; ++qb) a[qa * RB + qb] = cmulf(a[qa * RB + qb], w);
+        }
+    }
+#pragma unroll
+    for (int qb = 0; qb < RB; ++qb) bfly<RA, RB>(a + qb);              // over qa, stride RB
+    if (RB > 1) {
+#pragma unroll
+        for (int pa = 0; pa < RA; ++pa) {
+            const int jp = j + pa * lp;
+            if (jp) {
+#pragma unroll
+                for (int qb = 1; qb < RB; ++qb)
+                    a[pa * RB + qb] = cmulf(a[pa * RB + qb], __ldg(&tw[jp * qb * tws_b]));
+            }
+            bfly<RB, 1>(a + pa * RB);                                  // over qb, stride 1
+        }
+    }
+#pragma unroll
+    for (int pb = 0; pb < RB; ++pb)
+#pragma unroll
+        for (int pa = 0; pa < RA; ++pa) e0[(pa * lp + pb * Lt) * WP] = a[pa * RB + pb];
+}
+
+template <int W>
 __global__ void __launch_bounds__(kFftThreads)
 fft_tile_kernel(const PassParams P) {
-    extern __shared__ __align__(16) float2 tile[];      // [n][kWp]
+    constexpr int WP = W + 1;                           // padded pitch (float2)
+    constexpr int LOGW = W == 8 ? 3 : 2;
+    extern __shared__ __align__(16) float2 tile[];      // [n][WP]
     const int tid = threadIdx.x;
     const int n = P.n, m = P.m;
-    const int c0 = blockIdx.x * kW;
+    const int c0 = blockIdx.x * W;
     const float2* in = P.in + (long long)blockIdx.y * P.in_ch_stride;
     float2* out = P.out + (long long)blockIdx.y * P.out_ch_stride;
-    const int cw = m - c0 < kW ? m - c0 : kW;           // valid columns in this tile
+    const int cw = m - c0 < W ? m - c0 : W;             // valid columns in this tile
 
     // ---- load: row i (cw contiguous complex) -> tile[perm[i]]
-    for (int idx = tid; idx < n * kW; idx += kFftThreads) {
-        const int i = idx >> 3, c = idx & (kW - 1);
+    for (int idx = tid; idx < n * W; idx += kFftThreads) {
+        const int i = idx >> LOGW, c = idx & (W - 1);
         float2 v = make_float2(0.f, 0.f);
         if (c < cw) {
             v = in[(long long)i * m + c0 + c];
             if (P.conj_in) v.y = -v.y;
         }
-        tile[__ldg(&P.perm[i]) * kWp + c] = v;
+        tile[__ldg(&P.perm[i]) * WP + c] = v;
     }
     __syncthreads();
 
-    // ---- in-place DIT stages
-    for (int s = 0; s < P.ax.nstage; ++s) {
-        const int r = P.ax.radix[s], lp = P.ax.lprev[s], tws = P.ax.twstride[s];
+    // ---- in-place DIT: one shared-memory sweep per fused stage pair
+    for (int s = 0; s < P.ax.npass; ++s) {
+        const int ra = P.ax.ra[s], rb = P.ax.rb[s], lp = P.ax.lprev[s];
+        const int ta = P.ax.tws_a[s], tb = P.ax.tws_b[s];
         const unsigned magic = P.ax.magic[s];
-        const int nbf = n / r;                           // butterflies per column
-        for (int w = tid; w < nbf * kW; w += kFftThreads) {
-            const int c = w & (kW - 1);
-            const int b = w >> 3;
+        const int nsb = n / (ra * rb);                   // super-butterflies per column
+        const int code = ra * 8 + rb;
+        for (int w = tid; w < nsb * W; w += kFftThreads) {
+            const int c = w & (W - 1);
+            const int b = w >> LOGW;
             const int g = lp == 1 ? b : (int)__umulhi((unsigned)b, magic);
             const int j = b - g * lp;
-            float2* e0 = tile + (g * lp * r + j) * kWp + c;
-            const int step = lp * kWp;
-            if (r == 4) {
-                float2 a0 = e0[0], a1 = e0[step], a2 = e0[2 * step], a3 = e0[3 * step];
-                if (j) {
-                    a1 = cmulf(a1, __ldg(&P.tw[j * tws]));
-                    a2 = cmulf(a2, __ldg(&P.tw[2 * j * tws]));
-                    a3 = cmulf(a3, __ldg(&P.tw[3 * j * tws]));
-                }
-                float2 t0 = caddf(a0, a2), t1 = csubf(a0, a2), t2 = caddf(a1, a3), t3 = mulmi(csubf(a1, a3));
-                e0[0] = caddf(t0, t2); e0[step] = caddf(t1, t3);
-                e0[2 * step] = csubf(t0, t2); e0[3 * step] = csubf(t1, t3);
-            } else if (r == 2) {
-                float2 a0 = e0[0], a1 = e0[step];
-                if (j) a1 = cmulf(a1, __ldg(&P.tw[j * tws]));
-                e0[0] = caddf(a0, a1); e0[step] = csubf(a0, a1);
-            } else if (r == 3) {
-                float2 a0 = e0[0], a1 = e0[step], a2 = e0[2 * step];
-                if (j) {
-                    a1 = cmulf(a1, __ldg(&P.tw[j * tws]));
-                    a2 = cmulf(a2, __ldg(&P.tw[2 * j * tws]));
-                }
-                const float S3 = 0.86602540378443865f;
-                float2 t1 = caddf(a1, a2);
-                float2 t2 = make_float2(a0.x - 0.5f * t1.x, a0.y - 0.5f * t1.y);
-                float2 d = csubf(a1, a2);
-                float2 t3 = mulmi(make_float2(S3 * d.x, S3 * d.y));
-                e0[0] = caddf(a0, t1); e0[step] = caddf(t2, t3); e0[2 * step] = csubf(t2, t3);
-            } else {   // r == 5
-                float2 a0 = e0[0], a1 = e0[step], a2 = e0[2 * step], a3 = e0[3 * step], a4 = e0[4 * step];
-                if (j) {
-                    a1 = cmulf(a1, __ldg(&P.tw[j * tws]));
-                    a2 = cmulf(a2, __ldg(&P.tw[2 * j * tws]));
-                    a3 = cmulf(a3, __ldg(&P.tw[3 * j * tws]));
-                    a4 = cmulf(a4, __ldg(&P.tw[4 * j * tws]));
-                }
-                const float C1 = 0.30901699437494742f, C2 = -0.80901699437494742f;
-                const float S1 = 0.95105651629515357f, S2 = 0.58778525229247313f;
-                float2 t1 = caddf(a1, a4), t2 = caddf(a2, a3), t3 = csubf(a1, a4), t4 = csubf(a2, a3);
-                float2 m1 = make_float2(a0.x + C1 * t1.x + C2 * t2.x, a0.y + C1 * t1.y + C2 * t2.y);
-                float2 m2 = make_float2(a0.x + C2 * t1.x + C1 * t2.x, a0.y + C2 * t1.y + C1 * t2.y);
-                float2 n1 = mulmi(make_float2(S1 * t3.x + S2 * t4.x, S1 * t3.y + S2 * t4.y));   // -i n1
-                float2 n2 = mulmi(make_float2(S2 * t3.x - S1 * t4.x, S2 * t3.y - S1 * t4.y));   // -i n2
-                e0[0] = make_float2(a0.x + t1.x + t2.x, a0.y + t1.y + t2.y);
-                e0[step] = caddf(m1, n1); e0[4 * step] = csubf(m1, n1);
-                e0[2 * step] = caddf(m2, n2); e0[3 * step] = csubf(m2, n2);
+            float2* col = tile + c;
+            switch (code) {
+                case 4 * 8 + 4: super_bfly<4, 4, WP>(col, g, j, lp, P.tw, ta, tb); break;
+                case 4 * 8 + 2: super_bfly<4, 2, WP>(col, g, j, lp, P.tw, ta, tb); break;
+                case 4 * 8 + 3: super_bfly<4, 3, WP>(col, g, j, lp, P.tw, ta, tb); break;
+                case 4 * 8 + 5: super_bfly<4, 5, WP>(col, g, j, lp, P.tw, ta, tb); break;
+                case 2 * 8 + 3: super_bfly<2, 3, WP>(col, g, j, lp, P.tw, ta, tb); break;
+                case 2 * 8 + 5: super_bfly<2, 5, WP>(col, g, j, lp, P.tw, ta, tb); break;
+                case 3 * 8 + 3: super_bfly<3, 3, WP>(col, g, j, lp, P.tw, ta, tb); break;
+                case 3 * 8 + 5: super_bfly<3, 5, WP>(col, g, j, lp, P.tw, ta, tb); break;
+                case 5 * 8 + 5: super_bfly<5, 5, WP>(col, g, j, lp, P.tw, ta, tb); break;
+                case 2 * 8 + 1: super_bfly<2, 1, WP>(col, g, j, lp, P.tw, ta, tb); break;
+                case 3 * 8 + 1: super_bfly<3, 1, WP>(col, g, j, lp, P.tw, ta, tb); break;
+                case 4 * 8 + 1: super_bfly<4, 1, WP>(col, g, j, lp, P.tw, ta, tb); break;
+                default:        super_bfly<5, 1, WP>(col, g, j, lp, P.tw, ta, tb); break;
             }
         }
         __syncthreads();
@@ -137,11 +187,11 @@ fft_tile_kernel(const PassParams P) {
 
     // ---- store
     if (P.transposed) {
-        // out[(c0 + c) * n + q]: contiguous along q; pitch 9 keeps the shared reads conflict free
+        // out[(c0 + c) * n + q]: contiguous along q; the odd pitch keeps the shared reads conflict free
         for (int c = 0; c < cw; ++c) {
             const long long col = c0 + c;
             for (int q = tid; q < n; q += kFftThreads) {
-                float2 v = tile[q * kWp + c];
+                float2 v = tile[q * WP + c];
                 if (P.twiddle) {
                     const long long e = (long long)q * col;              // < N
                     const float2 wh = __ldg(&P.tw_hi[e >> kBigShift]);
@@ -152,10 +202,10 @@ fft_tile_kernel(const PassParams P) {
             }
         }
     } else {
-        for (int idx = tid; idx < n * kW; idx += kFftThreads) {
-            const int q = idx >> 3, c = idx & (kW - 1);
+        for (int idx = tid; idx < n * W; idx += kFftThreads) {
+            const int q = idx >> LOGW, c = idx & (W - 1);
             if (c < cw && (q <= P.keep_lo || q >= P.keep_hi)) {
-                float2 v = tile[q * kWp + c];
+                float2 v = tile[q * WP + c];
                 v.x *= P.scale; v.y *= P.conj_out ? -P.scale : P.scale;
                 out[(long long)q * m + c0 + c] = v;
             }
@@ -197,30 +247,56 @@ resample_repack_kernel(const float2* __restrict__ Z, float2* __restrict__ G, lon
     G[(long long)blockIdx.y * g_stride + k] = make_float2(E.x - O.y, E.y + O.x);
 }
 
+static bool pair_ok(int ra, int rb) {
+    const int code = ra * 8 + rb;
+    switch (code) {
+        case 4 * 8 + 4: case 4 * 8 + 2: case 4 * 8 + 3: case 4 * 8 + 5: case 2 * 8 + 3:
+        case 2 * 8 + 5: case 3 * 8 + 3: case 3 * 8 + 5: case 5 * 8 + 5: return true;
+        default: return false;
+    }
+}
+
+// stages (radix list, DIT order) -> fused passes
 static int fill_axis(const ecog_fft_axis& a, AxisDev& d) {
     if (a.n < 1 || a.nstage < 0 || a.nstage > 16) return fail(ECOG_E_VALUE, "fft axis: bad plan n=%d nstage=%d", a.n, a.nstage);
-    d.n = a.n; d.nstage = a.nstage;
+    memset(&d, 0, sizeof(d));
+    d.n = a.n;
     long long L = 1;
-    for (int s = 0; s < a.nstage; ++s) {
-        const int r = a.radix[s];
-        if (r != 2 && r != 3 && r != 4 && r != 5) return fail(ECOG_E_VALUE, "fft axis: radix %d not supported", r);
-        d.radix[s] = r; d.lprev[s] = (int)L;
-        d.magic[s] = (unsigned)((0x100000000ull + (unsigned long long)L - 1) / (unsigned long long)L);
-        L *= r;
-        d.twstride[s] = (int)(a.n / L);
+    int s = 0, np = 0;
+    while (s < a.nstage) {
+        const int ra = a.radix[s];
+        if (ra != 2 && ra != 3 && ra != 4 && ra != 5) return fail(ECOG_E_VALUE, "fft axis: radix %d not supported", ra);
+        int rb = 1;
+        if (s + 1 < a.nstage && pair_ok(ra, a.radix[s + 1])) rb = a.radix[s + 1];
+        d.ra[np] = ra; d.rb[np] = rb; d.lprev[np] = (int)L;
+        d.magic[np] = (unsigned)((0x100000000ull + (unsigned long long)L - 1) / (unsigned long long)L);
+        d.tws_a[np] = (int)(a.n / (L * ra));
+        d.tws_b[np] = (int)(a.n / (L * ra * rb));
+        L *= (long long)ra * rb;
+        s += rb > 1 ? 2 : 1;
+        ++np;
     }
+    d.npass = np;
     if (L != a.n) return fail(ECOG_E_VALUE, "fft axis: radices multiply to %lld, not n=%d", L, a.n);
-    if ((long long)a.n * kWp * (long long)sizeof(float2) > 220 * 1024)
+    if ((long long)a.n * 5 * (long long)sizeof(float2) > 220 * 1024)
         return fail(ECOG_E_UNSUPPORTED, "fft axis: n=%d does not fit shared memory", a.n);
     if (a.n / 2 >= 65536) return fail(ECOG_E_UNSUPPORTED, "fft axis: n=%d too long", a.n);
     return ECOG_OK;
 }
 
 static int launch_pass(PassParams& P, int64_t C, cudaStream_t st, const char* what) {
-    const size_t smem = (size_t)P.n * kWp * sizeof(float2);
-    ECOG_CUDA(cudaFuncSetAttribute(fft_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)ceil_div(P.m, kW), (unsigned)C);
-    fft_tile_kernel<<<grid, kFftThreads, smem, st>>>(P);
+    // 8-column tiles (64-byte segments) when two CTAs still fit an SM, else 4-column tiles
+    const size_t smem8 = (size_t)P.n * 9 * sizeof(float2), smem4 = (size_t)P.n * 5 * sizeof(float2);
+    const bool use8 = smem8 <= 100 * 1024 || smem4 > 110 * 1024 ? smem8 <= 220 * 1024 : false;
+    if (use8) {
+        ECOG_CUDA(cudaFuncSetAttribute(fft_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+        dim3 grid((unsigned)ceil_div(P.m, 8), (unsigned)C);
+        fft_tile_kernel<8><<<grid, kFftThreads, smem8, st>>>(P);
+    } else {
+        ECOG_CUDA(cudaFuncSetAttribute(fft_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        dim3 grid((unsigned)ceil_div(P.m, 4), (unsigned)C);
+        fft_tile_kernel<4><<<grid, kFftThreads, smem4, st>>>(P);
+    }
     return check_launch(what);
 }
 

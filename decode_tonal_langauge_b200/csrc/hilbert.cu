@@ -9,7 +9,11 @@
 //   - the two real blocks ride as real/imag parts of ONE forward complex FFT and are
 //     separated with the conjugate-symmetry split;
 //   - per band and block: multiply by the gain table, inverse FFT (as conj-forward),
-//     |.| (or real part) accumulated in registers -> mean over bands never leaves the SM.
+//     |.| (or real part) accumulated in registers -> mean over bands never leaves the SM;
+//   - a band occupies only a few hundred of the 2048 positive bins.  For the envelope the
+//     band is shifted down to bin 0 (|z| is invariant to a spectral shift), so only
+//     `rows` x 256 inputs of the inverse transform are non-zero and its first radix-16
+//     pass collapses to `rows` terms (rows = 1 for the high-gamma bank at 2 kHz).
 // FFT: 4096 = 16 x 16 x 16, each thread holds 16 points in registers, three radix-16
 // passes with two shared-memory exchanges (padded index i + i/16, conflict free).
 // The kernel is FP32-ALU/shared-memory bound (~9 FFTs per 4096 samples), NOT HBM bound:
@@ -66,19 +70,23 @@ __device__ __forceinline__ void dft16(float2 (&v)[16]) {
 // passes 2 and 3 of the 4096-point forward FFT; pass-1 output must already be in `buf`
 // (index padi(256 k0 + tid)).  Result: v[k2] = X[k0 + 16 k1 + 256 k2] with tid = 16 k0 + k1.
 __device__ __forceinline__ void fft4096_finish(float2 (&v)[16], float2* buf, const float2* __restrict__ tw2, int tid) {
+    float2 t2[16];
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) t2[k1] = __ldg(&tw2[k1 * kHT + tid]);   // in flight across the barrier
     __syncthreads();
     const int k0 = tid >> 4, n0 = tid & 15;
+    float2* p2 = buf + 272 * k0 + n0;            // padi(256 k0 + 16 n1 + n0) = 272 k0 + 17 n1 + n0
 #pragma unroll
-    for (int n1 = 0; n1 < 16; ++n1) v[n1] = buf[padi(256 * k0 + 16 * n1 + n0)];
+    for (int n1 = 0; n1 < 16; ++n1) v[n1] = p2[17 * n1];
     dft16(v);
 #pragma unroll
-    for (int k1 = 1; k1 < 16; ++k1) v[k1] = cmul(v[k1], __ldg(&tw2[k1 * kHT + tid]));
-    v[0] = cmul(v[0], __ldg(&tw2[tid]));
+    for (int k1 = 0; k1 < 16; ++k1) v[k1] = cmul(v[k1], t2[k1]);
 #pragma unroll
-    for (int k1 = 0; k1 < 16; ++k1) buf[padi(256 * k0 + 16 * k1 + n0)] = v[k1];
+    for (int k1 = 0; k1 < 16; ++k1) p2[17 * k1] = v[k1];
     __syncthreads();
+    const float2* p3 = buf + 17 * tid;           // padi(16 tid + j) = 17 tid + j
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = buf[padi(16 * tid + j)];
+    for (int j = 0; j < 16; ++j) v[j] = p3[j];
     dft16(v);
 }
 
@@ -87,17 +95,77 @@ __device__ __forceinline__ void fft4096_pass1(float2 (&v)[16], float2* buf, cons
     dft16(v);
 #pragma unroll
     for (int k0 = 1; k0 < 16; ++k0) v[k0] = cmul(v[k0], __ldg(&tw1[k0 * kHT + tid]));
+    float2* p1 = buf + tid + (tid >> 4);         // padi(256 k0 + tid) = 272 k0 + tid + tid/16
 #pragma unroll
-    for (int k0 = 0; k0 < 16; ++k0) buf[padi(256 * k0 + tid)] = v[k0];
+    for (int k0 = 0; k0 < 16; ++k0) p1[272 * k0] = v[k0];
 }
 
+// First radix-16 pass of an inverse transform whose input is non-zero only in rows
+// n2 < CNT (k = 256 n2 + tid): the band occupies CNT*256 consecutive bins after the
+// per-band spectral shift.  CNT = 1: A[k0] = v0;  2: v0 + W16^k0 v1;  4 / 8: the first
+// radix-4 layer of dft16 degenerates to copies / 2-point butterflies.
+template <int CNT>
+__device__ __forceinline__ void dft16_rows(float2 (&v)[16]) {
+    if (CNT == 1) {
+#pragma unroll
+        for (int k = 1; k < 16; ++k) v[k] = v[0];
+        return;
+    }
+    if (CNT == 2) {
+        const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
+        const float2 a = v[0], b = v[1];
+        const float wr[16] = {1.f, C1, C2, S1, 0.f, -S1, -C2, -C1, -1.f, -C1, -C2, -S1, 0.f, S1, C2, C1};
+        const float wi[16] = {0.f, -S1, -C2, -C1, -1.f, -C1, -C2, -S1, 0.f, S1, C2, C1, 1.f, C1, C2, S1};
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+            v[k] = make_float2(fmaf(wr[k], b.x, fmaf(-wi[k], b.y, a.x)), fmaf(wr[k], b.y, fmaf(wi[k], b.x, a.y)));
+        return;
+    }
+    const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
+    // stage 1: a[m][p] = sum_q v[m + 4q] W4^{qp}, only q < CNT/4 present; a[m][p] kept at v[m + 4p]
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        if (CNT == 4) {
+            v[m + 4] = v[m]; v[m + 8] = v[m]; v[m + 12] = v[m];
+        } else {   // CNT == 8: q in {0, 1}
+            const float2 x0 = v[m], x1 = v[m + 4];
+            v[m] = cadd(x0, x1); v[m + 8] = csub(x0, x1);
+            v[m + 4] = cadd(x0, mul_mi(x1)); v[m + 12] = csub(x0, mul_mi(x1));
+        }
+    }
+    v[1 + 4] = cmul(v[1 + 4], make_float2(C1, -S1));
+    v[1 + 8] = cmul(v[1 + 8], make_float2(C2, -C2));
+    v[1 + 12] = cmul(v[1 + 12], make_float2(S1, -C1));
+    v[2 + 4] = cmul(v[2 + 4], make_float2(C2, -C2));
+    v[2 + 8] = mul_mi(v[2 + 8]);
+    v[2 + 12] = cmul(v[2 + 12], make_float2(-C2, -C2));
+    v[3 + 4] = cmul(v[3 + 4], make_float2(S1, -C1));
+    v[3 + 8] = cmul(v[3 + 8], make_float2(-C2, -C2));
+    v[3 + 12] = cmul(v[3 + 12], make_float2(-C1, S1));
+#pragma unroll
+    for (int p = 0; p < 4; ++p) dft4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
+#pragma unroll
+    for (int p = 0; p < 4; ++p)
+#pragma unroll
+        for (int r = p + 1; r < 4; ++r) { float2 t = v[4 * p + r]; v[4 * p + r] = v[4 * r + p]; v[4 * r + p] = t; }
+}
+
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+struct BandShift { int s[64]; };
+
+template <int CNT>
 __global__ void __launch_bounds__(kHT, 2)
 hilbert_env_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t ldx, int64_t ldy,
-                   const float* __restrict__ gain, int nb, int halo, int envelope,
+                   const float* __restrict__ gain, int nb, BandShift shift, int halo, int envelope,
                    const float2* __restrict__ tw, int64_t nBlocks) {
     extern __shared__ __align__(16) float2 hsm[];
-    float2* bufA = hsm;                       // [4096 + 256]
-    float2* bufB = hsm + (kN + kN / 16);      // [4096 + 256]
+    float2* bufA = hsm;                       // [4096 + 256]  conj spectra of block 0 | block 1 (2048 each)
+    float2* bufB = hsm + (kN + kN / 16);      // [4096 + 256]  exchange buffer
     const int tid = threadIdx.x;
     const int64_t ch = blockIdx.y;
     const int U = kN - 2 * halo;
@@ -105,26 +173,36 @@ hilbert_env_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T
     const float* xr = x + ch * ldx;
     const float2* tw1 = tw;                 // [16][256] : W_256^{(tid>>4) k0}
     const float2* tw2 = tw + 16 * kHT;      // [16][256] : W_4096^{(tid&15)((tid>>4) + 16 k1)}
+    const int k0 = tid >> 4, k1 = tid & 15;
+    const int nat0 = k0 + 17 * k1;          // padi(k0 + 16 k1 + 256 k2) = nat0 + 272 k2
+    const int p1 = tid + k0;                // padi(256 r + tid)         = p1 + 272 r
 
     float2 v[16];
     {   // two real blocks as one complex signal, circular halo
         int64_t s0 = (b0 * U - halo) % T; if (s0 < 0) s0 += T;
         int64_t s1 = (b1 * U - halo) % T; if (s1 < 0) s1 += T;
         const bool has1 = b1 < nBlocks;
+        const bool wrap = (s0 + kN > T) || (s1 + kN > T);
+        if (!wrap) {
 #pragma unroll
-        for (int n2 = 0; n2 < 16; ++n2) {
-            const int i = 256 * n2 + tid;
-            v[n2].x = xr[(s0 + i) % T];
-            v[n2].y = has1 ? xr[(s1 + i) % T] : 0.f;
+            for (int n2 = 0; n2 < 16; ++n2) {
+                const int i = 256 * n2 + tid;
+                v[n2].x = xr[s0 + i];
+                v[n2].y = has1 ? xr[s1 + i] : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) {
+                const int i = 256 * n2 + tid;
+                v[n2].x = xr[(s0 + i) % T];
+                v[n2].y = has1 ? xr[(s1 + i) % T] : 0.f;
+            }
         }
     }
     fft4096_pass1(v, bufA, tw1, tid);
     fft4096_finish(v, bufA, tw2, tid);
-    {   // natural-order spectrum Z[k] -> bufB
-        const int k0 = tid >> 4, k1 = tid & 15;
 #pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) bufB[padi(k0 + 16 * k1 + 256 * k2)] = v[k2];
-    }
+    for (int k2 = 0; k2 < 16; ++k2) bufB[nat0 + 272 * k2] = v[k2];      // natural-order spectrum Z[k]
     __syncthreads();
     // conjugate-symmetry split (factor 1/2 folded into the gain table):
     //   block0: S0[k] = Z[k] + conj(Z[N-k]),  block1: S1[k] = -i (Z[k] - conj(Z[N-k]))
@@ -138,57 +216,63 @@ hilbert_env_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T
             const float2 a = make_float2(zk.x + zm.x, zk.y - zm.y);     // Z[k] + conj(Z[N-k])
             const float2 d = make_float2(zk.x - zm.x, zk.y + zm.y);     // Z[k] - conj(Z[N-k])
             s0 = make_float2(a.x, -a.y);                                 // conj(a)
-            s1 = make_float2(d.y, d.x);                                  // conj(-i d) = conj((d.y, -d.x))
+            s1 = make_float2(d.y, d.x);                                  // conj(-i d)
         }
         bufA[padi(k)] = s0;
         bufA[padi(kHalf + k)] = s1;
     }
     __syncthreads();
 
-    float acc0[16], acc1[16];
+    float* yr = y + ch * ldy;
+    for (int sel = 0; sel < 2; ++sel) {
+        float acc[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) { acc0[j] = 0.f; acc1[j] = 0.f; }
-
-    for (int band = 0; band < nb; ++band) {
-        const float* g = gain + (size_t)band * kHalf;
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        for (int band = 0; band < nb; ++band) {
+            const float* g = gain + (size_t)band * (CNT * 256);
+            const int sh = shift.s[band];
+            // band spectrum shifted down by sh bins: rows n2 < CNT only (|z| is shift invariant;
+            // sh = 0 when the real part is requested)
 #pragma unroll
-        for (int sel = 0; sel < 2; ++sel) {
-            // analytic spectrum: bins >= N/2 are zero
-#pragma unroll
-            for (int n2 = 0; n2 < 8; ++n2) {
-                const int k = 256 * n2 + tid;
-                const float gk = __ldg(&g[k]);
+            for (int n2 = 0; n2 < CNT; ++n2) {
+                const int j = 256 * n2 + tid;
+                const float gk = __ldg(&g[j]);
+                const int k = sh + j;                        // < 2048 by construction of the table
                 const float2 sv = bufA[padi(sel * kHalf + k)];
                 v[n2] = make_float2(sv.x * gk, sv.y * gk);
             }
+            float2 t1[16];
 #pragma unroll
-            for (int n2 = 8; n2 < 16; ++n2) v[n2] = make_float2(0.f, 0.f);
+            for (int e = 1; e < 16; ++e) t1[e] = __ldg(&tw1[e * kHT + tid]);
+            dft16_rows<CNT>(v);
+#pragma unroll
+            for (int e = 1; e < 16; ++e) v[e] = cmul(v[e], t1[e]);
             __syncthreads();                       // previous transform's pass-3 reads of bufB are done
-            fft4096_pass1(v, bufB, tw1, tid);
-            fft4096_finish(v, bufB, tw2, tid);
-            // v[k2] = conj(z[t]), t = k0 + 16 k1 + 256 k2
-            if (sel == 0) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc0[j] += envelope ? sqrtf(fmaf(v[j].x, v[j].x, v[j].y * v[j].y)) : v[j].x;
+            for (int e = 0; e < 16; ++e) bufB[p1 + 272 * e] = v[e];
+            fft4096_finish(v, bufB, tw2, tid);
+            // v[k2] = conj(z[t]) (times a unit phasor when shifted), t = k0 + 16 k1 + 256 k2
+            if (envelope) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] += fast_sqrt(fmaf(v[j].x, v[j].x, v[j].y * v[j].y));
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc1[j] += envelope ? sqrtf(fmaf(v[j].x, v[j].x, v[j].y * v[j].y)) : v[j].x;
+                for (int j = 0; j < 16; ++j) acc[j] += v[j].x;
             }
         }
-    }
-    __syncthreads();
-    {
-        const int k0 = tid >> 4, k1 = tid & 15;
+        __syncthreads();                           // all pass-3 reads of bufB done
+        float* ob = reinterpret_cast<float*>(bufB);   // natural order floats, pitch as padi
 #pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) bufB[padi(k0 + 16 * k1 + 256 * k2)] = make_float2(acc0[k2], acc1[k2]);
-    }
-    __syncthreads();
-    float* yr = y + ch * ldy;
-    for (int i = tid; i < U; i += kHT) {
-        const float2 r = bufB[padi(halo + i)];
-        const int64_t t0 = b0 * U + i, t1 = b1 * U + i;
-        if (t0 < T) yr[t0] = r.x;
-        if (b1 < nBlocks && t1 < T) yr[t1] = r.y;
+        for (int k2 = 0; k2 < 16; ++k2) ob[nat0 + 272 * k2] = acc[k2];
+        __syncthreads();
+        const int64_t bb = sel == 0 ? b0 : b1;
+        if (bb < nBlocks) {
+            for (int i = tid; i < U; i += kHT) {
+                const int64_t t = bb * U + i;
+                if (t < T) yr[t] = ob[padi(halo + i)];
+            }
+        }
+        __syncthreads();                           // ob is reused as the exchange buffer
     }
 }
 
@@ -216,19 +300,40 @@ extern "C" int ecog_hilbert_twiddles(float* h_out) {
 }
 
 extern "C" int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
-                                const float* d_gain, int32_t nbands, int32_t halo, int32_t envelope,
-                                const float* d_twiddle, ecog_stream_t stream) {
+                                const float* d_gain, int32_t nbands, int32_t rows, const int32_t* h_shift,
+                                int32_t halo, int32_t envelope, const float* d_twiddle, ecog_stream_t stream) {
     if (C <= 0 || T <= 0 || ldx < T || ldy < T || C > 65535) return fail(ECOG_E_VALUE, "ecog_hilbert_env: bad shape");
-    if (nbands < 1) return fail(ECOG_E_VALUE, "ecog_hilbert_env: no bands");
+    if (nbands < 1 || nbands > 64) return fail(ECOG_E_VALUE, "ecog_hilbert_env: 1..64 bands supported, got %d", nbands);
+    if (rows != 1 && rows != 2 && rows != 4 && rows != 8)
+        return fail(ECOG_E_VALUE, "ecog_hilbert_env: rows must be 1, 2, 4 or 8 (got %d)", rows);
     if (halo < 0 || 2 * halo >= kN / 2)
         return fail(ECOG_E_UNSUPPORTED, "ecog_hilbert_env: halo %d does not fit a %d-sample block", halo, kN);
     if (d_x == d_y) return fail(ECOG_E_VALUE, "ecog_hilbert_env: in-place operation is not supported");
+    BandShift sh;
+    for (int b = 0; b < 64; ++b) {
+        sh.s[b] = (b < nbands && h_shift) ? h_shift[b] : 0;
+        if (sh.s[b] < 0 || sh.s[b] + rows * 256 > kHalf)
+            return fail(ECOG_E_VALUE, "ecog_hilbert_env: band %d shift %d leaves the half spectrum", b, sh.s[b]);
+        if (!envelope && sh.s[b] != 0)
+            return fail(ECOG_E_VALUE, "ecog_hilbert_env: spectral shifts are only valid for the envelope");
+    }
     const int U = kN - 2 * halo;
     const int64_t nBlocks = ceil_div(T, U);
     dim3 grid((unsigned)ceil_div(nBlocks, 2), (unsigned)C);
     const size_t smem = (size_t)2 * (kN + kN / 16) * sizeof(float2);
-    ECOG_CUDA(cudaFuncSetAttribute(hilbert_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    hilbert_env_kernel<<<grid, kHT, smem, (cudaStream_t)stream>>>(
-        d_x, d_y, T, ldx, ldy, d_gain, nbands, halo, envelope, reinterpret_cast<const float2*>(d_twiddle), nBlocks);
+    const float2* tw = reinterpret_cast<const float2*>(d_twiddle);
+    cudaStream_t st = (cudaStream_t)stream;
+#define ECOG_HILBERT_LAUNCH(R)                                                                                   \
+    do {                                                                                                         \
+        ECOG_CUDA(cudaFuncSetAttribute(hilbert_env_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                       (int)smem));                                                              \
+        hilbert_env_kernel<R><<<grid, kHT, smem, st>>>(d_x, d_y, T, ldx, ldy, d_gain, nbands, sh, halo, envelope, \
+                                                       tw, nBlocks);                                             \
+    } while (0)
+    if (rows == 1) ECOG_HILBERT_LAUNCH(1);
+    else if (rows == 2) ECOG_HILBERT_LAUNCH(2);
+    else if (rows == 4) ECOG_HILBERT_LAUNCH(4);
+    else ECOG_HILBERT_LAUNCH(8);
+#undef ECOG_HILBERT_LAUNCH
     return check_launch("hilbert_env");
 }

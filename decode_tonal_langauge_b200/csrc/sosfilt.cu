@@ -11,11 +11,11 @@
 //   3. main  : every chunk is re-run from its true start state and writes float32.
 // The backward sweep repeats 1-3 on the forward result, in place, time reversed.
 //
-// Data movement: 512 chunks per CTA; 16-sample time tiles of all 512 chunks are
-// staged through shared memory with a 3-deep cp.async ring (64 B per chunk per
-// stage, coalesced), each thread reads its own tile row with conflict-free 128-bit
-// shared loads (row pitch 20 words), results go back through a shared tile and are
-// stored with 128-bit coalesced writes.  Arithmetic is FP64-pipe bound
+// Data movement: 512 chunks per CTA, two CTAs per SM; 16-sample time tiles of all 512
+// chunks are staged through shared memory with a double-buffered cp.async pipeline
+// (64 B per chunk per stage, coalesced), each thread reads its own tile row with
+// conflict-free 128-bit shared loads (row pitch 20 words), overwrites it with the results,
+// and the tile is stored with 128-bit coalesced writes.  Arithmetic is FP64-pipe bound
 // (5 DFMA per biquad per sample + 2 conversions), see DESIGN.md.
 #include "common.cuh"
 
@@ -24,7 +24,7 @@ namespace ecog {
 constexpr int kSosThreads = 512;
 constexpr int kSub = 16;              // samples per stage per chunk
 constexpr int kPitch = kSub + 4;      // shared row pitch in floats (conflict-free LDS.128)
-constexpr int kRing = 3;
+constexpr int kRing = 2;
 
 struct SosCoef {
     double c[ECOG_MAX_SECTIONS][5];   // b0 b1 b2 a1 a2
@@ -47,15 +47,15 @@ __device__ __forceinline__ double sos_step(double u, const double (&c)[NSEC][5],
 // WRITE=false: tail pass (zero state, last `tail` samples, end state -> slot k+1)
 // WRITE=true : main pass (state from slot k, float32 output)
 template <int NSEC, bool REV, bool WRITE, bool VEC>
-__global__ void __launch_bounds__(kSosThreads, 1)
+__global__ void __launch_bounds__(kSosThreads, 2)
 sos_chunk_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, int64_t T,
                  int64_t ldx, int64_t ldy, int L, int tail, int nChunks, int padlen,
-                 SosCoef coef, double* __restrict__ state, double* __restrict__ padbuf) {
+                 SosCoef coef, double* __restrict__ state, double* __restrict__ gbuf,
+                 double* __restrict__ padbuf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* in_tile = reinterpret_cast<float*>(smem_raw);                       // [kRing][512][kPitch]
-    float* out_tile = in_tile + (size_t)kRing * kSosThreads * kPitch;          // [512][kPitch]
-    int64_t* gbase = reinterpret_cast<int64_t*>(out_tile + (size_t)kSosThreads * kPitch);  // [512] row*ld
-    int* cstart = reinterpret_cast<int*>(gbase + kSosThreads);                 // [512] chunk edge (a or b) - may exceed int? no: < 2^31 checked on host
+    float* tiles = reinterpret_cast<float*>(smem_raw);                         // [kRing][512][kPitch]
+    int64_t* gbase = reinterpret_cast<int64_t*>(tiles + (size_t)kRing * kSosThreads * kPitch);  // [512] row
+    int* cstart = reinterpret_cast<int*>(gbase + kSosThreads);                 // [512] chunk edge a (fwd) / b (rev)
     int* clen = cstart + kSosThreads;                                          // [512]
 
     const int tid = threadIdx.x;
@@ -94,7 +94,7 @@ sos_chunk_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, 
     // cooperative stage loader: VEC -> 4 pieces of 16 B per row, else 16 pieces of 4 B
     auto issue = [&](int stage) {
         if (stage < nStages) {
-            float* dst = in_tile + (size_t)(stage % kRing) * kSosThreads * kPitch;
+            float* dst = tiles + (size_t)(stage % kRing) * kSosThreads * kPitch;
             if (VEC) {
                 for (int i = tid; i < kSosThreads * 4; i += kSosThreads) {
                     const int r = i >> 2, p = i & 3;
@@ -120,24 +120,28 @@ sos_chunk_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, 
         cp_async_commit();
     };
 
-    for (int st = first; st < first + kRing; ++st) issue(st);
-
+    issue(first);
     const int mylen = clen[tid];
     for (int st = first; st < nStages; ++st) {
-        cp_async_wait<kRing - 1>();
-        __syncthreads();
-        const float* mine = in_tile + (size_t)(st % kRing) * kSosThreads * kPitch + tid * kPitch;
-        float* outp = out_tile + tid * kPitch;
+        cp_async_wait<0>();                 // stage st has landed
+        __syncthreads();                    // ... for everyone; the other buffer's stores are done
+        issue(st + 1);                      // refill the other buffer while this one is processed
+        float* mine = tiles + (size_t)(st % kRing) * kSosThreads * kPitch + tid * kPitch;
+        float4 xin[kSub / 4];
 #pragma unroll
         for (int v = 0; v < kSub / 4; ++v) {
-            float4 xv, yv;
-            const int base = st * kSub + 4 * v;        // logical sample index within the chunk
             if (!REV) {
-                xv = *reinterpret_cast<const float4*>(mine + 4 * v);
+                xin[v] = *reinterpret_cast<const float4*>(mine + 4 * v);
             } else {
                 float4 t4 = *reinterpret_cast<const float4*>(mine + (kSub - 4 - 4 * v));
-                xv = make_float4(t4.w, t4.z, t4.y, t4.x);
+                xin[v] = make_float4(t4.w, t4.z, t4.y, t4.x);
             }
+        }
+#pragma unroll
+        for (int v = 0; v < kSub / 4; ++v) {
+            float4 yv;
+            const float4 xv = xin[v];
+            const int base = st * kSub + 4 * v;        // logical sample index within the chunk
             if (base + 4 <= mylen) {
                 yv.x = (float)sos_step<NSEC>((double)xv.x, c, s);
                 yv.y = (float)sos_step<NSEC>((double)xv.y, c, s);
@@ -149,13 +153,14 @@ sos_chunk_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, 
                 if (base + 1 < mylen) yv.y = (float)sos_step<NSEC>((double)xv.y, c, s);
                 if (base + 2 < mylen) yv.z = (float)sos_step<NSEC>((double)xv.z, c, s);
             }
-            if (WRITE) {
-                if (!REV) *reinterpret_cast<float4*>(outp + 4 * v) = yv;
-                else *reinterpret_cast<float4*>(outp + (kSub - 4 - 4 * v)) = make_float4(yv.w, yv.z, yv.y, yv.x);
+            if (WRITE) {     // results overwrite this thread's own tile row
+                if (!REV) *reinterpret_cast<float4*>(mine + 4 * v) = yv;
+                else *reinterpret_cast<float4*>(mine + (kSub - 4 - 4 * v)) = make_float4(yv.w, yv.z, yv.y, yv.x);
             }
         }
-        __syncthreads();
         if (WRITE) {
+            __syncthreads();
+            const float* out_tile = tiles + (size_t)(st % kRing) * kSosThreads * kPitch;
             if (VEC) {
                 for (int i = tid; i < kSosThreads * 4; i += kSosThreads) {
                     const int r = i >> 2, p = i & 3;
@@ -179,13 +184,12 @@ sos_chunk_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, 
                 }
             }
         }
-        issue(st + kRing);
     }
     cp_async_wait<0>();
 
     if (!WRITE) {
-        if (need) {   // end state of chunk k is the affine term of slot k+1
-            double* sp = state + (q + 1) * (2 * NSEC);
+        if (need) {   // end state of chunk k: the affine term g_k of the chunk map
+            double* sp = gbuf + q * (2 * NSEC);
 #pragma unroll
             for (int j = 0; j < NSEC; ++j) { sp[2 * j] = s[j][0]; sp[2 * j + 1] = s[j][1]; }
         }
@@ -205,11 +209,13 @@ sos_chunk_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, 
     }
 }
 
-// one thread per row: start-up state, then the sequential carry over chunks
+// one thread per row: start-up state, then the sequential carry over chunks.  g_k is read from
+// its own buffer two chunks ahead of the recurrence so that no global latency sits on the chain.
 template <int NSEC, bool REV>
 __global__ void sos_scan_kernel(const float* __restrict__ x, int64_t C, int64_t T, int64_t ldx,
                                 int nChunks, int padlen, int zero_phase, SosCoef coef, SosMatrix M,
-                                double* __restrict__ state, const double* __restrict__ padbuf) {
+                                double* __restrict__ state, const double* __restrict__ gbuf,
+                                const double* __restrict__ padbuf) {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= C) return;
     constexpr int NS = 2 * NSEC;
@@ -243,48 +249,55 @@ __global__ void sos_scan_kernel(const float* __restrict__ x, int64_t C, int64_t 
 #pragma unroll
     for (int j = 0; j < NSEC; ++j) { v[2 * j] = s[j][0]; v[2 * j + 1] = s[j][1]; }
     double* sp = state + row * nChunks * NS;
-    for (int k = 0; k < nChunks; ++k) {
-        double g[NS];
-        if (k + 1 < nChunks) {
+    const double* gp = gbuf + row * nChunks * NS;
+    double g0[NS], g1[NS];
 #pragma unroll
-            for (int i = 0; i < NS; ++i) g[i] = sp[(int64_t)(k + 1) * NS + i];
-        }
+    for (int i = 0; i < NS; ++i) {
+        g0[i] = nChunks > 1 ? gp[i] : 0.0;
+        g1[i] = nChunks > 2 ? gp[NS + i] : 0.0;
+    }
+    for (int k = 0; k < nChunks; ++k) {
 #pragma unroll
         for (int i = 0; i < NS; ++i) sp[(int64_t)k * NS + i] = v[i];
-        if (k + 1 < nChunks) {
-            double nv[NS];
+        if (k + 1 >= nChunks) break;
+        double g2[NS];
 #pragma unroll
-            for (int i = 0; i < NS; ++i) {
-                double acc = g[i];
+        for (int i = 0; i < NS; ++i) g2[i] = k + 3 < nChunks ? gp[(int64_t)(k + 2) * NS + i] : 0.0;
+        double nv[NS];
 #pragma unroll
-                for (int j = 0; j < NS; ++j) acc = fma(M.m[i][j], v[j], acc);
-                nv[i] = acc;
+        for (int i = 0; i < NS; ++i) {
+            double acc0 = g0[i], acc1 = 0.0;
+#pragma unroll
+            for (int j = 0; j < NS; j += 2) {
+                acc0 = fma(M.m[i][j], v[j], acc0);
+                acc1 = fma(M.m[i][j + 1], v[j + 1], acc1);
             }
-#pragma unroll
-            for (int i = 0; i < NS; ++i) v[i] = nv[i];
+            nv[i] = acc0 + acc1;
         }
+#pragma unroll
+        for (int i = 0; i < NS; ++i) { v[i] = nv[i]; g0[i] = g1[i]; g1[i] = g2[i]; }
     }
 }
 
 static size_t sos_smem_bytes() {
-    return ((size_t)(kRing + 1) * kSosThreads * kPitch) * sizeof(float) +
+    return ((size_t)kRing * kSosThreads * kPitch) * sizeof(float) +
            (size_t)kSosThreads * (sizeof(int64_t) + 2 * sizeof(int));
 }
 
 template <int NSEC, bool REV, bool WRITE>
 static int launch_chunk(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                         const ecog_sos_plan& p, int nChunks, const SosCoef& coef, double* state,
-                        double* padbuf, bool vec, cudaStream_t st) {
+                        double* gbuf, double* padbuf, bool vec, cudaStream_t st) {
     const size_t smem = sos_smem_bytes();
     const unsigned grid = (unsigned)ceil_div(C * nChunks, kSosThreads);
     if (vec) {
         auto k = sos_chunk_kernel<NSEC, REV, WRITE, true>;
         ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kSosThreads, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, coef, state, padbuf);
+        k<<<grid, kSosThreads, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, coef, state, gbuf, padbuf);
     } else {
         auto k = sos_chunk_kernel<NSEC, REV, WRITE, false>;
         ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kSosThreads, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, coef, state, padbuf);
+        k<<<grid, kSosThreads, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, coef, state, gbuf, padbuf);
     }
     return check_launch(WRITE ? "sos_main" : "sos_tail");
 }
@@ -292,21 +305,21 @@ static int launch_chunk(const float* x, float* y, int64_t C, int64_t T, int64_t 
 template <int NSEC>
 static int run_sos(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                    const ecog_sos_plan& p, const SosCoef& coef, const SosMatrix& M, double* state,
-                   double* padbuf, cudaStream_t st) {
+                   double* gbuf, double* padbuf, cudaStream_t st) {
     const int nChunks = (int)ceil_div(T, p.chunk);
     const bool vec = aligned16(x) && aligned16(y) && T % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0;
     const unsigned sgrid = (unsigned)ceil_div(C, 64);
     // forward sweep: x -> y
-    if (nChunks > 1) ECOG_TRY((launch_chunk<NSEC, false, false>(x, y, C, T, ldx, ldy, p, nChunks, coef, state, padbuf, vec, st)));
-    sos_scan_kernel<NSEC, false><<<sgrid, 64, 0, st>>>(x, C, T, ldx, nChunks, p.padlen, p.zero_phase, coef, M, state, padbuf);
+    if (nChunks > 1) ECOG_TRY((launch_chunk<NSEC, false, false>(x, y, C, T, ldx, ldy, p, nChunks, coef, state, gbuf, padbuf, vec, st)));
+    sos_scan_kernel<NSEC, false><<<sgrid, 64, 0, st>>>(x, C, T, ldx, nChunks, p.padlen, p.zero_phase, coef, M, state, gbuf, padbuf);
     ECOG_TRY(check_launch("sos_scan"));
-    ECOG_TRY((launch_chunk<NSEC, false, true>(x, y, C, T, ldx, ldy, p, nChunks, coef, state, padbuf, vec, st)));
+    ECOG_TRY((launch_chunk<NSEC, false, true>(x, y, C, T, ldx, ldy, p, nChunks, coef, state, gbuf, padbuf, vec, st)));
     if (!p.zero_phase) return ECOG_OK;
     // backward sweep: y -> y in place, time reversed
-    if (nChunks > 1) ECOG_TRY((launch_chunk<NSEC, true, false>(y, y, C, T, ldy, ldy, p, nChunks, coef, state, padbuf, vec, st)));
-    sos_scan_kernel<NSEC, true><<<sgrid, 64, 0, st>>>(y, C, T, ldy, nChunks, p.padlen, p.zero_phase, coef, M, state, padbuf);
+    if (nChunks > 1) ECOG_TRY((launch_chunk<NSEC, true, false>(y, y, C, T, ldy, ldy, p, nChunks, coef, state, gbuf, padbuf, vec, st)));
+    sos_scan_kernel<NSEC, true><<<sgrid, 64, 0, st>>>(y, C, T, ldy, nChunks, p.padlen, p.zero_phase, coef, M, state, gbuf, padbuf);
     ECOG_TRY(check_launch("sos_scan"));
-    return launch_chunk<NSEC, true, true>(y, y, C, T, ldy, ldy, p, nChunks, coef, state, padbuf, vec, st);
+    return launch_chunk<NSEC, true, true>(y, y, C, T, ldy, ldy, p, nChunks, coef, state, gbuf, padbuf, vec, st);
 }
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -322,7 +335,7 @@ extern "C" size_t ecog_sos_workspace(const ecog_sos_plan* plan, int64_t C, int64
                                          : (plan->nsec <= 6 ? 6 : 8);
     size_t states = align_up((size_t)C * nChunks * 2 * nsec_pad * sizeof(double), 256);
     size_t pad = align_up((size_t)C * (plan->padlen > 0 ? plan->padlen : 1) * sizeof(double), 256);
-    return states + pad;
+    return 2 * states + pad;       // chunk start states, chunk affine terms, filtered right pad
 }
 
 extern "C" int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
@@ -374,14 +387,15 @@ extern "C" int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, 
     }
     const size_t states = align_up((size_t)C * nChunks * 2 * ns * sizeof(double), 256);
     double* state = (double*)d_workspace;
-    double* padbuf = (double*)((char*)d_workspace + states);
+    double* gbuf = (double*)((char*)d_workspace + states);
+    double* padbuf = (double*)((char*)d_workspace + 2 * states);
     cudaStream_t st = (cudaStream_t)stream;
     switch (ns) {
-        case 1: return run_sos<1>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, padbuf, st);
-        case 2: return run_sos<2>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, padbuf, st);
-        case 3: return run_sos<3>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, padbuf, st);
-        case 4: return run_sos<4>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, padbuf, st);
-        case 6: return run_sos<6>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, padbuf, st);
-        default: return run_sos<8>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, padbuf, st);
+        case 1: return run_sos<1>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, gbuf, padbuf, st);
+        case 2: return run_sos<2>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, gbuf, padbuf, st);
+        case 3: return run_sos<3>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, gbuf, padbuf, st);
+        case 4: return run_sos<4>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, gbuf, padbuf, st);
+        case 6: return run_sos<6>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, gbuf, padbuf, st);
+        default: return run_sos<8>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, gbuf, padbuf, st);
     }
 }

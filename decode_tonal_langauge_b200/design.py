@@ -233,12 +233,12 @@ def response_tail(sos, limit: int, eps: float = 1e-18) -> int:
 
 
 def choose_chunk(C: int, T: int, chunk: Optional[int] = None) -> int:
-    """Chunk length so that C * ceil(T/chunk) chunk-threads fill one wave of 148 x 512."""
+    """Chunk length so that C * ceil(T/chunk) chunk-threads fill one wave of 148 SMs x 2 CTAs x 512."""
     if chunk is not None:
         if chunk % SUB:
             raise ValueError(f"chunk must be a multiple of {SUB}")
         return int(chunk)
-    items = NUM_SMS * SOS_THREADS
+    items = NUM_SMS * 2 * SOS_THREADS
     n_chunks = max(1, items // max(C, 1))
     L = -(-T // n_chunks)
     L = max(-(-L // SUB) * SUB, 1024)

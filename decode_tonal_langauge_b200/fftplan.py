@@ -141,16 +141,33 @@ def resample_plan(T: int, num: int) -> ResamplePlan:
 HILBERT_N = 4096
 
 
-def hilbert_gain(cfs: np.ndarray, sds: np.ndarray, fs: float) -> np.ndarray:
-    """(nb, 2048) float32 gain on the 4096-point block grid: Gaussian x analytic factor 2,
-    times 1/2 (conjugate-symmetry split), 1/N (inverse FFT) and 1/nb (mean over bands).
-    ref: frequency_filter.py:158-175,184 -- H[0] = 0."""
+def hilbert_gain(cfs: np.ndarray, sds: np.ndarray, fs: float, envelope: bool = True):
+    """Per-band gain tables on the 4096-point block grid.
+
+    Returns (gain (nb, rows*256) float32, shift (nb,) int32, rows).  gain = Gaussian x analytic
+    factor 2, times 1/2 (conjugate-symmetry split), 1/N (inverse FFT) and 1/nb (mean over
+    bands); ref: frequency_filter.py:158-175,184 -- H[0] = 0.  Bins whose gain is below 1e-12
+    of the band peak are dropped; for the envelope each band is shifted down to its first kept
+    bin (|z| is invariant to a spectral shift) so that it fits rows*256 bins."""
     N = HILBERT_N
     f = np.arange(N // 2, dtype=np.float64) * fs / N
     g = np.exp(-0.5 * ((f[None, :] - cfs[:, None]) / sds[:, None]) ** 2)
     g[:, 0] = 0.0
-    g *= 2.0 * 0.5 / N / len(cfs)
-    return np.ascontiguousarray(g, dtype=np.float32)
+    keep = g >= 1e-12 * g.max(axis=1, keepdims=True)
+    lo = np.array([np.argmax(k) for k in keep])
+    hi = np.array([len(k) - np.argmax(k[::-1]) for k in keep])       # one past the last kept bin
+    if not envelope:
+        lo[:] = 0
+    width = int((hi - lo).max())
+    rows = next(r for r in (1, 2, 4, 8) if width <= r * 256)
+    lo = np.minimum(lo, N // 2 - rows * 256)
+    out = np.zeros((len(cfs), rows * 256), dtype=np.float64)
+    for b in range(len(cfs)):
+        seg = g[b, lo[b]:lo[b] + rows * 256].copy()
+        seg[np.arange(lo[b], lo[b] + rows * 256) >= hi[b]] = 0.0
+        out[b] = seg
+    out *= 2.0 * 0.5 / N / len(cfs)
+    return np.ascontiguousarray(out, dtype=np.float32), lo.astype(np.int32), rows
 
 
 def hilbert_halo(cfs: np.ndarray, sds: np.ndarray, fs: float, T: int, nsigma: float = 6.5) -> int:

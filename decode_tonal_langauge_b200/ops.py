@@ -187,6 +187,9 @@ def _hilbert_twiddles(device) -> torch.Tensor:
     return _dev_table("hilbert_tw", make, device)
 
 
+_hilbert_plans = {}
+
+
 def hilbert(x: torch.Tensor, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0,
             filterbank_bias=np.log10(0.39), filterbank_slope=0.5, envelope=True,
             out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -197,11 +200,16 @@ def hilbert(x: torch.Tensor, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0,
     if len(cfs) == 0:
         raise ValueError("the frequency ranges contain no filter-bank centre frequency")
     halo = FP.hilbert_halo(cfs, sds, float(fs), T)
-    key = ("hilbert_gain", tuple(cfs.tolist()), tuple(sds.tolist()), float(fs))
-    gain = _dev_table(key, lambda: FP.hilbert_gain(cfs, sds, float(fs)), x.device)
+    key = ("hilbert_gain", tuple(cfs.tolist()), tuple(sds.tolist()), float(fs), bool(envelope))
+    plan = _hilbert_plans.get(key)
+    if plan is None:
+        plan = _hilbert_plans[key] = FP.hilbert_gain(cfs, sds, float(fs), bool(envelope))
+    gain_h, shift, rows = plan
+    gain = _dev_table(key, lambda: gain_h, x.device)
     y = out if out is not None else torch.empty((Cn, T), dtype=torch.float32, device=x.device)
-    nat.check(lib.ecog_hilbert_env(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), _ptr(gain), len(cfs), halo,
-                                   1 if envelope else 0, _ptr(_hilbert_twiddles(x.device)), _stream()))
+    nat.check(lib.ecog_hilbert_env(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), _ptr(gain), len(cfs), rows,
+                                   _hptr(shift), halo, 1 if envelope else 0,
+                                   _ptr(_hilbert_twiddles(x.device)), _stream()))
     return y
 
 

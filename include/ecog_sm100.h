@@ -98,15 +98,17 @@ int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx
 
 /* ------------------------------------ K4: Gaussian-Hilbert envelope (block-wise)
  * replaces preprocess/signal/frequency_filter.py:154-184.
- * Overlap-save with 4096-point shared-memory FFTs and a circular halo.  d_gain:
- * nbands x 2048 float32 = Gaussian x analytic mask / (4096 * nbands) sampled on the
- * block grid (host, float64 -> float32).  d_twiddle: table from ecog_hilbert_twiddles. */
+ * Overlap-save with 4096-point shared-memory FFTs and a circular halo of `halo` samples.
+ * Band b uses bins [h_shift[b], h_shift[b] + rows*256) of the block's half spectrum;
+ * d_gain is nbands x (rows*256) float32 = Gaussian x analytic mask / (4096 * nbands) on
+ * those bins (host, float64 -> float32).  rows in {1,2,4,8}.  With envelope=0 (real part)
+ * every h_shift must be 0.  d_twiddle: table from ecog_hilbert_twiddles.              */
 #define ECOG_HILBERT_N 4096
 size_t ecog_hilbert_twiddle_floats(void);
 int ecog_hilbert_twiddles(float* h_out);   /* host helper: fills the per-thread twiddle table */
 int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
-                     const float* d_gain, int32_t nbands, int32_t halo, int32_t envelope,
-                     const float* d_twiddle, ecog_stream_t stream);
+                     const float* d_gain, int32_t nbands, int32_t rows, const int32_t* h_shift,
+                     int32_t halo, int32_t envelope, const float* d_twiddle, ecog_stream_t stream);
 
 /* ------------------------------------------------- K5: whole-row FFT resample
  * replaces preprocess/signal/downsample.py:21-27 (scipy.signal.resample, real input).

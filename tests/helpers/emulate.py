@@ -153,7 +153,7 @@ def fft4096_model(z: np.ndarray, tw: np.ndarray) -> np.ndarray:
     return out
 
 
-def hilbert_block_model(x32: np.ndarray, gain: np.ndarray, halo: int, envelope: bool = True) -> np.ndarray:
+def hilbert_block_model(x32: np.ndarray, plan, halo: int, envelope: bool = True) -> np.ndarray:
     """Model of ecog_hilbert_env for one row: overlap-save blocks with circular halo,
     two blocks per complex FFT, conj-forward inverse, mean folded into the gain."""
     N = 4096
@@ -161,6 +161,7 @@ def hilbert_block_model(x32: np.ndarray, gain: np.ndarray, halo: int, envelope: 
     U = N - 2 * halo
     nblk = -(-T // U)
     y = np.zeros(T, dtype=np.float32)
+    gain, shift, rows = plan
     g = gain.astype(np.float64)
     for b0 in range(0, nblk, 2):
         i = np.arange(N)
@@ -176,8 +177,8 @@ def hilbert_block_model(x32: np.ndarray, gain: np.ndarray, halo: int, envelope: 
         acc = [np.zeros(N), np.zeros(N)]
         for band in range(g.shape[0]):
             for sel, S in enumerate((S0, S1)):
-                Yc = np.zeros(N, dtype=np.complex128)
-                Yc[:N // 2] = np.conj(S) * g[band]
+                Yc = np.zeros(N, dtype=np.complex128)          # band shifted down to bin 0
+                Yc[:rows * 256] = np.conj(S[shift[band]:shift[band] + rows * 256]) * g[band]
                 zc = np.fft.fft(Yc)
                 acc[sel] += np.abs(zc) if envelope else zc.real
         for sel in range(2 if has1 else 1):

@@ -74,14 +74,18 @@ def test_hilbert_models(golden):
     cfs, sds = D.gaussian_bank([70.0, 150.0])
     assert len(cfs) == 8 and abs(cfs[0] - 73.728) < 1e-3
     halo = FP.hilbert_halo(cfs, sds, fs, x.shape[1])
-    gain = FP.hilbert_gain(cfs, sds, fs)
-    y = np.stack([EM.hilbert_block_model(r, gain, halo, True) for r in x])
+    plan = FP.hilbert_gain(cfs, sds, fs, True)
+    assert plan[2] == 1 and plan[0].shape == (8, 256)          # high-gamma bank at 2 kHz: one row of bins
+    y = np.stack([EM.hilbert_block_model(r, plan, halo, True) for r in x])
     assert max_rel(y, g["hilbert_env"]) < 1e-6
-    y = np.stack([EM.hilbert_block_model(r, gain, halo, False) for r in x])
+    plan = FP.hilbert_gain(cfs, sds, fs, False)
+    assert (plan[1] == 0).all()
+    y = np.stack([EM.hilbert_block_model(r, plan, halo, False) for r in x])
     assert max_rel(y, g["hilbert_real"]) < 1e-6
+    assert FP.hilbert_gain(cfs, sds, 400.0, True)[2] == 4      # same bank at 400 Hz: wider in bins
     cfs2, sds2 = D.gaussian_bank([[30.0, 55.0], [70.0, 150.0]])
     halo2 = FP.hilbert_halo(cfs2, sds2, fs, x.shape[1])
-    y = np.stack([EM.hilbert_block_model(r, FP.hilbert_gain(cfs2, sds2, fs), halo2, True) for r in x])
+    y = np.stack([EM.hilbert_block_model(r, FP.hilbert_gain(cfs2, sds2, fs, True), halo2, True) for r in x])
     assert max_rel(y, g["hilbert_two_ranges"]) < 1e-6
     with pytest.raises(NotImplementedError):
         c3, s3 = D.gaussian_bank([0.5, 4.0])
@@ -120,5 +124,5 @@ def test_causal_design_matches_reference(golden):
 def test_choose_chunk_fills_one_wave():
     L = D.choose_chunk(256, 7_200_000)
     n_chunks = -(-7_200_000 // L)
-    assert L % 16 == 0 and 256 * n_chunks <= 148 * 512
+    assert L % 16 == 0 and 256 * n_chunks <= 148 * 2 * 512
     assert D.choose_chunk(4, 12000) >= 1024
