@@ -209,16 +209,25 @@ sos_chunk_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, 
     }
 }
 
-// one thread per row: start-up state, then the sequential carry over chunks.  g_k is read from
-// its own buffer two chunks ahead of the recurrence so that no global latency sits on the chain.
+// One warp per row: start-up state, then the sequential carry S_{k+1} = M S_k + g_k over chunks.
+// The g_k vectors are fetched 32 chunks at a time with one coalesced load per lane (double
+// buffered through shared memory), every lane then runs the same short recurrence out of shared
+// memory (no global latency on the dependency chain) and the 32 start states are written back
+// coalesced.
+constexpr int kScanWarps = 2;
+
 template <int NSEC, bool REV>
-__global__ void sos_scan_kernel(const float* __restrict__ x, int64_t C, int64_t T, int64_t ldx,
-                                int nChunks, int padlen, int zero_phase, SosCoef coef, SosMatrix M,
-                                double* __restrict__ state, const double* __restrict__ gbuf,
-                                const double* __restrict__ padbuf) {
-    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= C) return;
+__global__ void __launch_bounds__(kScanWarps * 32)
+sos_scan_kernel(const float* __restrict__ x, int64_t C, int64_t T, int64_t ldx,
+                int nChunks, int padlen, int zero_phase, SosCoef coef, SosMatrix M,
+                double* __restrict__ state, const double* __restrict__ gbuf,
+                const double* __restrict__ padbuf) {
     constexpr int NS = 2 * NSEC;
+    __shared__ double gs[kScanWarps][2][32][NS + 1];
+    __shared__ double ss[kScanWarps][32][NS + 1];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t row = (int64_t)blockIdx.x * kScanWarps + wib;
+    if (row >= C) return;                                   // whole warp exits together
     double c[NSEC][5], s[NSEC][2];
 #pragma unroll
     for (int j = 0; j < NSEC; ++j) {
@@ -226,7 +235,7 @@ __global__ void sos_scan_kernel(const float* __restrict__ x, int64_t C, int64_t 
         for (int i = 0; i < 5; ++i) c[j][i] = coef.c[j][i];
         s[j][0] = 0.0; s[j][1] = 0.0;
     }
-    if (zero_phase) {
+    if (zero_phase) {      // every lane computes the same start-up (uniform, broadcast loads)
         if (!REV) {
             const float* xr = x + row * ldx;
             const float x0 = xr[0];
@@ -250,32 +259,45 @@ __global__ void sos_scan_kernel(const float* __restrict__ x, int64_t C, int64_t 
     for (int j = 0; j < NSEC; ++j) { v[2 * j] = s[j][0]; v[2 * j + 1] = s[j][1]; }
     double* sp = state + row * nChunks * NS;
     const double* gp = gbuf + row * nChunks * NS;
-    double g0[NS], g1[NS];
+    const int nG = nChunks - 1;                             // g_0 .. g_{nChunks-2}
+    auto fetch = [&](int batch, int buf) {                  // lane -> g of chunk batch*32 + lane
+        const int k = batch * 32 + lane;
+        if (k < nG) {
 #pragma unroll
-    for (int i = 0; i < NS; ++i) {
-        g0[i] = nChunks > 1 ? gp[i] : 0.0;
-        g1[i] = nChunks > 2 ? gp[NS + i] : 0.0;
-    }
-    for (int k = 0; k < nChunks; ++k) {
-#pragma unroll
-        for (int i = 0; i < NS; ++i) sp[(int64_t)k * NS + i] = v[i];
-        if (k + 1 >= nChunks) break;
-        double g2[NS];
-#pragma unroll
-        for (int i = 0; i < NS; ++i) g2[i] = k + 3 < nChunks ? gp[(int64_t)(k + 2) * NS + i] : 0.0;
-        double nv[NS];
-#pragma unroll
-        for (int i = 0; i < NS; ++i) {
-            double acc0 = g0[i], acc1 = 0.0;
-#pragma unroll
-            for (int j = 0; j < NS; j += 2) {
-                acc0 = fma(M.m[i][j], v[j], acc0);
-                acc1 = fma(M.m[i][j + 1], v[j + 1], acc1);
-            }
-            nv[i] = acc0 + acc1;
+            for (int i = 0; i < NS; ++i) gs[wib][buf][lane][i] = gp[(int64_t)k * NS + i];
         }
+    };
+    fetch(0, 0);
+    for (int batch = 0; batch * 32 < nChunks; ++batch) {
+        __syncwarp();
+        fetch(batch + 1, (batch + 1) & 1);                  // loads in flight during the recurrence
+        const int k0 = batch * 32;
+        const int cnt = nChunks - k0 < 32 ? nChunks - k0 : 32;
+        for (int t = 0; t < cnt; ++t) {
+            if (lane < NS) ss[wib][t][lane] = 0.0;          // placeholder keeps the loop uniform
 #pragma unroll
-        for (int i = 0; i < NS; ++i) { v[i] = nv[i]; g0[i] = g1[i]; g1[i] = g2[i]; }
+            for (int i = 0; i < NS; ++i) if (lane == i) ss[wib][t][i] = v[i];
+            if (k0 + t + 1 < nChunks) {
+                double nv[NS];
+#pragma unroll
+                for (int i = 0; i < NS; ++i) {
+                    double acc0 = gs[wib][batch & 1][t][i], acc1 = 0.0;
+#pragma unroll
+                    for (int j = 0; j < NS; j += 2) {
+                        acc0 = fma(M.m[i][j], v[j], acc0);
+                        acc1 = fma(M.m[i][j + 1], v[j + 1], acc1);
+                    }
+                    nv[i] = acc0 + acc1;
+                }
+#pragma unroll
+                for (int i = 0; i < NS; ++i) v[i] = nv[i];
+            }
+        }
+        __syncwarp();
+        if (lane < cnt) {                                   // coalesced write-back of 32 start states
+#pragma unroll
+            for (int i = 0; i < NS; ++i) sp[(int64_t)(k0 + lane) * NS + i] = ss[wib][lane][i];
+        }
     }
 }
 
@@ -308,16 +330,16 @@ static int run_sos(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, 
                    double* gbuf, double* padbuf, cudaStream_t st) {
     const int nChunks = (int)ceil_div(T, p.chunk);
     const bool vec = aligned16(x) && aligned16(y) && T % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0;
-    const unsigned sgrid = (unsigned)ceil_div(C, 64);
+    const unsigned sgrid = (unsigned)ceil_div(C, kScanWarps);
     // forward sweep: x -> y
     if (nChunks > 1) ECOG_TRY((launch_chunk<NSEC, false, false>(x, y, C, T, ldx, ldy, p, nChunks, coef, state, gbuf, padbuf, vec, st)));
-    sos_scan_kernel<NSEC, false><<<sgrid, 64, 0, st>>>(x, C, T, ldx, nChunks, p.padlen, p.zero_phase, coef, M, state, gbuf, padbuf);
+    sos_scan_kernel<NSEC, false><<<sgrid, kScanWarps * 32, 0, st>>>(x, C, T, ldx, nChunks, p.padlen, p.zero_phase, coef, M, state, gbuf, padbuf);
     ECOG_TRY(check_launch("sos_scan"));
     ECOG_TRY((launch_chunk<NSEC, false, true>(x, y, C, T, ldx, ldy, p, nChunks, coef, state, gbuf, padbuf, vec, st)));
     if (!p.zero_phase) return ECOG_OK;
     // backward sweep: y -> y in place, time reversed
     if (nChunks > 1) ECOG_TRY((launch_chunk<NSEC, true, false>(y, y, C, T, ldy, ldy, p, nChunks, coef, state, gbuf, padbuf, vec, st)));
-    sos_scan_kernel<NSEC, true><<<sgrid, 64, 0, st>>>(y, C, T, ldy, nChunks, p.padlen, p.zero_phase, coef, M, state, gbuf, padbuf);
+    sos_scan_kernel<NSEC, true><<<sgrid, kScanWarps * 32, 0, st>>>(y, C, T, ldy, nChunks, p.padlen, p.zero_phase, coef, M, state, gbuf, padbuf);
     ECOG_TRY(check_launch("sos_scan"));
     return launch_chunk<NSEC, true, true>(y, y, C, T, ldy, ldy, p, nChunks, coef, state, gbuf, padbuf, vec, st);
 }

@@ -1,0 +1,3 @@
+"""Drop-in module: same dotted name and entry points as the reference's `preprocess/io/tdt_blocks.py (npz block directories; no TDT wheel needed)`;
+the implementation lives in decode_tonal_langauge_b200 and runs on the B200."""
+from decode_tonal_langauge_b200.stages import load_block, save_block  # noqa: F401

@@ -1,0 +1,2 @@
+"""Drop-in module: same dotted name and entry points as the reference's `utils/__init__.py`;
+the implementation lives in decode_tonal_langauge_b200 and runs on the B200."""

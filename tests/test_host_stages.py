@@ -1,0 +1,198 @@
+"""Host logic of the stage drivers and plug-in host: naming, provenance, TextGrid parsing,
+parameter scoping.  CPU only."""
+import os
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import yaml
+
+from decode_tonal_langauge_b200 import config as cfgmod
+from decode_tonal_langauge_b200 import stages, textgrid_io
+from decode_tonal_langauge_b200.preprocessor import preprocess_signal
+
+EXAMPLE = {
+    "preprocess": {"module": "preprocess_main", "params": {"modalities": {"ecog": {"type": "signal", "preprocessing": {
+        "steps": [
+            {"module": "preprocess.downsample", "params": {"downsample_freq": 400}},
+            {"module": "preprocess.frequency_filter", "params": {"bands": [
+                {"method": "hilbert", "params": {"freq_ranges": [70, 150], "envelope": True}},
+                {"method": "butter", "params": {"freqs": [0.3, 100], "filter_type": "bandpass"}}]}},
+            {"module": "preprocess.zscore_rereference", "params": {"rereference_interval": [0.0, 25.0]}}]}},
+        "audio": {"type": "signal"}}}},
+}
+
+
+def test_setup_name_matches_reference_for_example_config():
+    # value produced by the reference's generate_setup_name on example_config.yaml:27-45
+    assert stages.generate_setup_name(EXAMPLE["preprocess"]["params"]["modalities"]) == \
+        "downsample__frequency_filter__zscore_rereference_4d5793"
+    assert stages.generate_setup_name({"audio": {"type": "signal"}}) == "raw"
+
+
+def test_hash_names_against_live_reference():
+    from oracle import reference_bridge as rb
+    if not rb.available():
+        pytest.skip("reference tree not mounted")
+    cfg = yaml.safe_load(open(os.path.join(rb.REFERENCE_ROOT, "example_config.yaml")))
+    sb = rb.load("preprocess.pipelines.subject_block")
+    assert stages.generate_setup_name(cfg["preprocess"]["params"]["modalities"]) == \
+        sb.generate_setup_name(cfg["preprocess"]["params"]["modalities"])
+    uc = rb.load("utils.config")
+    assert cfgmod.generate_hash_name_from_config("s__1", cfg["channel_selection"]) == \
+        uc.generate_hash_name_from_config("s__1", cfg["channel_selection"])
+    es = rb.load("extract_samples")
+    assert cfgmod.yaml_hash_name("setup", cfg["sample_collection"]) == \
+        es._generate_output_dir_name("setup", cfg["sample_collection"])
+    ns = cfgmod.dict_to_namespace({"a": {"b": [1, {"c": 2}]}, "root_dir": {"x": 1}}, exclude_keys=["root_dir"])
+    ref = uc.dict_to_namespace({"a": {"b": [1, {"c": 2}]}, "root_dir": {"x": 1}}, exclude_keys=["root_dir"])
+    assert ns == ref and ns.root_dir == {"x": 1}
+
+
+def test_update_configuration_merges_provenance(tmp_path):
+    prev = tmp_path / "prev.yaml"
+    prev.write_text(yaml.dump({"preprocess": {"io": {"root_dir": "r"}}}))
+    out = tmp_path / "config.yaml"
+    cfgmod.update_configuration(str(out), str(prev), "sample_collection", {"params": {"x": 1}})
+    merged = yaml.safe_load(out.read_text())
+    assert merged == {"preprocess": {"io": {"root_dir": "r"}}, "sample_collection": {"params": {"x": 1}}}
+    cfgmod.update_configuration(str(out), str(tmp_path / "missing.yaml"), "channel_selection", {})
+    assert yaml.safe_load(out.read_text()) == {"channel_selection": {}}
+
+
+LONG_TG = '''File type = "ooTextFile"
+Object class = "TextGrid"
+
+xmin = 0
+xmax = 12.5
+tiers? <exists>
+size = 2
+item []:
+    item [1]:
+        class = "IntervalTier"
+        name = "Success"
+        xmin = 0
+        xmax = 12.5
+        intervals: size = 5
+        intervals [1]:
+            xmin = 0
+            xmax = 1.234
+            text = ""
+        intervals [2]:
+            xmin = 1.234
+            xmax = 1.9
+            text = "3i"
+        intervals [3]:
+            xmin = 1.9
+            xmax = 4.06
+            text = "rest"
+        intervals [4]:
+            xmin = 4.06
+            xmax = 4.71
+            text = "1a said ""ma"""
+        intervals [5]:
+            xmin = 4.5
+            xmax = 5.0
+            text = "2i"
+    item [2]:
+        class = "IntervalTier"
+        name = "fail"
+        xmin = 0
+        xmax = 12.5
+        intervals: size = 1
+        intervals [1]:
+            xmin = 7.0
+            xmax = 7.5
+            text = "4a"
+'''
+
+SHORT_TG = '''File type = "ooTextFile"
+Object class = "TextGrid"
+
+0
+12.5
+<exists>
+1
+"IntervalTier"
+"success"
+0
+12.5
+2
+0.52
+1.0
+"2a"
+1.0
+12.5
+""
+'''
+
+
+def test_textgrid_parser_and_interval_table(tmp_path):
+    tg = textgrid_io.TextGrid.fromString(LONG_TG)
+    assert [t.name for t in tg.tiers] == ["Success", "fail"]
+    assert len(tg.tiers[0].intervals) == 5 and tg.tiers[0].intervals[3].mark == '1a said "ma"'
+    df = textgrid_io.read_textgrid(tg, start_offset=0.2, end_offset=0.0, tier_list=["success"])
+    # third trial (4.5 s) overlaps the previous one's end (4.7) after the offset -> skipped
+    assert df["start"].tolist() == [1.0, 3.9] and df["end"].tolist() == [1.9, 4.7]
+    assert df["tone"].tolist() == [3, 1] and df["syllable"].tolist() == ["i", "a"]
+    assert df["start"].dtype == np.float64
+    all_tiers = textgrid_io.read_textgrid(tg, 0.0, 0.0, None)
+    assert len(all_tiers) == 3 and all_tiers["tone"].tolist()[-1] == 4
+    short = textgrid_io.TextGrid.fromString(SHORT_TG)
+    assert short.tiers[0].intervals[0].mark == "2a" and short.tiers[0].intervals[0].minTime == 0.52
+    (tmp_path / "x_B2.TextGrid").write_text(LONG_TG)
+    (tmp_path / "y_B7.TextGrid").write_text(SHORT_TG)
+    (tmp_path / "notes.txt").write_text("ignored")
+    tables = textgrid_io.handle_textgrids(str(tmp_path), start_offset=0.2, tier_list=["success"], blocks=[2, 7])
+    assert sorted(tables) == [2, 7] and len(tables[7]) == 1 and tables[7]["start"].iloc[0] == 0.3
+    assert list(textgrid_io.handle_textgrids(str(tmp_path), blocks=[7])) == [7]
+
+
+def test_step_runner_param_scope_and_rate_threading():
+    x = np.ones((2, 8), dtype=np.float32)
+    steps = [{"module": "helpers.fake_step", "params": {"gain": 2.0}},
+             {"module": "helpers.fake_step", "params": {"gain": 3.0, "halve_rate": True}}]
+    p = Namespace(signal_freq=100)
+    y, f = preprocess_signal(x, steps, p)              # repeated step + repeated key: allowed (B6)
+    assert f == 50 and y.shape == (2, 4) and np.all(y == 6.0) and p.signal_freq == 50
+    assert not hasattr(p, "gain")                      # step parameters do not leak into the caller's scope
+    with pytest.raises(ValueError, match="already exists"):
+        preprocess_signal(x, steps, Namespace(signal_freq=100), strict_params=True)
+
+
+def test_iter_blocks_and_block_ids(tmp_path):
+    for d in ("HS1-B2", "HS1-B10", "HS1-notes", "HS1-3"):
+        (tmp_path / "Sub1" / d).mkdir(parents=True)
+    got = list(stages.iter_blocks(str(tmp_path), ["Sub1"], [7]))
+    assert [(s, b) for s, b, _ in got] == [(7, 3), (7, 10), (7, 2)] or sorted(b for _, b, _ in got) == [2, 3, 10]
+    assert stages.get_block_id("HS1-B12") == 12 and stages.get_block_id("HS1-x") is None
+
+
+def test_stage_io_wiring():
+    outs = {"preprocess": "/p", "sample_collection": "/s", "channel_selection": "/c"}
+    sc = {}
+    stages._wire_io(outs, "sample_collection", sc)
+    assert sc["params"]["io"]["recording_dir"] == "/p"
+    sc = {"params": {"io": {"sample_dir": "/mine"}}}
+    stages._wire_io(outs, "channel_selection", sc)
+    assert sc["params"]["io"]["sample_dir"] == "/mine"
+    sc = {}
+    stages._wire_io(outs, "training", sc)
+    assert sc["params"]["io"] == {"sample_dir": "/s", "channel_selection_dir": "/c"}
+
+
+def test_dropin_names_resolve():
+    import importlib
+    import decode_tonal_langauge_b200 as pkg
+    pkg.install_dropin()
+    for name in ("preprocess.downsample", "preprocess.signal.downsample", "preprocess.frequency_filter",
+                 "preprocess.zscore_rereference", "preprocess.car_rereference", "preprocess.channel_zscore",
+                 "preprocess.rolling_zscore", "preprocess.preprocessor", "preprocess.pipelines.subject_block",
+                 "preprocess.io.tdt_blocks", "preprocess_main", "extract_samples", "channel_selection_main",
+                 "channel_selection.active", "channel_selection.discriminative", "data_loading.text_align", "main"):
+        mod = importlib.import_module(name)
+        assert mod.__file__.startswith(pkg.DROPIN_DIR), (name, mod.__file__)
+    assert callable(importlib.import_module("preprocess.downsample").run)
+    assert callable(importlib.import_module("preprocess_main").run)         # Appendix B4
+    from channel_selection.utils import get_max_length
+    assert get_max_length(np.array([1, 2, 3, 7, 8, 10, 11, 12, 13])) == 4
