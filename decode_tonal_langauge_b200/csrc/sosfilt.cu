@@ -254,9 +254,22 @@ sos_scan_kernel(const float* __restrict__ x, int64_t C, int64_t T, int64_t ldx,
             for (int i = padlen - 1; i >= 0; --i) (void)sos_step<NSEC>(pb[i], c, s);
         }
     }
-    double v[NS];
+    // matrix-vector recurrence spread over the warp: P lanes per output component, each lane owns
+    // JP columns of M in registers; partial sums meet with xor shuffles, the new state is
+    // re-distributed with one shuffle per owned column.
+    constexpr int P = NS >= 8 ? (NS > 8 ? 2 : 4) : (NS >= 4 ? 4 : 2);
+    constexpr int JP = (NS + P - 1) / P;
+    const int oi = lane / P < NS ? lane / P : NS - 1;     // output component of this lane (clamped for idle lanes)
+    const int jg = lane % P;
+    double mrow[JP], vj[JP];
 #pragma unroll
-    for (int j = 0; j < NSEC; ++j) { v[2 * j] = s[j][0]; v[2 * j + 1] = s[j][1]; }
+    for (int u = 0; u < JP; ++u) {
+        const int j = jg * JP + u;
+        mrow[u] = j < NS ? M.m[oi][j] : 0.0;
+        const int jj = j < NS ? j : 0;
+        vj[u] = (jj & 1) ? s[jj >> 1][1] : s[jj >> 1][0];
+    }
+    double vi = (oi & 1) ? s[oi >> 1][1] : s[oi >> 1][0];  // current state component oi
     double* sp = state + row * nChunks * NS;
     const double* gp = gbuf + row * nChunks * NS;
     const int nG = nChunks - 1;                             // g_0 .. g_{nChunks-2}
@@ -274,23 +287,19 @@ sos_scan_kernel(const float* __restrict__ x, int64_t C, int64_t T, int64_t ldx,
         const int k0 = batch * 32;
         const int cnt = nChunks - k0 < 32 ? nChunks - k0 : 32;
         for (int t = 0; t < cnt; ++t) {
-            if (lane < NS) ss[wib][t][lane] = 0.0;          // placeholder keeps the loop uniform
-#pragma unroll
-            for (int i = 0; i < NS; ++i) if (lane == i) ss[wib][t][i] = v[i];
+            if (jg == 0 && lane / P < NS) ss[wib][t][oi] = vi;
             if (k0 + t + 1 < nChunks) {
-                double nv[NS];
+                double acc = jg == 0 ? gs[wib][batch & 1][t][oi] : 0.0;
 #pragma unroll
-                for (int i = 0; i < NS; ++i) {
-                    double acc0 = gs[wib][batch & 1][t][i], acc1 = 0.0;
+                for (int u = 0; u < JP; ++u) acc = fma(mrow[u], vj[u], acc);
 #pragma unroll
-                    for (int j = 0; j < NS; j += 2) {
-                        acc0 = fma(M.m[i][j], v[j], acc0);
-                        acc1 = fma(M.m[i][j + 1], v[j + 1], acc1);
-                    }
-                    nv[i] = acc0 + acc1;
+                for (int o = P / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                vi = acc;
+#pragma unroll
+                for (int u = 0; u < JP; ++u) {
+                    const int j = jg * JP + u;
+                    vj[u] = __shfl_sync(0xffffffffu, acc, (j < NS ? j : 0) * P);
                 }
-#pragma unroll
-                for (int i = 0; i < NS; ++i) v[i] = nv[i];
             }
         }
         __syncwarp();

@@ -89,7 +89,8 @@ def test_yaml_pipeline_end_to_end(tmp_path):
 
     # ---- preprocess stage: directory name, provenance, block files
     setup = outputs["preprocess"]
-    assert os.path.basename(setup) == stages.generate_setup_name(cfg["preprocess"]["params"]["modalities"])
+    on_disk = yaml.safe_load(path.read_text())      # the name hashes the parameter reprs in FILE order
+    assert os.path.basename(setup) == stages.generate_setup_name(on_disk["preprocess"]["params"]["modalities"])
     assert "preprocess" in yaml.safe_load(open(os.path.join(setup, "config.yaml")))
     ecog = np.load(os.path.join(setup, "subject_1", "B1_ecog.npz"))
     audio = np.load(os.path.join(setup, "subject_1", "B1_audio.npz"))
