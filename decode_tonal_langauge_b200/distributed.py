@@ -1,0 +1,135 @@
+"""Multi-GPU plumbing: one process per GPU, ``torch.distributed`` (NCCL over NVLink).
+
+The path shards two ways:
+
+* **sessions / blocks** are independent (ref: preprocess/pipelines/subject_block.py:74-101 loops
+  blocks with no cross-block state): ``assign_sessions`` deals them round-robin, no collective;
+* **channels** of one recording: every step is row-independent except CAR, whose only
+  cross-channel quantity is the per-timestep sum over the included channels
+  (ref: preprocess/signal/car_rereference.py:34-39).  Each rank owns a contiguous block of
+  rows, ``ecog_car_colsum`` produces its partial sums, ONE ``all_reduce(SUM)`` of T floats
+  runs between the two kernel enqueues, and ``ecog_car_apply`` subtracts the global mean.
+  Channel scores / selected sets are all-gathered at the end.
+
+``backend`` is the object providing ``car_colsum`` / ``car_apply`` (default: the CUDA ops).
+The CPU test-suite injects a numpy backend to exercise this file over ``gloo``; the product
+never does.
+"""
+from __future__ import annotations
+
+from argparse import Namespace
+from copy import deepcopy
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced partition of ``range(n)``: the first ``n % world`` ranks get one extra."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def assign_sessions(n_sessions: int, rank: int, world: int) -> List[int]:
+    """Round-robin deal of independent sessions (no communication)."""
+    return list(range(rank, n_sessions, world))
+
+
+def _default_backend():
+    from . import ops
+    return ops
+
+
+def car_sharded(x_local: torch.Tensor, c_lo: int, n_channels: int, exclude_channels: Sequence[int] = (),
+                group=None, backend=None) -> torch.Tensor:
+    """CAR of a channel shard.  ``x_local`` holds global rows [c_lo, c_lo + x_local.shape[0])."""
+    backend = backend or _default_backend()
+    if not isinstance(exclude_channels, (list, tuple)):
+        raise ValueError("exclude_channels must be a list of integers.")
+    if any(ch < 0 or ch >= n_channels for ch in exclude_channels):
+        raise ValueError("exclude_channels contains invalid channel indices.")
+    c_hi = c_lo + x_local.shape[0]
+    weights = None
+    local_excl = [ch - c_lo for ch in exclude_channels if c_lo <= ch < c_hi]
+    if local_excl:
+        w = np.ones(x_local.shape[0], dtype=np.float32)
+        w[local_excl] = 0.0
+        weights = torch.from_numpy(w).to(x_local.device)
+    partial = backend.car_colsum(x_local, weights)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)     # T floats over NVLink
+    n_included = n_channels - len(set(exclude_channels))
+    return backend.car_apply(x_local, partial, n_included)
+
+
+def preprocess_signal_sharded(x_local, steps: List[dict], block_params: Namespace, c_lo: int, n_channels: int,
+                              group=None, backend=None):
+    """``preprocess_signal`` for a channel shard resident on this rank's device: identical step
+    semantics, except that ``car_rereference`` exchanges the column sums.  Returns
+    ``(local tensor, signal_freq, bands)`` where ``bands`` is the number of concatenated
+    band copies the local rows are organised in (see ``gather_channels``)."""
+    from . import steps as S
+    from .preprocessor import _resolve
+    x = x_local
+    bands = 1
+    for step in steps:
+        scope = Namespace(**vars(block_params))
+        for k, v in (step.get("params") or {}).items():
+            setattr(scope, k, deepcopy(v))
+        name, fn = _resolve(step["module"])
+        if name == "car_rereference":
+            excl = getattr(scope, "exclude_channels", [])
+            # after a multi-band frequency_filter the global layout is band-major; CAR then spans
+            # bands * n_channels rows and this shard holds `bands` disjoint slices of them
+            if bands != 1:
+                raise NotImplementedError("channel-sharded CAR after a multi-band frequency_filter")
+            x = car_sharded(x, c_lo, n_channels, excl, group, backend)
+        else:
+            x = fn(x, scope)
+            if name == "frequency_filter":
+                bands *= max(1, len(getattr(scope, "bands", []) or []))
+        block_params.signal_freq = scope.signal_freq
+    return x, block_params.signal_freq, bands
+
+
+def gather_channels(y_local: torch.Tensor, n_channels: int, bands: int = 1, group=None) -> torch.Tensor:
+    """All-gather shard outputs into the reference's global row order.  A multi-band
+    ``frequency_filter`` concatenates band-major, so rank r's rows [b*Cr, (b+1)*Cr) go to global
+    rows b*C + [c_lo, c_hi)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return y_local
+    T = y_local.shape[1]
+    sizes = [shard_bounds(n_channels, r, world) for r in range(world)]
+    cmax = max(hi - lo for lo, hi in sizes) * bands
+    pad = torch.zeros((cmax, T), dtype=y_local.dtype, device=y_local.device)
+    pad[: y_local.shape[0]] = y_local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    out = torch.empty((bands * n_channels, T), dtype=y_local.dtype, device=y_local.device)
+    for r, (lo, hi) in enumerate(sizes):
+        cr = hi - lo
+        for b in range(bands):
+            out[b * n_channels + lo: b * n_channels + hi] = parts[r][b * cr:(b + 1) * cr]
+    return out
+
+
+def gather_selection(runs_local: torch.Tensor, c_lo: int, n_channels: int, length_threshold: int,
+                     group=None) -> List[int]:
+    """All-gather per-shard longest-run vectors ((C/P,) int32) and apply the strict
+    ``run > length_threshold`` rule (ref: channel_selection/utils.py:73) on the global vector."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        full = runs_local
+    else:
+        sizes = [shard_bounds(n_channels, r, world) for r in range(world)]
+        cmax = max(hi - lo for lo, hi in sizes)
+        pad = torch.zeros(cmax, dtype=runs_local.dtype, device=runs_local.device)
+        pad[: runs_local.shape[0]] = runs_local
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        full = torch.cat([parts[r][: hi - lo] for r, (lo, hi) in enumerate(sizes)])
+    return [int(c) for c in torch.nonzero(full > length_threshold).flatten().cpu().tolist()]
