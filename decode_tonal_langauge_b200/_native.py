@@ -16,14 +16,16 @@ ECOG_E_VALUE = -1
 ECOG_E_CUDA = -2
 ECOG_E_WORKSPACE = -3
 ECOG_E_UNSUPPORTED = -4
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_SECTIONS = 8
+SOS_SCAN = 0
+SOS_WARMUP = 1
 HILBERT_N = 4096
 
 
 class SosPlan(C.Structure):
     _fields_ = [("nsec", C.c_int32), ("zero_phase", C.c_int32), ("padlen", C.c_int32),
-                ("chunk", C.c_int32), ("tail", C.c_int32)]
+                ("chunk", C.c_int32), ("tail", C.c_int32), ("mode", C.c_int32), ("threads", C.c_int32)]
 
 
 class FftAxis(C.Structure):
@@ -41,7 +43,7 @@ class ResampleTables(C.Structure):
                 ("tw_big_f_hi", C.c_void_p), ("tw_big_f_lo", C.c_void_p),
                 ("tw_big_i_hi", C.c_void_p), ("tw_big_i_lo", C.c_void_p),
                 ("big_f_split", C.c_int32), ("big_i_split", C.c_int32),
-                ("tw_T", C.c_void_p), ("tw_num", C.c_void_p)]
+                ("tw_T", C.c_void_p), ("tw_num", C.c_void_p), ("bin_gain", C.c_void_p)]
 
 
 _P = C.c_void_p
@@ -69,6 +71,7 @@ PROTOTYPES = {
     "ecog_resample_workspace": (_SZ, [C.POINTER(ResamplePlan), _I64]),
     "ecog_fft_resample": (C.c_int, [_P, _P, _I64, _I64, _I64, C.POINTER(ResamplePlan),
                                     C.POINTER(ResampleTables), _P, _SZ, _P]),
+    "ecog_fir_decimate": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _I32, _I32, _I32, _P]),
     "ecog_epoch_gather": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _I64, _I64, _I32, _P]),
     "ecog_anova_f": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P, _P, _I32, _P, _P, _P]),
     "ecog_sig_runlength": (C.c_int, [_P, _I64, _I64, _F64, _P, _P]),

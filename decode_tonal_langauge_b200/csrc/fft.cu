@@ -217,7 +217,8 @@ fft_tile_kernel(const PassParams P) {
 __global__ void __launch_bounds__(256)
 resample_repack_kernel(const float2* __restrict__ Z, float2* __restrict__ G, long long z_stride,
                        long long g_stride, int N, int Nh, long long T, long long num,
-                       const float2* __restrict__ twT, const float2* __restrict__ twNum) {
+                       const float2* __restrict__ twT, const float2* __restrict__ twNum,
+                       const float* __restrict__ gain) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= Nh) return;
     const float2* z = Z + (long long)blockIdx.y * z_stride;
@@ -235,6 +236,7 @@ resample_repack_kernel(const float2* __restrict__ Z, float2* __restrict__ G, lon
         // X = 0.5 sum - 0.5 i wd
         float2 x = make_float2(0.5f * (sum.x + wd.y), 0.5f * (sum.y - wd.x));
         float f = s * (kk == mh ? nyq : 1.0f);
+        if (gain) f *= __ldg(&gain[kk]);                                 // 1 / H1[k] of the FIR pre-decimator
         x.x *= f; x.y *= f;
         if (kk == 0 || kk == Nh) x.y = 0.f;                              // irfft ignores these imaginary parts
         return x;
@@ -366,7 +368,8 @@ extern "C" int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_
     {
         dim3 grid((unsigned)ceil_div(Nh, 256), (unsigned)C);
         resample_repack_kernel<<<grid, 256, 0, st>>>(bufZ, bufG, N, Nh, (int)N, (int)Nh, T, num,
-                                                     (const float2*)tb->tw_T, (const float2*)tb->tw_num);
+                                                     (const float2*)tb->tw_T, (const float2*)tb->tw_num,
+                                                     tb->bin_gain);
         ECOG_TRY(check_launch("resample_repack"));
     }
     // ---- inverse pass A (conjugated input)

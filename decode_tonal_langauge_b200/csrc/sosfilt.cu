@@ -310,6 +310,225 @@ sos_scan_kernel(const float* __restrict__ x, int64_t C, int64_t T, int64_t ldx,
     }
 }
 
+// ------------------------------------------------------------------ warm-up path
+// Single kernel per sweep, no scan: when the cascade forgets a zero-state start within
+// `tail` samples (max |A^tail| < 1e-10, decided by the host) a chunk's true start state is
+// reproduced by running the recurrence from a ZERO state over the `tail` samples that precede
+// the chunk.  One thread = one chunk: stages -tail/16 .. -1 are the warm-up (loads only),
+// stages 0 .. L/16-1 filter the chunk and are written.  Chunks whose warm-up would cross the
+// row edge are exact instead: the filtfilt start-up state (zi * ext[0] pushed through the odd
+// extension pad) is injected at the stage where the row starts.  Redundant work is tail/L,
+// against a full extra pass for the scan path, and the chunk length is chosen for a few
+// warps per scheduler only (the FP64 pipe saturates early), which makes L long.
+// Thread q -> (row q / nChunks, chunk q % nChunks): a CTA walks neighbouring chunks of one row
+// (few DRAM pages / TLB entries live per CTA).
+// The backward sweep cannot run in place (its warm-up reads the forward result of the
+// neighbouring chunk), so the forward result lives in the workspace.
+template <int NSEC, bool REV, bool VEC, int NT>
+__global__ void __launch_bounds__(NT, 1024 / NT)
+sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, int64_t T,
+                int64_t ldx, int64_t ldy, int L, int tail, int nChunks, int padlen, int zero_phase,
+                SosCoef coef, double* __restrict__ padbuf) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* tiles = reinterpret_cast<float*>(smem_raw);                                   // [kRing][NT][kPitch]
+    int64_t* gbase = reinterpret_cast<int64_t*>(tiles + (size_t)kRing * NT * kPitch);    // [NT] row
+    int* cedge = reinterpret_cast<int*>(gbase + NT);                                     // [NT] a (fwd) / b (rev)
+    int* culo = cedge + NT;                                                              // [NT] first valid logical offset
+    int* cuhi = culo + NT;                                                               // [NT] one past the last
+
+    const int tid = threadIdx.x;
+    const int64_t q = (int64_t)blockIdx.x * NT + tid;
+    const bool valid = q < C * nChunks;
+    const int64_t row = valid ? q / nChunks : 0;
+    const int k = valid ? (int)(q - row * nChunks) : 0;
+    int64_t a, b;
+    if (!REV) { a = (int64_t)k * L; b = a + L < T ? a + L : T; }
+    else      { b = T - (int64_t)k * L; a = b - L > 0 ? b - L : 0; }
+    const int64_t before = REV ? T - b : a;            // samples between the row edge and the chunk, sweep order
+    const int ulo = valid ? (before < tail ? -(int)before : -tail) : 0;
+    const int uhi = valid ? (int)(b - a) : 0;
+    gbase[tid] = row;
+    cedge[tid] = (int)(REV ? b : a);
+    culo[tid] = ulo;
+    cuhi[tid] = uhi;
+    __syncthreads();
+
+    double c[NSEC][5], s[NSEC][2];
+#pragma unroll
+    for (int j = 0; j < NSEC; ++j) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) c[j][i] = coef.c[j][i];
+        s[j][0] = 0.0; s[j][1] = 0.0;
+    }
+    // chunks that see the row edge get the exact start-up at the stage where the row starts
+    const bool inject = valid && before <= tail;
+    const int s_inject = inject ? -(int)(before / kSub) : (1 << 30);
+
+    const int nStages = L / kSub;
+    const int first = -(tail / kSub);
+
+    // cooperative stage loader: VEC -> 4 pieces of 16 B per row, else 16 pieces of 4 B
+    auto issue = [&](int stage) {
+        if (stage < nStages) {
+            float* dst = tiles + (size_t)((stage - first) % kRing) * NT * kPitch;
+            if (VEC) {
+                for (int i = tid; i < NT * 4; i += NT) {
+                    const int r = i >> 2, p = i & 3;
+                    int u0; int64_t off;
+                    if (!REV) { u0 = stage * kSub + 4 * p; off = (int64_t)cedge[r] + u0; }
+                    else { u0 = stage * kSub + 12 - 4 * p; off = (int64_t)cedge[r] - u0 - 4; }
+                    const bool ok = u0 >= culo[r] && u0 + 4 <= cuhi[r];
+                    const float* g = x + gbase[r] * ldx + (ok ? off : 0);
+                    cp_async16_zfill(dst + r * kPitch + 4 * p, g, ok);
+                }
+            } else {
+                for (int i = tid; i < NT * kSub; i += NT) {
+                    const int r = i / kSub, p = i - r * kSub;
+                    int u; int64_t off;
+                    if (!REV) { u = stage * kSub + p; off = (int64_t)cedge[r] + u; }
+                    else { u = stage * kSub + 15 - p; off = (int64_t)cedge[r] - u - 1; }
+                    const bool ok = u >= culo[r] && u < cuhi[r];
+                    const float* g = x + gbase[r] * ldx + (ok ? off : 0);
+                    cp_async4_zfill(dst + r * kPitch + p, g, ok);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    issue(first);
+    for (int st = first; st < nStages; ++st) {
+        cp_async_wait<0>();
+        __syncthreads();
+        issue(st + 1);
+        if (st == s_inject && zero_phase) {
+            // filtfilt start-up: zi * ext[0], then the odd-extension pad (zero state for the causal filter)
+            if (!REV) {
+                const float* xr = x + row * ldx;
+                const float x0 = xr[0];
+                const float e0 = 2.0f * x0 - xr[padlen];
+#pragma unroll
+                for (int j = 0; j < NSEC; ++j) { s[j][0] = coef.zi[j][0] * (double)e0; s[j][1] = coef.zi[j][1] * (double)e0; }
+                for (int i = 0; i < padlen; ++i) {
+                    const float e = 2.0f * x0 - xr[padlen - i];
+                    (void)sos_step<NSEC>((double)e, c, s);
+                }
+            } else {
+                const double* pb = padbuf + row * padlen;
+                const double y0 = pb[padlen - 1];
+#pragma unroll
+                for (int j = 0; j < NSEC; ++j) { s[j][0] = coef.zi[j][0] * y0; s[j][1] = coef.zi[j][1] * y0; }
+                for (int i = padlen - 1; i >= 0; --i) (void)sos_step<NSEC>(pb[i], c, s);
+            }
+        }
+        float* mine = tiles + (size_t)((st - first) % kRing) * NT * kPitch + tid * kPitch;
+        float4 xin[kSub / 4];
+#pragma unroll
+        for (int v = 0; v < kSub / 4; ++v) {
+            if (!REV) {
+                xin[v] = *reinterpret_cast<const float4*>(mine + 4 * v);
+            } else {
+                float4 t4 = *reinterpret_cast<const float4*>(mine + (kSub - 4 - 4 * v));
+                xin[v] = make_float4(t4.w, t4.z, t4.y, t4.x);
+            }
+        }
+        const bool write = st >= 0;
+#pragma unroll
+        for (int v = 0; v < kSub / 4; ++v) {
+            float4 yv;
+            const float4 xv = xin[v];
+            const int base = st * kSub + 4 * v;        // logical offset of the first of four samples
+            if (base >= ulo && base + 4 <= uhi) {
+                yv.x = (float)sos_step<NSEC>((double)xv.x, c, s);
+                yv.y = (float)sos_step<NSEC>((double)xv.y, c, s);
+                yv.z = (float)sos_step<NSEC>((double)xv.z, c, s);
+                yv.w = (float)sos_step<NSEC>((double)xv.w, c, s);
+            } else {   // outside the row / ragged chunk end: zero filled input, state frozen
+                yv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (base + 0 >= ulo && base + 0 < uhi) yv.x = (float)sos_step<NSEC>((double)xv.x, c, s);
+                if (base + 1 >= ulo && base + 1 < uhi) yv.y = (float)sos_step<NSEC>((double)xv.y, c, s);
+                if (base + 2 >= ulo && base + 2 < uhi) yv.z = (float)sos_step<NSEC>((double)xv.z, c, s);
+                if (base + 3 >= ulo && base + 3 < uhi) yv.w = (float)sos_step<NSEC>((double)xv.w, c, s);
+            }
+            if (write) {
+                if (!REV) *reinterpret_cast<float4*>(mine + 4 * v) = yv;
+                else *reinterpret_cast<float4*>(mine + (kSub - 4 - 4 * v)) = make_float4(yv.w, yv.z, yv.y, yv.x);
+            }
+        }
+        if (write) {
+            __syncthreads();
+            const float* out_tile = tiles + (size_t)((st - first) % kRing) * NT * kPitch;
+            if (VEC) {
+                for (int i = tid; i < NT * 4; i += NT) {
+                    const int r = i >> 2, p = i & 3;
+                    int u0; int64_t off;
+                    if (!REV) { u0 = st * kSub + 4 * p; off = (int64_t)cedge[r] + u0; }
+                    else { u0 = st * kSub + 12 - 4 * p; off = (int64_t)cedge[r] - u0 - 4; }
+                    if (u0 + 4 <= cuhi[r]) {
+                        float4 v4 = *reinterpret_cast<const float4*>(out_tile + r * kPitch + 4 * p);
+                        *reinterpret_cast<float4*>(y + gbase[r] * ldy + off) = v4;
+                    }
+                }
+            } else {
+                for (int i = tid; i < NT * kSub; i += NT) {
+                    const int r = i / kSub, p = i - r * kSub;
+                    int u; int64_t off;
+                    if (!REV) { u = st * kSub + p; off = (int64_t)cedge[r] + u; }
+                    else { u = st * kSub + 15 - p; off = (int64_t)cedge[r] - u - 1; }
+                    if (u < cuhi[r]) y[gbase[r] * ldy + off] = out_tile[r * kPitch + p];
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // forward sweep: the thread that owns a row's last chunk runs on through the right odd-extension
+    // pad (float32 like scipy's odd_ext) and keeps the filtered pad in float64 for the backward start-up
+    if (!REV && zero_phase && valid && k == nChunks - 1) {
+        const float* xr = x + row * ldx;
+        const float xe = xr[T - 1];
+        double* pb = padbuf + row * padlen;
+        for (int i = 0; i < padlen; ++i) {
+            const float e = 2.0f * xe - xr[T - 2 - i];
+            pb[i] = sos_step<NSEC>((double)e, c, s);
+        }
+    }
+}
+
+template <int NSEC, bool REV, int NT>
+static int launch_warm(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                       const ecog_sos_plan& p, int nChunks, const SosCoef& coef, double* padbuf, bool vec,
+                       cudaStream_t st) {
+    const size_t smem = ((size_t)kRing * NT * kPitch) * sizeof(float) + (size_t)NT * (sizeof(int64_t) + 3 * sizeof(int));
+    const unsigned grid = (unsigned)ceil_div(C * nChunks, NT);
+    if (vec) {
+        auto k = sos_warm_kernel<NSEC, REV, true, NT>;
+        ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, NT, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, p.zero_phase, coef, padbuf);
+    } else {
+        auto k = sos_warm_kernel<NSEC, REV, false, NT>;
+        ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, NT, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, p.zero_phase, coef, padbuf);
+    }
+    return check_launch(REV ? "sos_warm_bwd" : "sos_warm_fwd");
+}
+
+template <int NSEC>
+static int run_sos_warm(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                        const ecog_sos_plan& p, const SosCoef& coef, float* tmp, int64_t ldt, double* padbuf,
+                        cudaStream_t st) {
+    const int nChunks = (int)ceil_div(T, p.chunk);
+    float* mid = p.zero_phase ? tmp : y;
+    const int64_t ldm = p.zero_phase ? ldt : ldy;
+    const bool vec = aligned16(x) && aligned16(y) && aligned16(mid) && T % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldm % 4 == 0;
+    const bool wide = p.threads >= 512;
+    if (wide) ECOG_TRY((launch_warm<NSEC, false, 512>(x, mid, C, T, ldx, ldm, p, nChunks, coef, padbuf, vec, st)));
+    else      ECOG_TRY((launch_warm<NSEC, false, 256>(x, mid, C, T, ldx, ldm, p, nChunks, coef, padbuf, vec, st)));
+    if (!p.zero_phase) return ECOG_OK;
+    if (wide) return launch_warm<NSEC, true, 512>(mid, y, C, T, ldm, ldy, p, nChunks, coef, padbuf, vec, st);
+    return launch_warm<NSEC, true, 256>(mid, y, C, T, ldm, ldy, p, nChunks, coef, padbuf, vec, st);
+}
+
 static size_t sos_smem_bytes() {
     return ((size_t)kRing * kSosThreads * kPitch) * sizeof(float) +
            (size_t)kSosThreads * (sizeof(int64_t) + 2 * sizeof(int));
@@ -359,8 +578,14 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 using namespace ecog;
 
+static int64_t warm_ld(int64_t T) { return (T + 3) / 4 * 4; }
+
 extern "C" size_t ecog_sos_workspace(const ecog_sos_plan* plan, int64_t C, int64_t T) {
     if (!plan || plan->chunk <= 0) return 0;
+    if (plan->mode == ECOG_SOS_WARMUP) {      // filtered right pad + (zero phase) the forward result
+        size_t pad = align_up((size_t)C * (plan->padlen > 0 ? plan->padlen : 1) * sizeof(double), 256);
+        return pad + (plan->zero_phase ? (size_t)C * warm_ld(T) * sizeof(float) : 0);
+    }
     const int64_t nChunks = ceil_div(T, plan->chunk);
     const int nsec_pad = plan->nsec <= 4 ? (plan->nsec == 3 ? 3 : (plan->nsec <= 2 ? plan->nsec : 4))
                                          : (plan->nsec <= 6 ? 6 : 8);
@@ -378,8 +603,10 @@ extern "C" int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, 
     if (C <= 0 || T <= 0 || ldx < T || ldy < T || T >= (int64_t)1 << 31)
         return fail(ECOG_E_VALUE, "ecog_sosfilt: bad shape C=%lld T=%lld", (long long)C, (long long)T);
     if (p.nsec < 1 || p.nsec > ECOG_MAX_SECTIONS) return fail(ECOG_E_VALUE, "ecog_sosfilt: nsec=%d out of range", p.nsec);
-    if (p.chunk < kSub || p.chunk % kSub || p.tail < kSub || p.tail % kSub || p.tail > p.chunk)
-        return fail(ECOG_E_VALUE, "ecog_sosfilt: chunk=%d tail=%d must be multiples of %d with tail<=chunk", p.chunk, p.tail, kSub);
+    if (p.chunk < kSub || p.chunk % kSub || p.tail < 0 || p.tail % kSub)
+        return fail(ECOG_E_VALUE, "ecog_sosfilt: chunk=%d tail=%d must be multiples of %d", p.chunk, p.tail, kSub);
+    if (p.mode == ECOG_SOS_SCAN && (p.tail < kSub || p.tail > p.chunk))
+        return fail(ECOG_E_VALUE, "ecog_sosfilt: scan mode needs %d <= tail=%d <= chunk=%d", kSub, p.tail, p.chunk);
     if (p.zero_phase) {
         if (!h_zi) return fail(ECOG_E_VALUE, "ecog_sosfilt: zero_phase needs h_zi");
         if (p.padlen < 1) return fail(ECOG_E_VALUE, "ecog_sosfilt: zero_phase needs padlen >= 1");
@@ -387,7 +614,11 @@ extern "C" int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, 
             return fail(ECOG_E_VALUE, "The length of the input vector x must be greater than padlen, which is %d.", p.padlen);
     }
     const int nChunks = (int)ceil_div(T, p.chunk);
-    if (nChunks > 1 && !h_M) return fail(ECOG_E_VALUE, "ecog_sosfilt: chunked rows need the chunk transition matrix h_M");
+    if (p.mode != ECOG_SOS_SCAN && p.mode != ECOG_SOS_WARMUP) return fail(ECOG_E_VALUE, "ecog_sosfilt: unknown mode %d", p.mode);
+    if (p.mode == ECOG_SOS_WARMUP && !p.zero_phase && d_x == d_y)
+        return fail(ECOG_E_VALUE, "ecog_sosfilt: the causal warm-up path cannot run in place");
+    if (p.mode == ECOG_SOS_SCAN && nChunks > 1 && !h_M)
+        return fail(ECOG_E_VALUE, "ecog_sosfilt: chunked rows need the chunk transition matrix h_M");
     if (workspace_bytes < ecog_sos_workspace(plan, C, T))
         return fail(ECOG_E_WORKSPACE, "ecog_sosfilt: workspace %zu < %zu", workspace_bytes, ecog_sos_workspace(plan, C, T));
 
@@ -416,11 +647,25 @@ extern "C" int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, 
         for (int i = 0; i < n0; ++i)
             for (int j = 0; j < n0; ++j) M.m[i][j] = h_M[i * n0 + j];
     }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p.mode == ECOG_SOS_WARMUP) {
+        double* padbuf = (double*)d_workspace;
+        const size_t pad = align_up((size_t)C * (p.padlen > 0 ? p.padlen : 1) * sizeof(double), 256);
+        float* tmp = (float*)((char*)d_workspace + pad);
+        const int64_t ldt = warm_ld(T);
+        switch (ns) {
+            case 1: return run_sos_warm<1>(d_x, d_y, C, T, ldx, ldy, p, coef, tmp, ldt, padbuf, st);
+            case 2: return run_sos_warm<2>(d_x, d_y, C, T, ldx, ldy, p, coef, tmp, ldt, padbuf, st);
+            case 3: return run_sos_warm<3>(d_x, d_y, C, T, ldx, ldy, p, coef, tmp, ldt, padbuf, st);
+            case 4: return run_sos_warm<4>(d_x, d_y, C, T, ldx, ldy, p, coef, tmp, ldt, padbuf, st);
+            case 6: return run_sos_warm<6>(d_x, d_y, C, T, ldx, ldy, p, coef, tmp, ldt, padbuf, st);
+            default: return run_sos_warm<8>(d_x, d_y, C, T, ldx, ldy, p, coef, tmp, ldt, padbuf, st);
+        }
+    }
     const size_t states = align_up((size_t)C * nChunks * 2 * ns * sizeof(double), 256);
     double* state = (double*)d_workspace;
     double* gbuf = (double*)((char*)d_workspace + states);
     double* padbuf = (double*)((char*)d_workspace + 2 * states);
-    cudaStream_t st = (cudaStream_t)stream;
     switch (ns) {
         case 1: return run_sos<1>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, gbuf, padbuf, st);
         case 2: return run_sos<2>(d_x, d_y, C, T, ldx, ldy, p, coef, M, state, gbuf, padbuf, st);

@@ -245,6 +245,32 @@ def choose_chunk(C: int, T: int, chunk: Optional[int] = None) -> int:
     return int(L)
 
 
+WARM_EPS = 1e-10          # zero-input response bound that makes a zero-state warm-up exact enough
+WARM_MAX_OVERHEAD = 0.75  # use the warm-up path only while tail / chunk stays below this
+
+
+def choose_warm_chunk(C: int, T: int, threads_per_sm: int = 512) -> int:
+    """Chunk length of the warm-up path: C * ceil(T/chunk) chunk-threads = one wave of
+    148 SMs x threads_per_sm.  Few warps per scheduler already saturate the FP64 pipe, and
+    long chunks keep the redundant warm-up (tail / chunk) small."""
+    n_chunks = max(1, (NUM_SMS * threads_per_sm) // max(C, 1))
+    L = -(-T // n_chunks)
+    return int(max(-(-L // SUB) * SUB, 1024))
+
+
+def warm_tail(design: "SosDesign", limit: int) -> int:
+    """Warm-up length (multiple of 16) after which max|A^n| < WARM_EPS, or -1 if > limit."""
+    t = _warm_tail(design.sos.tobytes(), design.nsec, int(limit))
+    return t
+
+
+@functools.lru_cache(maxsize=256)
+def _warm_tail(sos_bytes: bytes, nsec: int, limit: int) -> int:
+    sos = np.frombuffer(sos_bytes, dtype=np.float64).reshape(nsec, 6)
+    t = response_tail(sos, limit + SUB, WARM_EPS)
+    return t if t <= limit else -1
+
+
 @dataclass(frozen=True)
 class SosDesign:
     sos: np.ndarray            # (nsec, 6)

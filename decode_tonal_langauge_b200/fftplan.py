@@ -137,6 +137,61 @@ def resample_plan(T: int, num: int) -> ResamplePlan:
     return ResamplePlan(T, num, big_plan(T // 2), big_plan(Nh), tw_T, tw_num)
 
 
+# ------------------------------------------------------- two-stage resampling
+FIR_MAX_TAPS = 256
+FIR_ATTENUATION_DB = 120.0
+
+
+@dataclass(frozen=True)
+class PreDecimation:
+    D: int                  # integer decimation factor of the FIR stage
+    taps: np.ndarray        # float32 (ntaps,), ntaps % 4 == 0 (zero padded), DC gain 1
+    offset: int             # y1[m] = sum_j taps[j] x[(m D + j - offset) mod T]; offset % 4 == 0
+    bin_gain: np.ndarray    # float32 (num/2 + 1,): 1 / H1[k], H1 = DFT_T of the (float32) taps
+
+
+@functools.lru_cache(maxsize=16)
+def predecimation(T: int, num: int):
+    """FIR pre-decimator for ``resample(T -> num)`` or None when the ratio is too small.
+
+    The brick wall keeps bins k <= num/2 of the T-point spectrum.  Decimating by D folds bin
+    T/D - k onto k, so the FIR must pass [0, num/2] (any non-zero gain: it is divided out
+    bin by bin) and stop [T/D - num/2, T/2] by FIR_ATTENUATION_DB.  Kaiser design in float64,
+    rounded to float32 once; the compensation uses the ROUNDED taps' exact response."""
+    from scipy import signal as sp_signal
+    from scipy import fft as sp_fft
+    if num >= T or num % 2:
+        return None
+    for D in (4, 2):
+        if T % D or (T // D) % 2:
+            continue
+        T1 = T // D
+        if T1 < 1.15 * num:
+            continue
+        f_pass = num / T                      # in units of the input Nyquist frequency
+        f_stop = 2.0 / D - num / T
+        ntaps, beta = sp_signal.kaiserord(FIR_ATTENUATION_DB, f_stop - f_pass)
+        ntaps |= 1                            # odd -> symmetric about an integer sample
+        if ntaps + 3 > FIR_MAX_TAPS or ntaps >= T:
+            continue
+        h = sp_signal.firwin(ntaps, 0.5 * (f_pass + f_stop), window=("kaiser", beta))
+        c = (ntaps - 1) // 2
+        lead = (-c) % 4                       # leading zeros so that the centre offset is a multiple of 4
+        total = -(-(lead + ntaps) // 4) * 4
+        taps = np.zeros(total, dtype=np.float32)
+        taps[lead:lead + ntaps] = h.astype(np.float32)
+        offset = c + lead
+        # exact response of the rounded taps on the T-point grid (zero-phase arrangement)
+        k = np.zeros(T, dtype=np.float64)
+        idx = (np.arange(total) - offset) % T
+        np.add.at(k, idx, taps.astype(np.float64))
+        H1 = sp_fft.rfft(k)[: num // 2 + 1]
+        if np.max(np.abs(H1.imag)) > 1e-9 or np.min(H1.real) < 0.5:
+            continue                          # not a usable pass band (cannot happen for a Kaiser low-pass)
+        return PreDecimation(D, taps, int(offset), (1.0 / H1.real).astype(np.float32))
+    return None
+
+
 # --------------------------------------------------------------------- Hilbert
 HILBERT_N = 4096
 

@@ -148,34 +148,58 @@ def zscore(x: torch.Tensor, t0: int = 0, t1: Optional[int] = None, nan_to_zero: 
 
 
 # ------------------------------------------------------------------------ K3
+def _sos_threads_per_sm() -> int:
+    import os
+    return int(os.environ.get("ECOG_SOS_TPS", "512"))
+
+
 def sosfilt(x: torch.Tensor, dsg: D.SosDesign, chunk: Optional[int] = None,
-            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, mode: Optional[str] = None) -> torch.Tensor:
+    """Biquad cascade, zero-phase (filtfilt semantics) or causal.  ``mode``: "warm" (one kernel
+    per sweep, start states from a zero-state warm-up), "scan" (exact carry scan) or None =
+    warm-up whenever the cascade forgets fast enough for the chunk length."""
     x = as_signal(x)
     Cn, T = x.shape
     if dsg.zero_phase and T <= dsg.padlen:
         raise ValueError(f"The length of the input vector x must be greater than padlen, which is {dsg.padlen}.")
-    L = D.choose_chunk(Cn, T, chunk)
-    n_chunks = -(-T // L)
-    if n_chunks > 1:
-        M, tail = D.chunk_ops(dsg, L)
-    else:
-        M, tail = None, L
-    plan = nat.SosPlan(dsg.nsec, 1 if dsg.zero_phase else 0, dsg.padlen, L, tail)
-    nbytes = lib.ecog_sos_workspace(C.byref(plan), Cn, T)
-    ws = workspace(nbytes, x.device)
     y = out if out is not None else torch.empty_like(x, memory_format=torch.contiguous_format)
     sos = np.ascontiguousarray(dsg.sos, dtype=np.float64)
     zi = None if dsg.zi is None else np.ascontiguousarray(dsg.zi, dtype=np.float64)
-    Mh = None if M is None else np.ascontiguousarray(M, dtype=np.float64)
+    Mh = None
+    plan = None
+    if mode in (None, "warm"):
+        tps = _sos_threads_per_sm()
+        L = int(chunk) if chunk is not None else D.choose_warm_chunk(Cn, T, tps)
+        if L % D.SUB:
+            raise ValueError(f"chunk must be a multiple of {D.SUB}")
+        n_chunks = -(-T // L)
+        limit = 1 << 30 if mode == "warm" else int(D.WARM_MAX_OVERHEAD * L)
+        tail = 0 if n_chunks == 1 else D.warm_tail(dsg, min(limit, T + D.SUB))
+        if n_chunks > 1 and tail < 0 and mode == "warm":
+            raise ValueError("the filter does not forget its state within the row; use mode='scan'")
+        if tail >= 0:
+            threads = 512 if Cn * n_chunks >= 2 * D.NUM_SMS * 512 else 256
+            plan = nat.SosPlan(dsg.nsec, 1 if dsg.zero_phase else 0, dsg.padlen, L, tail, nat.SOS_WARMUP, threads)
+    if plan is None:
+        L = D.choose_chunk(Cn, T, chunk)
+        n_chunks = -(-T // L)
+        if n_chunks > 1:
+            Mm, tail = D.chunk_ops(dsg, L)
+            Mh = np.ascontiguousarray(Mm, dtype=np.float64)
+        else:
+            tail = L
+        plan = nat.SosPlan(dsg.nsec, 1 if dsg.zero_phase else 0, dsg.padlen, L, tail, nat.SOS_SCAN, 512)
+    nbytes = lib.ecog_sos_workspace(C.byref(plan), Cn, T)
+    ws = workspace(nbytes, x.device, "sos")
     nat.check(lib.ecog_sosfilt(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), C.byref(plan), _hptr(sos), _hptr(zi),
                                _hptr(Mh), _ptr(ws), ws.numel(), _stream()))
     return y
 
 
 def butter(x: torch.Tensor, freqs, fs, order=4, causal=False, filter_type="bandpass",
-           chunk: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+           chunk: Optional[int] = None, out: Optional[torch.Tensor] = None, mode: Optional[str] = None) -> torch.Tensor:
     """ref: frequency_filter.py:187-229 (butter_filter keyword names kept)."""
-    return sosfilt(x, D.butter_design(freqs, fs, order, causal, filter_type), chunk, out=out)
+    return sosfilt(x, D.butter_design(freqs, fs, order, causal, filter_type), chunk, out=out, mode=mode)
 
 
 # ------------------------------------------------------------------------ K4
@@ -232,10 +256,19 @@ def _axis(ap: FP.AxisPlan) -> nat.FftAxis:
     return a
 
 
-def fft_resample(x: torch.Tensor, num: int) -> torch.Tensor:
+def fir_decimate(x: torch.Tensor, taps: np.ndarray, offset: int, D: int) -> torch.Tensor:
+    """y[c, m] = sum_j taps[j] x[c, (m D + j - offset) mod T] (circular), float32."""
     x = as_signal(x)
     Cn, T = x.shape
-    num = int(num)
+    taps = np.ascontiguousarray(taps, dtype=np.float32)
+    y = torch.empty((Cn, T // int(D)), dtype=torch.float32, device=x.device)
+    nat.check(lib.ecog_fir_decimate(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), _hptr(taps), int(taps.shape[0]),
+                                    int(offset), int(D), _stream()))
+    return y
+
+
+def _fft_resample(x: torch.Tensor, num: int, bin_gain: Optional[np.ndarray], gain_key=None) -> torch.Tensor:
+    Cn, T = x.shape
     rp = FP.resample_plan(int(T), num)
     dev = x.device
     key = ("resample", T, num)
@@ -250,6 +283,10 @@ def fft_resample(x: torch.Tensor, num: int) -> torch.Tensor:
         dt = t(name, arr)
         keep.append(dt)
         setattr(tables, name, dt.data_ptr())
+    if bin_gain is not None:
+        g = _dev_table(("resample_gain", gain_key, num), lambda: bin_gain, dev)
+        keep.append(g)
+        tables.bin_gain = g.data_ptr()
     tables.big_f_split = FP.BIG_SPLIT
     tables.big_i_split = FP.BIG_SPLIT
     plan = nat.ResamplePlan()
@@ -263,6 +300,27 @@ def fft_resample(x: torch.Tensor, num: int) -> torch.Tensor:
     nat.check(lib.ecog_fft_resample(_ptr(x), _ptr(y), Cn, _ld(x), _ld(y), C.byref(plan), C.byref(tables),
                                     _ptr(ws), ws.numel(), _stream()))
     return y
+
+
+def fft_resample(x: torch.Tensor, num: int, two_stage: Optional[bool] = None) -> torch.Tensor:
+    """scipy.signal.resample(x, num, axis=1) for real rows (ref: downsample.py:21-27).
+
+    Large down-sampling ratios run in two stages: a circular FIR low-pass + decimate by D
+    (ecog_fir_decimate), then the brick wall on the T/D-sample rows with the FIR's pass-band
+    response divided out bin by bin.  ``two_stage=False`` forces the single whole-row FFT."""
+    x = as_signal(x)
+    Cn, T = x.shape
+    num = int(num)
+    pre = FP.predecimation(int(T), num) if two_stage in (None, True) else None
+    if pre is not None:
+        try:
+            FP.resample_plan(int(T) // pre.D, num)
+        except NotImplementedError:
+            pre = None
+    if pre is None:
+        return _fft_resample(x, num, None)
+    x1 = fir_decimate(x, pre.taps, pre.offset, pre.D)
+    return _fft_resample(x1, num, pre.bin_gain, gain_key=(int(T), pre.D))
 
 
 # ------------------------------------------------------------------------ K8

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ECOG_ABI_VERSION 1
+#define ECOG_ABI_VERSION 2
 
 #define ECOG_OK 0
 #define ECOG_E_VALUE (-1)     /* bad argument (reference raises ValueError)          */
@@ -87,8 +87,17 @@ typedef struct {
     int32_t zero_phase;  /* 1 = forward-backward with odd padding, 0 = causal        */
     int32_t padlen;      /* filtfilt pad (27 for order-4 band filters); 0 if causal   */
     int32_t chunk;       /* samples per scan chunk, multiple of 16                    */
-    int32_t tail;        /* multiple of 16, <= chunk                                  */
+    int32_t tail;        /* multiple of 16; <= chunk in scan mode                     */
+    int32_t mode;        /* ECOG_SOS_SCAN (exact carry scan) or ECOG_SOS_WARMUP        */
+    int32_t threads;     /* warm-up mode: threads per CTA, 256 or 512                 */
 } ecog_sos_plan;
+/* ECOG_SOS_WARMUP: one kernel per sweep; every chunk re-creates its start state by filtering
+ * the `tail` samples before it from a zero state (valid when the host has checked that the
+ * cascade's zero-input response is < 1e-10 after `tail` samples); chunks within `tail` of the
+ * row edge use the exact filtfilt start-up instead.  h_M is not used.  The workspace then
+ * also holds the forward result (C x T float32) of a zero-phase call.                       */
+#define ECOG_SOS_SCAN 0
+#define ECOG_SOS_WARMUP 1
 #define ECOG_MAX_SECTIONS 8
 size_t ecog_sos_workspace(const ecog_sos_plan* plan, int64_t C, int64_t T);
 int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
@@ -135,11 +144,25 @@ typedef struct {
     const float *tw_big_f_hi, *tw_big_f_lo, *tw_big_i_hi, *tw_big_i_lo;
     int32_t big_f_split, big_i_split;
     const float *tw_T, *tw_num;
+    const float *bin_gain;   /* optional (NULL = none): num/2 + 1 per-bin gains applied to the kept
+                                spectrum, i.e. 1 / H1[k] of the FIR pre-decimator (ecog_fir_decimate) */
 } ecog_resample_tables;
 size_t ecog_resample_workspace(const ecog_resample_plan* plan, int64_t C);
 int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_t ldx, int64_t ldy,
                       const ecog_resample_plan* plan, const ecog_resample_tables* tables,
                       void* d_workspace, size_t workspace_bytes, ecog_stream_t stream);
+
+/* ------------------------------- K5a: circular FIR low-pass + integer decimation
+ * First stage of the two-stage realisation of downsample.py:21-27 for large ratios:
+ *   y[c, m] = sum_{j<ntaps} h[j] * x[c, (m*D + j - offset) mod T],  m = 0 .. T/D - 1.
+ * The brick wall of scipy.signal.resample is then applied by ecog_fft_resample on the T/D
+ * samples per row, with bin_gain[k] = 1 / H1[k] dividing this stage's (known, non-zero)
+ * pass-band response out exactly; bins k <= num/2 are alias-free to the stop-band
+ * attenuation of h (120 dB Kaiser design, decode_tonal_langauge_b200/fftplan.py).
+ * h_taps: host, ntaps <= 256.  D in {2, 4}; T % D == 0.                               */
+int ecog_fir_decimate(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                      const float* h_taps, int32_t ntaps, int32_t offset, int32_t D,
+                      ecog_stream_t stream);
 
 /* ------------------------------------------------------- K8: epoch gather
  * replaces data_loading/text_align.py:290-304,331-340,380-394.

@@ -1,8 +1,9 @@
 """Run single operators at chosen shapes (profiling helper for ncu / CUDA-event timing).
 
     python scripts/prof_ops.py hilbert 128 1200000
-    python scripts/prof_ops.py resample 32 7200000
-    python scripts/prof_ops.py notch|bandpass|car|zscore C T
+    python scripts/prof_ops.py resample|resample1 32 7200000      (two-stage | single whole-row FFT)
+    python scripts/prof_ops.py notch|bandpass|notch_scan|bandpass_scan|car|zscore|fir C T [reps]
+    python scripts/prof_ops.py all 256 7200000                     (every operator, one line each)
 """
 import os
 import sys
@@ -10,28 +11,50 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from decode_tonal_langauge_b200 import fftplan as FP  # noqa: E402
 from decode_tonal_langauge_b200 import ops  # noqa: E402
 
 op, C, T = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 fs = 2000.0
 x = torch.randn((C, T), device="cuda") * 30
-fn = {
+
+
+def fir():
+    pre = FP.predecimation(T, T // 5)
+    return ops.fir_decimate(x, pre.taps, pre.offset, pre.D)
+
+
+FN = {
     "hilbert": lambda: ops.hilbert(x, fs, [70.0, 150.0]),
     "resample": lambda: ops.fft_resample(x, T // 5),
+    "resample1": lambda: ops.fft_resample(x, T // 5, two_stage=False),
+    "fir": fir,
     "notch": lambda: ops.butter(x, [58, 62], fs, 4, False, "bandstop"),
     "bandpass": lambda: ops.butter(x, [70, 150], fs, 4, False, "bandpass"),
+    "notch_scan": lambda: ops.butter(x, [58, 62], fs, 4, False, "bandstop", mode="scan"),
+    "bandpass_scan": lambda: ops.butter(x, [70, 150], fs, 4, False, "bandpass", mode="scan"),
     "car": lambda: ops.car(x),
     "zscore": lambda: ops.zscore(x),
-}[op]
-for _ in range(2):
-    fn()
-torch.cuda.synchronize()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-for _ in range(reps):
-    y = fn()
-e1.record()
-torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / reps
-print(f"{op} C={C} T={T}: {ms:.3f} ms  {C * T / ms / 1e6:.1f} G ch-samp/s")
+}
+
+
+def run(name):
+    fn = FN[name]
+    for _ in range(2):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        y = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    del y
+    print(f"{name} C={C} T={T} tps={os.environ.get('ECOG_SOS_TPS', '512')}: {ms:.3f} ms  "
+          f"{C * T / ms / 1e6:.1f} G ch-samp/s", flush=True)
+
+
+for name in (FN if op == "all" else op.split(",")):
+    run(name)

@@ -53,6 +53,48 @@ def sos_chunk_scan(x32: np.ndarray, design, chunk: int, M: np.ndarray, tail: int
     return out
 
 
+def sos_warm_model(x32: np.ndarray, design, chunk: int, tail: int) -> np.ndarray:
+    """Model of csrc/sosfilt.cu::sos_warm_kernel: every chunk starts from a zero state `tail`
+    samples early, or from the exact filtfilt start-up when the row edge is within `tail`."""
+    sos = design.sos
+    nsec = sos.shape[0]
+    C, T = x32.shape
+    P = design.padlen
+
+    def sweep(u, s0):
+        """u: (T,) samples in sweep order, s0: exact state at u[0] -> float32 result, exact end state"""
+        y = np.empty(T, dtype=np.float32)
+        n_chunks = -(-T // chunk)
+        for k in range(n_chunks):
+            a, b = k * chunk, min((k + 1) * chunk, T)
+            if a <= tail:
+                out, _ = sp_signal.sosfilt(sos, u[:b], zi=s0)
+                y[a:b] = out[a:].astype(np.float32)
+            else:
+                out, _ = sp_signal.sosfilt(sos, u[a - tail:b], zi=np.zeros((nsec, 2)))
+                y[a:b] = out[tail:].astype(np.float32)
+        _, zf = sp_signal.sosfilt(sos, u, zi=s0)      # the last chunk's thread carries the true state on
+        return y, zf
+
+    out = np.empty_like(x32)
+    for c in range(C):
+        x = x32[c]
+        if not design.zero_phase:
+            out[c], _ = sweep(x.astype(np.float64), np.zeros((nsec, 2)))
+            continue
+        left = (np.float32(2.0) * x[0] - x[P:0:-1]).astype(np.float32)
+        right = (np.float32(2.0) * x[-1] - x[-2:-(P + 2):-1]).astype(np.float32)
+        s = design.zi * np.float64(left[0])
+        _, s = sp_signal.sosfilt(sos, left.astype(np.float64), zi=s)
+        yf, s_end = sweep(x.astype(np.float64), s)
+        ypad, _ = sp_signal.sosfilt(sos, right.astype(np.float64), zi=s_end)
+        s = design.zi * ypad[-1]
+        _, s = sp_signal.sosfilt(sos, ypad[::-1], zi=s)
+        yb, _ = sweep(yf[::-1].astype(np.float64), s)
+        out[c] = yb[::-1]
+    return out
+
+
 # ----------------------------------------------------------------------------- FFT models
 def _c(t):  # (n, 2) float32 table -> complex128
     return t[:, 0].astype(np.float64) + 1j * t[:, 1].astype(np.float64)
@@ -102,7 +144,19 @@ def big_fft(z: np.ndarray, plan) -> np.ndarray:
     return X.reshape(-1)                                    # k = p * na + q
 
 
-def resample_model(x32: np.ndarray, plan) -> np.ndarray:
+def fir_decimate_model(x32: np.ndarray, pre) -> np.ndarray:
+    """Model of csrc/firdecim.cu for one row: circular FIR + decimate, float32 accumulation."""
+    T = x32.shape[0]
+    T1 = T // pre.D
+    y = np.zeros(T1, dtype=np.float32)
+    base = np.arange(T1, dtype=np.int64) * pre.D - pre.offset
+    for j, h in enumerate(pre.taps):
+        if h != 0:
+            y += np.float32(h) * x32[(base + j) % T]
+    return y
+
+
+def resample_model(x32: np.ndarray, plan, bin_gain=None) -> np.ndarray:
     """Model of ecog_fft_resample for one row (float32 in, float32 out)."""
     T, num = plan.T, plan.num
     N, Nh = T // 2, num // 2
@@ -114,6 +168,8 @@ def resample_model(x32: np.ndarray, plan) -> np.ndarray:
     Zm = np.conj(Z[(N - k) % N])
     X = 0.5 * (Zk + Zm) - 0.5j * _c(plan.tw_T) * (Zk - Zm)
     Y = X * (num / T)
+    if bin_gain is not None:
+        Y = Y * bin_gain.astype(np.float64)
     Y[k > m // 2] = 0
     if m % 2 == 0 and num != T:
         Y[m // 2] *= 2.0 if num < T else 0.5

@@ -54,6 +54,26 @@ def test_resample_model_vs_oracle(T, num):
     assert max_rel(got, ref) < 2e-6
 
 
+@pytest.mark.parametrize("T,num", [(12000, 2400), (24000, 3200), (60000, 20000), (36000, 4800)])
+def test_two_stage_resample_model_vs_oracle(T, num):
+    """FIR pre-decimation + gain-compensated brick wall == scipy.signal.resample of the whole row."""
+    pre = FP.predecimation(T, num)
+    assert pre is not None and T % pre.D == 0 and pre.offset % 4 == 0 and len(pre.taps) % 4 == 0
+    rng = np.random.default_rng(T + num)
+    x = rng.standard_normal(T).astype(np.float32) * 30          # white: worst case for aliasing
+    x1 = EM.fir_decimate_model(x, pre)
+    got = EM.resample_model(x1, FP.resample_plan(T // pre.D, num), pre.bin_gain)
+    ref = S.fft_resample(x[None].astype(np.float64), num)[0]
+    assert max_rel(got, ref) < 3e-6
+
+
+def test_predecimation_declines_small_ratios():
+    assert FP.predecimation(24000, 12000) is None       # T/2 == num: no transition band
+    assert FP.predecimation(16000, 16000) is None
+    assert FP.predecimation(6000, 9000) is None         # up-sampling
+    assert FP.predecimation(12002, 2400) is None        # T/2 odd: the FFT stage needs even rows
+
+
 def test_resample_odd_lengths_are_declared_unsupported():
     with pytest.raises(NotImplementedError):
         FP.resample_plan(9001, 1800)
@@ -110,6 +130,35 @@ def test_sos_design_and_chunk_scan_model(golden, key, freqs, btype, tol):
         else:   # ill-conditioned design: the long-double rule of SURVEY.md section 8c
             truth = S.filtfilt_pad(d.b, d.a, x, dtype=np.longdouble)
             assert max_rel(y, truth) <= max(1e-5, max_rel(g[key], truth))
+
+
+@pytest.mark.parametrize("key,freqs,btype", [("notch", [58, 62], "bandstop"), ("bandpass", [70, 150], "bandpass")])
+def test_sos_warm_up_model(golden, key, freqs, btype):
+    """The warm-up path (zero-state start `tail` samples early, exact start-up near the row edge)
+    meets the same bar as the exact carry scan."""
+    g = golden("steps")
+    x, fs = g["x"], float(g["fs"])
+    d = D.butter_design(freqs, fs, 4, False, btype)
+    tail = D.warm_tail(d, 1 << 20)
+    assert tail > 0 and tail % 16 == 0
+    for chunk in (1024, 2048):
+        y = EM.sos_warm_model(x, d, chunk, tail)
+        truth = S.filtfilt_pad(d.b, d.a, x, dtype=np.longdouble)
+        assert max_rel(y, truth) <= max(1e-6, 1.05 * max_rel(g[key], truth))
+    # long row: chunks far from the edges really start from zero
+    rng = np.random.default_rng(5)
+    xl = (rng.standard_normal((1, 60000)) * 30).astype(np.float32)
+    if key == "bandpass":
+        y = EM.sos_warm_model(xl, d, 4096, tail)
+        assert max_rel(y, S.butter_filter(xl, freqs, fs, filter_type=btype)) < 1e-6
+
+
+def test_warm_chunk_choice():
+    L = D.choose_warm_chunk(256, 7_200_000, 512)
+    assert L % 16 == 0 and 256 * -(-7_200_000 // L) <= 148 * 512
+    d = D.butter_design([58, 62], 2000.0, 4, False, "bandstop")
+    assert 0 < D.warm_tail(d, int(0.75 * L)) < 0.5 * L           # the C2 notch runs on the warm-up path
+    assert D.warm_tail(d, 4096) == -1                            # short chunks: declined -> scan path
 
 
 def test_causal_design_matches_reference(golden):
