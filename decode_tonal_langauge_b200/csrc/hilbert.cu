@@ -276,11 +276,137 @@ hilbert_env_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T
     }
 }
 
+// ---------------------------------------------------------------- fast path: <= 8 narrow bands
+// Specialisation for banks whose bands fit one row of 256 bins (the high-gamma bank at 2 kHz).
+// The generic kernel is shared-memory-bandwidth bound: per inverse transform every thread moves
+// 65 float2 through shared memory and 31 twiddles through L1.  Here
+//   * the gained, shifted band spectra SG[block][band][256] are built ONCE per CTA (one complex
+//     product per thread and band) straight from the natural-order spectrum;
+//   * an inverse has only 256 non-zero inputs, so its first radix-16 pass is the identity: the
+//     thread (k0, n0) of pass 2 reads its 16 inputs SG[16 n1 + n0] directly (broadcast loads,
+//     one wavefront each) and multiplies by W_256^{n1 k0} W_4096^{n0 k0} held in registers;
+//   * the remaining inter-pass twiddle is W_256^{n0 k1}: a 16 x 16 table in shared memory;
+//   * the exchange buffer alternates between two regions, so one barrier per transform.
+// Per inverse and thread: 16 + 16 + 16 + 16 shared-memory accesses instead of 65 + 31.
+constexpr int kFastBands = 8;
+
+template <bool ENV>
+__global__ void __launch_bounds__(kHT, 2)
+hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t ldx, int64_t ldy,
+                    const float* __restrict__ gain, int nb, BandShift shift, int halo,
+                    const float2* __restrict__ tw, int64_t nBlocks) {
+    extern __shared__ __align__(16) float2 hsm[];
+    float2* bufA = hsm;                                   // [4096 + 256] exchange buffer 0
+    float2* bufB = bufA + (kN + kN / 16);                 // [4096 + 256] exchange buffer 1 / natural-order spectrum
+    float2* SG = bufB + (kN + kN / 16);                   // [2][kFastBands][256] gained band spectra (conjugated)
+    float2* twBs = SG + 2 * kFastBands * 256;             // [16][16] W_256^{n0 k1}, index k1 * 16 + n0
+    const int tid = threadIdx.x;
+    const int64_t ch = blockIdx.y;
+    const int U = kN - 2 * halo;
+    const int64_t b0 = 2 * (int64_t)blockIdx.x, b1 = b0 + 1;
+    const float* xr = x + ch * ldx;
+    const float2* tw1 = tw;                               // [16][256]
+    const float2* tw2 = tw + 16 * kHT;                    // [16][256]
+    const float2* twAg = tw + 32 * kHT;                   // [16][256] W_256^{n1 k0} W_4096^{n0 k0}
+    const int k0 = tid >> 4, k1 = tid & 15;
+    const int nat0 = k0 + 17 * k1;                        // padi(k0 + 16 k1 + 256 k2) = nat0 + 272 k2
+
+    twBs[tid] = __ldg(&tw[48 * kHT + tid]);
+    float2 v[16];
+    {   // two real blocks as one complex signal, circular halo
+        int64_t s0 = (b0 * U - halo) % T; if (s0 < 0) s0 += T;
+        int64_t s1 = (b1 * U - halo) % T; if (s1 < 0) s1 += T;
+        const bool has1 = b1 < nBlocks;
+        const bool wrap = (s0 + kN > T) || (s1 + kN > T);
+        if (!wrap) {
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) {
+                const int i = 256 * n2 + tid;
+                v[n2].x = xr[s0 + i];
+                v[n2].y = has1 ? xr[s1 + i] : 0.f;
+            }
+        } else {
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) {
+                const int i = 256 * n2 + tid;
+                v[n2].x = xr[(s0 + i) % T];
+                v[n2].y = has1 ? xr[(s1 + i) % T] : 0.f;
+            }
+        }
+    }
+    fft4096_pass1(v, bufA, tw1, tid);
+    fft4096_finish(v, bufA, tw2, tid);
+#pragma unroll
+    for (int k2 = 0; k2 < 16; ++k2) bufB[nat0 + 272 * k2] = v[k2];      // natural-order spectrum Z[k]
+    __syncthreads();
+    // conjugate-symmetry split + gain + shift, stored conjugated (inverse = conj-forward FFT):
+    //   block0: conj(Z[k] + conj(Z[N-k])) g,  block1: conj(-i (Z[k] - conj(Z[N-k]))) g,  k = shift + tid
+    for (int band = 0; band < nb; ++band) {
+        const int k = shift.s[band] + tid;
+        const float2 zk = bufB[padi(k)], zm = bufB[padi((kN - k) & (kN - 1))];
+        const float gk = __ldg(&gain[band * 256 + tid]);
+        SG[band * 256 + tid] = make_float2((zk.x + zm.x) * gk, -(zk.y - zm.y) * gk);
+        SG[(kFastBands + band) * 256 + tid] = make_float2((zk.y + zm.y) * gk, (zk.x - zm.x) * gk);
+    }
+    float2 twA[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) twA[n1] = __ldg(&twAg[n1 * kHT + tid]);
+    __syncthreads();
+
+    const int n0 = k1;                                   // pass-2 role of this thread: (k0, n0)
+    float* yr = y + ch * ldy;
+    int flip = 0;
+    for (int sel = 0; sel < 2; ++sel) {
+        float acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+        for (int band = 0; band < nb; ++band) {
+            const float2* sg = SG + (sel * kFastBands + band) * 256 + n0;
+#pragma unroll
+            for (int n1 = 0; n1 < 16; ++n1) v[n1] = cmul(sg[16 * n1], twA[n1]);
+            dft16(v);
+#pragma unroll
+            for (int e = 1; e < 16; ++e) v[e] = cmul(v[e], twBs[e * 16 + n0]);
+            float2* buf = (flip & 1) ? bufB : bufA;
+            ++flip;
+            float2* p2 = buf + 272 * k0 + n0;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) p2[17 * e] = v[e];
+            __syncthreads();
+            const float2* p3 = buf + 17 * tid;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = p3[j];
+            dft16(v);
+            // v[k2] = conj(z[t]) (times a unit phasor when shifted), t = k0 + 16 k1 + 256 k2
+            if (ENV) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] += fast_sqrt(fmaf(v[j].x, v[j].x, v[j].y * v[j].y));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[j] += v[j].x;
+            }
+        }
+        // the buffer the NEXT transform would use was last read before the latest barrier: free
+        float* ob = reinterpret_cast<float*>((flip & 1) ? bufB : bufA);
+        ++flip;
+#pragma unroll
+        for (int k2 = 0; k2 < 16; ++k2) ob[nat0 + 272 * k2] = acc[k2];
+        __syncthreads();
+        const int64_t bb = sel == 0 ? b0 : b1;
+        if (bb < nBlocks) {
+            for (int i = tid; i < U; i += kHT) {
+                const int64_t t = bb * U + i;
+                if (t < T) yr[t] = ob[padi(halo + i)];
+            }
+        }
+    }
+}
+
 }  // namespace ecog
 
 using namespace ecog;
 
-extern "C" size_t ecog_hilbert_twiddle_floats(void) { return (size_t)2 * 16 * kHT * 2; }
+extern "C" size_t ecog_hilbert_twiddle_floats(void) { return (size_t)(3 * 16 * kHT + 256) * 2; }
 
 extern "C" int ecog_hilbert_twiddles(float* h_out) {
     if (!h_out) return fail(ECOG_E_VALUE, "ecog_hilbert_twiddles: null output");
@@ -295,6 +421,16 @@ extern "C" int ecog_hilbert_twiddles(float* h_out) {
             double a2 = -2.0 * PI * (double)((tid & 15) * ((tid >> 4) + 16 * e)) / 4096.0;
             h_out[2 * (16 * kHT + e * kHT + tid) + 0] = (float)cos(a2);
             h_out[2 * (16 * kHT + e * kHT + tid) + 1] = (float)sin(a2);
+            // fast path, pass-2 input: W_256^{n1 k0} W_4096^{n0 k0}, n1 = e, k0 = tid >> 4, n0 = tid & 15
+            double a3 = -2.0 * PI * ((double)(e * (tid >> 4)) / 256.0 + (double)((tid & 15) * (tid >> 4)) / 4096.0);
+            h_out[2 * (32 * kHT + e * kHT + tid) + 0] = (float)cos(a3);
+            h_out[2 * (32 * kHT + e * kHT + tid) + 1] = (float)sin(a3);
+        }
+    for (int k1 = 0; k1 < 16; ++k1)
+        for (int n0 = 0; n0 < 16; ++n0) {   // fast path, pass-2 output: W_256^{n0 k1}
+            double a4 = -2.0 * PI * (double)(n0 * k1) / 256.0;
+            h_out[2 * (48 * kHT + k1 * 16 + n0) + 0] = (float)cos(a4);
+            h_out[2 * (48 * kHT + k1 * 16 + n0) + 1] = (float)sin(a4);
         }
     return ECOG_OK;
 }
@@ -323,6 +459,17 @@ extern "C" int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t
     const size_t smem = (size_t)2 * (kN + kN / 16) * sizeof(float2);
     const float2* tw = reinterpret_cast<const float2*>(d_twiddle);
     cudaStream_t st = (cudaStream_t)stream;
+    if (rows == 1 && nbands <= kFastBands) {
+        const size_t smem8 = ((size_t)2 * (kN + kN / 16) + 2 * kFastBands * 256 + 256) * sizeof(float2);
+        if (envelope) {
+            ECOG_CUDA(cudaFuncSetAttribute(hilbert_env8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+            hilbert_env8_kernel<true><<<grid, kHT, smem8, st>>>(d_x, d_y, T, ldx, ldy, d_gain, nbands, sh, halo, tw, nBlocks);
+        } else {
+            ECOG_CUDA(cudaFuncSetAttribute(hilbert_env8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+            hilbert_env8_kernel<false><<<grid, kHT, smem8, st>>>(d_x, d_y, T, ldx, ldy, d_gain, nbands, sh, halo, tw, nBlocks);
+        }
+        return check_launch("hilbert_env8");
+    }
 #define ECOG_HILBERT_LAUNCH(R)                                                                                   \
     do {                                                                                                         \
         ECOG_CUDA(cudaFuncSetAttribute(hilbert_env_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \

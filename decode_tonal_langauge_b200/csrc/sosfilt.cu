@@ -331,27 +331,33 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
                 SosCoef coef, double* __restrict__ padbuf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);                                   // [kRing][NT][kPitch]
-    int64_t* gbase = reinterpret_cast<int64_t*>(tiles + (size_t)kRing * NT * kPitch);    // [NT] row
-    int* cedge = reinterpret_cast<int*>(gbase + NT);                                     // [NT] a (fwd) / b (rev)
-    int* culo = cedge + NT;                                                              // [NT] first valid logical offset
-    int* cuhi = culo + NT;                                                               // [NT] one past the last
+    int64_t* soff = reinterpret_cast<int64_t*>(tiles + (size_t)kRing * NT * kPitch);     // [NT] x offset of the chunk edge
+    int64_t* doff = soff + NT;                                                           // [NT] y offset of the chunk edge
+    int2* lohi = reinterpret_cast<int2*>(doff + NT);                                     // [NT] valid logical offsets
+    constexpr int PP = 4;                       // pieces per tile row: four samples each (one 16 B copy when VEC)
+    constexpr int PE = kSub / PP;
+    constexpr int NJ = PP;                      // pieces each thread moves per stage
 
     const int tid = threadIdx.x;
     const int64_t q = (int64_t)blockIdx.x * NT + tid;
     const bool valid = q < C * nChunks;
     const int64_t row = valid ? q / nChunks : 0;
     const int k = valid ? (int)(q - row * nChunks) : 0;
-    int64_t a, b;
-    if (!REV) { a = (int64_t)k * L; b = a + L < T ? a + L : T; }
-    else      { b = T - (int64_t)k * L; a = b - L > 0 ? b - L : 0; }
-    const int64_t before = REV ? T - b : a;            // samples between the row edge and the chunk, sweep order
-    const int ulo = valid ? (before < tail ? -(int)before : -tail) : 0;
-    const int uhi = valid ? (int)(b - a) : 0;
-    gbase[tid] = row;
-    cedge[tid] = (int)(REV ? b : a);
-    culo[tid] = ulo;
-    cuhi[tid] = uhi;
+    int64_t edge; int ulo, uhi;
+    {
+        int64_t a, b;
+        if (!REV) { a = (int64_t)k * L; b = a + L < T ? a + L : T; }
+        else      { b = T - (int64_t)k * L; a = b - L > 0 ? b - L : 0; }
+        const int64_t bef = REV ? T - b : a;            // samples between the row edge and the chunk, sweep order
+        edge = REV ? b : a;
+        ulo = valid ? (bef < tail ? -(int)bef : -tail) : 0;
+        uhi = valid ? (int)(b - a) : 0;
+    }
+    soff[tid] = row * ldx + edge;
+    doff[tid] = row * ldy + edge;
+    lohi[tid] = make_int2(ulo, uhi);
     __syncthreads();
+    const int pc = tid % PP;                    // this thread moves piece pc of tile rows tid / PP + j * (NT / PP)
 
     double c[NSEC][5], s[NSEC][2];
 #pragma unroll
@@ -361,35 +367,34 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
         s[j][0] = 0.0; s[j][1] = 0.0;
     }
     // chunks that see the row edge get the exact start-up at the stage where the row starts
-    const bool inject = valid && before <= tail;
-    const int s_inject = inject ? -(int)(before / kSub) : (1 << 30);
+    const int64_t before = REV ? T - edge : edge;
+    const int s_inject = valid && before <= tail ? -(int)(before / kSub) : (1 << 30);
 
     const int nStages = L / kSub;
     const int first = -(tail / kSub);
 
-    // cooperative stage loader: VEC -> 4 pieces of 16 B per row, else 16 pieces of 4 B
+    // logical offset of the first element of piece pc in stage st, and its distance from the chunk edge
     auto issue = [&](int stage) {
         if (stage < nStages) {
-            float* dst = tiles + (size_t)((stage - first) % kRing) * NT * kPitch;
-            if (VEC) {
-                for (int i = tid; i < NT * 4; i += NT) {
-                    const int r = i >> 2, p = i & 3;
-                    int u0; int64_t off;
-                    if (!REV) { u0 = stage * kSub + 4 * p; off = (int64_t)cedge[r] + u0; }
-                    else { u0 = stage * kSub + 12 - 4 * p; off = (int64_t)cedge[r] - u0 - 4; }
-                    const bool ok = u0 >= culo[r] && u0 + 4 <= cuhi[r];
-                    const float* g = x + gbase[r] * ldx + (ok ? off : 0);
-                    cp_async16_zfill(dst + r * kPitch + 4 * p, g, ok);
-                }
-            } else {
-                for (int i = tid; i < NT * kSub; i += NT) {
-                    const int r = i / kSub, p = i - r * kSub;
-                    int u; int64_t off;
-                    if (!REV) { u = stage * kSub + p; off = (int64_t)cedge[r] + u; }
-                    else { u = stage * kSub + 15 - p; off = (int64_t)cedge[r] - u - 1; }
-                    const bool ok = u >= culo[r] && u < cuhi[r];
-                    const float* g = x + gbase[r] * ldx + (ok ? off : 0);
-                    cp_async4_zfill(dst + r * kPitch + p, g, ok);
+            float* tile = tiles + (size_t)((stage - first) % kRing) * NT * kPitch;
+            const int u0 = !REV ? stage * kSub + PE * pc : stage * kSub + (kSub - PE) - PE * pc;
+            const int off = !REV ? u0 : -u0 - PE;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int r = tid / PP + j * (NT / PP);
+                const int2 lh = lohi[r];
+                const float* g = x + soff[r];
+                float* d = tile + r * kPitch + PE * pc;
+                if (VEC) {
+                    const bool ok = u0 >= lh.x && u0 + PE <= lh.y;
+                    cp_async16_zfill(d, ok ? g + off : g, ok);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < PE; ++e) {
+                        const int u = !REV ? u0 + e : u0 + PE - 1 - e;      // element e in ascending address order
+                        const bool ok = u >= lh.x && u < lh.y;
+                        cp_async4_zfill(d + e, ok ? g + off + e : g, ok);
+                    }
                 }
             }
         }
@@ -421,7 +426,8 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
                 for (int i = padlen - 1; i >= 0; --i) (void)sos_step<NSEC>(pb[i], c, s);
             }
         }
-        float* mine = tiles + (size_t)((st - first) % kRing) * NT * kPitch + tid * kPitch;
+        float* tile = tiles + (size_t)((st - first) % kRing) * NT * kPitch;
+        float* mine = tile + tid * kPitch;
         float4 xin[kSub / 4];
 #pragma unroll
         for (int v = 0; v < kSub / 4; ++v) {
@@ -433,49 +439,55 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
             }
         }
         const bool write = st >= 0;
+        const int sbase = st * kSub;
+        if (sbase >= ulo && sbase + kSub <= uhi) {          // whole stage inside the row: the common case
 #pragma unroll
-        for (int v = 0; v < kSub / 4; ++v) {
-            float4 yv;
-            const float4 xv = xin[v];
-            const int base = st * kSub + 4 * v;        // logical offset of the first of four samples
-            if (base >= ulo && base + 4 <= uhi) {
-                yv.x = (float)sos_step<NSEC>((double)xv.x, c, s);
-                yv.y = (float)sos_step<NSEC>((double)xv.y, c, s);
-                yv.z = (float)sos_step<NSEC>((double)xv.z, c, s);
-                yv.w = (float)sos_step<NSEC>((double)xv.w, c, s);
-            } else {   // outside the row / ragged chunk end: zero filled input, state frozen
-                yv = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (base + 0 >= ulo && base + 0 < uhi) yv.x = (float)sos_step<NSEC>((double)xv.x, c, s);
-                if (base + 1 >= ulo && base + 1 < uhi) yv.y = (float)sos_step<NSEC>((double)xv.y, c, s);
-                if (base + 2 >= ulo && base + 2 < uhi) yv.z = (float)sos_step<NSEC>((double)xv.z, c, s);
-                if (base + 3 >= ulo && base + 3 < uhi) yv.w = (float)sos_step<NSEC>((double)xv.w, c, s);
+            for (int v = 0; v < kSub / 4; ++v) {
+                float4 yv;
+                yv.x = (float)sos_step<NSEC>((double)xin[v].x, c, s);
+                yv.y = (float)sos_step<NSEC>((double)xin[v].y, c, s);
+                yv.z = (float)sos_step<NSEC>((double)xin[v].z, c, s);
+                yv.w = (float)sos_step<NSEC>((double)xin[v].w, c, s);
+                if (write) {
+                    if (!REV) *reinterpret_cast<float4*>(mine + 4 * v) = yv;
+                    else *reinterpret_cast<float4*>(mine + (kSub - 4 - 4 * v)) = make_float4(yv.w, yv.z, yv.y, yv.x);
+                }
             }
-            if (write) {
-                if (!REV) *reinterpret_cast<float4*>(mine + 4 * v) = yv;
-                else *reinterpret_cast<float4*>(mine + (kSub - 4 - 4 * v)) = make_float4(yv.w, yv.z, yv.y, yv.x);
+        } else {                                            // outside the row / ragged chunk end: state frozen
+#pragma unroll
+            for (int v = 0; v < kSub / 4; ++v) {
+                const float xv[4] = {xin[v].x, xin[v].y, xin[v].z, xin[v].w};
+                float yv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int u = sbase + 4 * v + e;
+                    if (u >= ulo && u < uhi) yv[e] = (float)sos_step<NSEC>((double)xv[e], c, s);
+                }
+                if (write) {
+                    if (!REV) *reinterpret_cast<float4*>(mine + 4 * v) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+                    else *reinterpret_cast<float4*>(mine + (kSub - 4 - 4 * v)) = make_float4(yv[3], yv[2], yv[1], yv[0]);
+                }
             }
         }
         if (write) {
             __syncthreads();
-            const float* out_tile = tiles + (size_t)((st - first) % kRing) * NT * kPitch;
-            if (VEC) {
-                for (int i = tid; i < NT * 4; i += NT) {
-                    const int r = i >> 2, p = i & 3;
-                    int u0; int64_t off;
-                    if (!REV) { u0 = st * kSub + 4 * p; off = (int64_t)cedge[r] + u0; }
-                    else { u0 = st * kSub + 12 - 4 * p; off = (int64_t)cedge[r] - u0 - 4; }
-                    if (u0 + 4 <= cuhi[r]) {
-                        float4 v4 = *reinterpret_cast<const float4*>(out_tile + r * kPitch + 4 * p);
-                        *reinterpret_cast<float4*>(y + gbase[r] * ldy + off) = v4;
+            const int u0 = !REV ? sbase + PE * pc : sbase + (kSub - PE) - PE * pc;
+            const int off = !REV ? u0 : -u0 - PE;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int r = tid / PP + j * (NT / PP);
+                const int hi = lohi[r].y;
+                float* g = y + doff[r] + off;
+                const float4 v4 = *reinterpret_cast<const float4*>(tile + r * kPitch + PE * pc);
+                if (VEC) {
+                    if (u0 + PE <= hi) *reinterpret_cast<float4*>(g) = v4;
+                } else {
+                    const float ve[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                    for (int e = 0; e < PE; ++e) {
+                        const int u = !REV ? u0 + e : u0 + PE - 1 - e;
+                        if (u < hi) g[e] = ve[e];
                     }
-                }
-            } else {
-                for (int i = tid; i < NT * kSub; i += NT) {
-                    const int r = i / kSub, p = i - r * kSub;
-                    int u; int64_t off;
-                    if (!REV) { u = st * kSub + p; off = (int64_t)cedge[r] + u; }
-                    else { u = st * kSub + 15 - p; off = (int64_t)cedge[r] - u - 1; }
-                    if (u < cuhi[r]) y[gbase[r] * ldy + off] = out_tile[r * kPitch + p];
                 }
             }
         }
@@ -499,7 +511,7 @@ template <int NSEC, bool REV, int NT>
 static int launch_warm(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                        const ecog_sos_plan& p, int nChunks, const SosCoef& coef, double* padbuf, bool vec,
                        cudaStream_t st) {
-    const size_t smem = ((size_t)kRing * NT * kPitch) * sizeof(float) + (size_t)NT * (sizeof(int64_t) + 3 * sizeof(int));
+    const size_t smem = ((size_t)kRing * NT * kPitch) * sizeof(float) + (size_t)NT * (2 * sizeof(int64_t) + sizeof(int2));
     const unsigned grid = (unsigned)ceil_div(C * nChunks, NT);
     if (vec) {
         auto k = sos_warm_kernel<NSEC, REV, true, NT>;

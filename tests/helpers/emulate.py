@@ -188,8 +188,8 @@ def resample_model(x32: np.ndarray, plan, bin_gain=None) -> np.ndarray:
 
 def fft4096_model(z: np.ndarray, tw: np.ndarray) -> np.ndarray:
     """Model of the 16x16x16 register FFT of csrc/hilbert.cu using the table from
-    ecog_hilbert_twiddles ((2,16,256,2) float32)."""
-    tw = tw.reshape(2, 16, 256, 2).astype(np.float64)
+    ecog_hilbert_twiddles (first two (16,256,2) float32 sections)."""
+    tw = tw[: 2 * 16 * 256 * 2].reshape(2, 16, 256, 2).astype(np.float64)
     tw1 = tw[0, :, :, 0] + 1j * tw[0, :, :, 1]
     tw2 = tw[1, :, :, 0] + 1j * tw[1, :, :, 1]
     tid = np.arange(256)
@@ -206,6 +206,28 @@ def fft4096_model(z: np.ndarray, tw: np.ndarray) -> np.ndarray:
     out = np.zeros(4096, dtype=np.complex128)
     k0, k1 = tid >> 4, tid & 15
     out[k0[None, :] + 16 * k1[None, :] + 256 * np.arange(16)[:, None]] = Xr
+    return out
+
+
+def fft4096_sparse_model(y256: np.ndarray, tw: np.ndarray) -> np.ndarray:
+    """Model of the fast-path inverse of csrc/hilbert.cu (hilbert_env8_kernel): forward FFT of a
+    4096-point signal that is non-zero only in its first 256 samples.  Pass 1 is the identity;
+    pass 2 reads SG[16 n1 + n0] x twA[n1, tid], then x twB[k1, n0]; pass 3 as in the dense FFT."""
+    tw = tw.astype(np.float64)
+    sec = 16 * 256 * 2
+    twA = tw[2 * sec:3 * sec].reshape(16, 256, 2)
+    twA = twA[..., 0] + 1j * twA[..., 1]                    # [n1, tid]
+    twB = tw[3 * sec:3 * sec + 512].reshape(16, 16, 2)
+    twB = twB[..., 0] + 1j * twB[..., 1]                    # [k1, n0]
+    tid = np.arange(256)
+    k0, n0 = tid >> 4, tid & 15
+    vin = y256[16 * np.arange(16)[:, None] + n0[None, :]] * twA          # [n1, tid]
+    B = np.fft.fft(vin, axis=0) * twB[:, n0]                             # [k1, tid]
+    buf = np.zeros(4096, dtype=np.complex128)
+    buf[256 * k0[None, :] + 16 * np.arange(16)[:, None] + n0[None, :]] = B
+    Xr = np.fft.fft(buf[16 * tid[None, :] + np.arange(16)[:, None]], axis=0)   # [k2, tid], tid = 16 k0 + k1
+    out = np.zeros(4096, dtype=np.complex128)
+    out[(tid >> 4)[None, :] + 16 * (tid & 15)[None, :] + 256 * np.arange(16)[:, None]] = Xr
     return out
 
 

@@ -111,6 +111,33 @@ def test_chain_full6_long_double_rule(golden):
     assert err_gpu <= max(TOL, err_ref), (err_gpu, err_ref)
 
 
+@pytest.mark.parametrize("chain", ["FULL6", "nocar", "car_first"])
+def test_pipelined_host_path_equals_monolithic(chain, monkeypatch):
+    """Host arrays of >= 64 channels go through the channel-chunked, copy-overlapped path; it must
+    give what the one-piece path gives (same kernels, different chunking) and match the oracle."""
+    from decode_tonal_langauge_b200 import preprocessor as P
+    from decode_tonal_langauge_b200.chains import FULL6_STEPS
+    from oracle import chains as ochains
+    steps = {"FULL6": FULL6_STEPS,
+             "nocar": [FULL6_STEPS[4], FULL6_STEPS[2], FULL6_STEPS[5]],
+             "car_first": [FULL6_STEPS[1], FULL6_STEPS[3], FULL6_STEPS[4]]}[chain]
+    rng = np.random.default_rng(3)
+    C, T, fs = 72, 40000, 2000
+    common = np.cumsum(rng.standard_normal(T)) * 0.2
+    x = (rng.standard_normal((C, T)) * 20 + common + 5 * np.sin(2 * np.pi * 60 * np.arange(T) / fs)).astype(np.float32)
+    used = []
+    real = P._pipelined_host_run
+    monkeypatch.setattr(P, "_pipelined_host_run", lambda *a, **k: used.append(1) or real(*a, **k))
+    y, f = P.preprocess_signal(x, steps, Namespace(signal_freq=fs))
+    assert used, "the pipelined path was not taken"
+    monkeypatch.setenv("ECOG_PIPELINE", "0")
+    y0, f0 = P.preprocess_signal(x, steps, Namespace(signal_freq=fs))
+    assert f == f0 and y.dtype == y0.dtype and y.shape == y0.shape
+    assert max_rel(y, y0) < 2e-6
+    ref, fr = ochains.run_chain(x, fs, steps)
+    assert fr == f and max_rel(y, ref) < 5e-5
+
+
 def test_strict_params_reproduces_reference_collision():
     from decode_tonal_langauge_b200.chains import FULL6_STEPS
     from decode_tonal_langauge_b200.preprocessor import preprocess_signal

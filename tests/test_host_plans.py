@@ -88,6 +88,10 @@ def test_hilbert_models(golden):
     z = rng.standard_normal(4096) + 1j * rng.standard_normal(4096)
     got = EM.fft4096_model(z, tw)
     assert np.max(np.abs(got - np.fft.fft(z))) < 2e-5
+    zs = np.zeros(4096, dtype=np.complex128)
+    zs[:256] = z[:256]
+    got = EM.fft4096_sparse_model(zs[:256], tw)             # fast path: 256 non-zero inputs
+    assert np.max(np.abs(got - np.fft.fft(zs))) < 1e-5
 
     g = golden("steps")
     x, fs = g["x"], float(g["fs"])
