@@ -31,10 +31,34 @@ WORKLOADS = {
     "C2": (256, 7_200_000, 2000, "BASELINE configs[1]: 256-ch ECoG @2 kHz, 60 min session, FULL6 chain"),
     "C1": (128, 1_200_000, 2000, "BASELINE configs[0] shape: 128-ch ECoG @2 kHz, 10 min, FULL6 chain"),
     "tiny": (16, 240_000, 2000, "16-ch @2 kHz, 2 min (debug)"),
+    # one recording channel-sharded over the ranks: CAR = colsum -> NCCL all_reduce -> apply (strong scaling)
+    "C4": (1024, 10_800_000, 3000, "BASELINE configs[3]: 1024-ch uECoG @3 kHz, 60 min, channel-sharded, NCCL CAR allreduce"),
+    "C4small": (64, 1_080_000, 3000, "64-ch @3 kHz, 6 min, channel-sharded (debug)"),
 }
+SHARDED = {"C4", "C4small"}
 # algorithmic bytes per RAW channel-sample, unfused contract of SURVEY.md section 8(d)
 FULL6_BYTES_PER_SAMPLE = 39.2
 HILBERT_BYTES_PER_SAMPLE = 8.0
+# per step, same contract (bytes per RAW channel-sample at 2 kHz -> 400 Hz)
+STEP_BYTES_PER_SAMPLE = {
+    "frequency_filter[butter_bandstop]": 8.0, "car_rereference": 8.0, "frequency_filter[butter_bandpass]": 8.0,
+    "frequency_filter[hilbert]": 8.0, "downsample": 4.8, "channel_zscore": 2.4,
+}
+
+
+def ncu_traffic(kernel: str, channels: int, samples: int):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture
+    (profiles/r01_traffic.json: bytes per channel-sample measured by ncu, scaled to this launch)."""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    e = t.get(kernel)
+    if not e:
+        return None
+    return {"gb_per_launch": e["dram_bytes_per_channel_sample"] * channels * samples / 1e9,
+            "source": e["source"]}
 
 
 def measured_peaks():
@@ -179,10 +203,22 @@ def run_ours(args):
     from decode_tonal_langauge_b200.preprocessor import preprocess_signal
 
     C, T, fs, desc = WORKLOADS[args.workload]
-    x = synth.device_session(C, T, fs, seed=rank)                  # one session per rank, resident in HBM
+    sharded = args.workload in SHARDED
+    if sharded:
+        from decode_tonal_langauge_b200 import distributed as D
+        c_lo, c_hi = D.shard_bounds(C, rank, world)
+        # every rank draws the same common-mode / line terms (same seed) and its own channel noise
+        x = synth.device_session(c_hi - c_lo, T, fs, seed=0, channel_seed=rank)
+        C_local = c_hi - c_lo
+    else:
+        x = synth.device_session(C, T, fs, seed=rank)              # one session per rank, resident in HBM
+        C_local = C
     torch.cuda.synchronize()
 
     def step(profile=None):
+        if sharded:
+            y, f, _ = D.preprocess_signal_sharded(x, FULL6_STEPS, Namespace(signal_freq=fs), c_lo, C)
+            return y
         y, f = preprocess_signal(x, FULL6_STEPS, Namespace(signal_freq=fs), profile=profile)
         return y
 
@@ -225,13 +261,18 @@ def run_ours(args):
     hil_key = "frequency_filter[hilbert]"
     peak, peak_src = measured_peaks()
     hil_ms = step_ms.get(hil_key)
-    hil_gbs = HILBERT_BYTES_PER_SAMPLE * C * T / (hil_ms * 1e-3) / 1e9 if hil_ms else None
-    chain_gbs = FULL6_BYTES_PER_SAMPLE * C * T / (total_ms / args.steps * 1e-3) / 1e9
+    hil_gbs = HILBERT_BYTES_PER_SAMPLE * C_local * T / (hil_ms * 1e-3) / 1e9 if hil_ms else None
+    chain_gbs = FULL6_BYTES_PER_SAMPLE * C_local * T / (total_ms / args.steps * 1e-3) / 1e9
+    step_roofline = {k: {"ms": v, "alg_gb": STEP_BYTES_PER_SAMPLE[k] * C_local * T / 1e9,
+                         "achieved_gbs": STEP_BYTES_PER_SAMPLE[k] * C_local * T / (v * 1e-3) / 1e9,
+                         "frac": STEP_BYTES_PER_SAMPLE[k] * C_local * T / (v * 1e-3) / 1e9 / peak}
+                     for k, v in step_ms.items() if k in STEP_BYTES_PER_SAMPLE}
+    traffic = ncu_traffic("hilbert_env8_kernel", C_local, T)
 
     # ---- end to end through the plug-in call with HOST buffers (pinned), H2D + D2H inside
     del y
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not sharded:
         host_in = torch.empty((C, T), dtype=torch.float32, pin_memory=True)
         host_in.copy_(x)
         torch.cuda.synchronize()
@@ -266,25 +307,32 @@ def run_ours(args):
         cpu = cpu_baseline_single(T, fs)
 
     if rank == 0:
-        value = world * C * T * args.steps / (total_ms * 1e-3)
+        units = C * T if sharded else world * C * T
+        value = units * args.steps / (total_ms * 1e-3)
         line = {
             "metric": "channel_samples_per_sec", "value": value, "unit": "channel-samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "chain": "FULL6", "channels": C, "samples": T, "fs": fs,
-                       "sharding": "one session per rank, no data-path collective",
+                       "sharding": ("channels of one recording split over the ranks; CAR column sums "
+                                    "all-reduced over NCCL (T floats per step)") if sharded else
+                                   "one session per rank, no data-path collective",
                        "l2": "inputs larger than L2 (7.4 GB per session); no flush needed",
                        "output": list(out_shape), "state_dtype": "f64 IIR state / statistics, f32 storage"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "hilbert_env_kernel (dominant: %.0f%% of the step)" %
+            "roofline": {"bound": "hbm", "kernel": "hilbert_env8_kernel (dominant: %.0f%% of the step)" %
                          (100 * hil_ms / (total_ms / args.steps)) if hil_ms else None,
                          "achieved": hil_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": hil_gbs / peak if hil_gbs else None, "traffic": None,
+                         "frac": hil_gbs / peak if hil_gbs else None,
+                         "traffic": traffic["gb_per_launch"] if traffic else None, "traffic_unit": "GB per launch",
+                         "traffic_source": traffic["source"] if traffic else None,
+                         "algorithmic_gb_per_launch": HILBERT_BYTES_PER_SAMPLE * C_local * T / 1e9,
                          "peak_source": peak_src,
-                         "note": "FP32-ALU/shared-memory bound kernel (9 FFTs per 4096 samples), see DESIGN.md",
+                         "note": "instruction-issue bound FP32 kernel (8.5 FFTs of 4096 points per 3222 samples), "
+                                 "not HBM bound; see DESIGN.md section 3",
                          "chain_achieved": chain_gbs, "chain_frac": chain_gbs / peak,
-                         "chain_bytes_per_sample": FULL6_BYTES_PER_SAMPLE},
+                         "chain_bytes_per_sample": FULL6_BYTES_PER_SAMPLE, "steps": step_roofline},
             "cpu_baseline": cpu, "step_ms": step_ms,
         }
         print(json.dumps(line), flush=True)

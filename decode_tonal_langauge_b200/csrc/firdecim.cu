@@ -122,6 +122,75 @@ static int dispatch_taps(int nt4, const float* x, float* y, int64_t C, int64_t T
     return launch_fir<D, 64>(x, y, C, T, ldx, ldy, off, taps, vec, st);
 }
 
+// ------------------------------------------------------------------ K6 causal FIR (long)
+// replaces the `fir` band method (ref: preprocess/signal/frequency_filter.py:260-274): the mean
+// over centre frequencies of lfilter(firwin(order+1, ...), 1, x) is ONE causal FIR with the
+// averaged taps (linearity), zero initial state:
+//   y[t] = sum_{j <= order} h[j] x[t - j],  x[t < 0] = 0.
+// Run as a correlation with the reversed taps g[i] = h[n-1-i] over a staged tile; taps live in
+// shared memory (read as broadcast 128-bit loads), every thread slides a 12-sample register
+// window over its 8 outputs: 32 FMA per two shared loads.
+constexpr int kFirR = 8;
+
+__global__ void __launch_bounds__(kFirThreads)
+fir_causal_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t ldx, int64_t ldy,
+                  const float* __restrict__ g, int n4, bool vec) {
+    // g: 4*n4 reversed taps (zero padded at the end), output t uses x[t - off + i], off = 4*n4 - 4:
+    // the host pads h so that the last real tap sits at index off (a multiple of 4).
+    extern __shared__ __align__(16) float4 fsm[];
+    constexpr int S4 = kFirR / 4;                                  // 2 words between neighbouring threads
+    const int span4 = S4 * kFirThreads + n4 + 1;                   // words staged per CTA
+    float4* xs = fsm;                                              // [span4 + span4 / S4 + 1], pad word every S4
+    float4* gs = fsm + span4 + span4 / S4 + 1;                     // [n4]
+    const int tid = threadIdx.x;
+    const int64_t ch = blockIdx.y;
+    const int64_t m0 = (int64_t)blockIdx.x * (kFirThreads * kFirR);
+    const float* xr = x + ch * ldx;
+    const int64_t tin = m0 - (int64_t)(4 * n4 - 4);                // first staged sample (may be < 0: zeros)
+    for (int n = tid; n < n4; n += kFirThreads) gs[n] = *reinterpret_cast<const float4*>(g + 4 * n);
+    for (int n = tid; n < span4; n += kFirThreads) {
+        const int64_t t = tin + 4 * (int64_t)n;
+        float4 v;
+        if (vec && t >= 0 && t + 4 <= T) {
+            v = *reinterpret_cast<const float4*>(xr + t);
+        } else {
+            float e[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e[k] = (t + k >= 0 && t + k < T) ? xr[t + k] : 0.f;
+            v = make_float4(e[0], e[1], e[2], e[3]);
+        }
+        xs[n + n / S4] = v;
+    }
+    __syncthreads();
+    float acc[kFirR];
+#pragma unroll
+    for (int r = 0; r < kFirR; ++r) acc[r] = 0.f;
+    const float4* win = xs + (S4 + 1) * tid;                       // word w of this thread: win[w + w / S4]
+    float4 a = win[0], b = win[1 + 1 / S4];                        // thread-relative words 0 and 1
+    for (int w = 0; w < n4; ++w) {
+        const float4 c = win[(w + 2) + (w + 2) / S4];              // word w + 2: samples 4w+8 .. 4w+11
+        const float4 gw = gs[w];
+        const float xv[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        const float gv[4] = {gw.x, gw.y, gw.z, gw.w};
+#pragma unroll
+        for (int r = 0; r < kFirR; ++r)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) acc[r] = fmaf(gv[e], xv[r + e], acc[r]);
+        a = b;
+        b = c;
+    }
+    const int64_t m = m0 + (int64_t)kFirR * tid;
+    float* yr = y + ch * ldy + m;
+    if (vec && m + kFirR <= T) {
+        *reinterpret_cast<float4*>(yr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        *reinterpret_cast<float4*>(yr + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < kFirR; ++r)
+            if (m + r < T) yr[r] = acc[r];
+    }
+}
+
 }  // namespace ecog
 
 using namespace ecog;
@@ -145,4 +214,20 @@ extern "C" int ecog_fir_decimate(const float* d_x, float* d_y, int64_t C, int64_
     cudaStream_t st = (cudaStream_t)stream;
     if (D == 2) return dispatch_taps<2>(nt4, d_x, d_y, C, T, ldx, ldy, offset, taps, vec, st);
     return dispatch_taps<4>(nt4, d_x, d_y, C, T, ldx, ldy, offset, taps, vec, st);
+}
+
+extern "C" int ecog_fir_causal(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                               const float* d_taps_rev, int32_t ntaps4, ecog_stream_t stream) {
+    if (C <= 0 || C > 65535 || T <= 0 || ldx < T || ldy < T) return fail(ECOG_E_VALUE, "ecog_fir_causal: bad shape");
+    if (!d_taps_rev || ntaps4 < 1 || ntaps4 > 2048)
+        return fail(ECOG_E_VALUE, "ecog_fir_causal: 1..2048 tap words supported, got %d", ntaps4);
+    if (!aligned16(d_taps_rev)) return fail(ECOG_E_VALUE, "ecog_fir_causal: tap table must be 16-byte aligned");
+    if (d_x == d_y) return fail(ECOG_E_VALUE, "ecog_fir_causal: in-place operation is not supported");
+    const bool vec = aligned16(d_x) && aligned16(d_y) && ldx % 4 == 0 && ldy % 4 == 0;
+    const int span4 = (kFirR / 4) * kFirThreads + ntaps4 + 1;
+    const size_t smem = (size_t)(span4 + span4 / (kFirR / 4) + 1 + ntaps4) * sizeof(float4);
+    ECOG_CUDA(cudaFuncSetAttribute(fir_causal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)ceil_div(T, (int64_t)kFirThreads * kFirR), (unsigned)C);
+    fir_causal_kernel<<<grid, kFirThreads, smem, (cudaStream_t)stream>>>(d_x, d_y, T, ldx, ldy, d_taps_rev, ntaps4, vec);
+    return check_launch("fir_causal");
 }

@@ -238,12 +238,54 @@ def hilbert(x: torch.Tensor, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0,
 
 
 # ------------------------------------------------------------------ K6 / K7
+def fir_bank_taps(fs, order: int, center_frequencies) -> np.ndarray:
+    """Averaged taps of the reference's FIR bank (ref: frequency_filter.py:260-274).  The
+    reference divides the band edges by the Nyquist frequency AND passes ``fs`` to firwin
+    (:265-268); reproduced as is.  float64."""
+    from scipy import signal as sp_signal
+    cfs = list(center_frequencies)
+    if not cfs:
+        raise ZeroDivisionError("division by zero")      # the reference divides by len(center_frequencies)
+    nyq = 0.5 * float(fs)
+    h = np.zeros(int(order) + 1, dtype=np.float64)
+    for fc in cfs:
+        h += sp_signal.firwin(int(order) + 1, [fc * 0.9 / nyq, fc * 1.1 / nyq], pass_zero=False, fs=fs)
+    return h / len(cfs)
+
+
+def fir_causal(x: torch.Tensor, h: np.ndarray, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y[c, t] = sum_j h[j] x[c, t - j] with zero initial state (scipy lfilter(h, 1, x))."""
+    x = as_signal(x)
+    Cn, T = x.shape
+    h = np.asarray(h, dtype=np.float64)
+    n4 = -(-(len(h) - 1) // 4) + 1
+    off = 4 * n4 - 4
+    g = np.zeros(4 * n4, dtype=np.float32)
+    idx = off - np.arange(4 * n4)
+    ok = (idx >= 0) & (idx < len(h))
+    g[ok] = h[idx[ok]].astype(np.float32)
+    gd = _dev_table(("fir_taps", g.tobytes()), lambda: g, x.device)
+    y = out if out is not None else torch.empty((Cn, T), dtype=torch.float32, device=x.device)
+    nat.check(lib.ecog_fir_causal(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), _ptr(gd), n4, _stream()))
+    return y
+
+
 def fir_bank(x: torch.Tensor, fs, order: int, center_frequencies, out: Optional[torch.Tensor] = None):
-    raise NotImplementedError("the 'fir' band method is not implemented yet (SURVEY.md section 8f row f3)")
+    """ref: frequency_filter.py:232-274 (fir_bandpass_filter keyword names kept)."""
+    return fir_causal(x, fir_bank_taps(fs, order, center_frequencies), out=out)
 
 
-def rolling_zscore(x: torch.Tensor, window: int, nan_to_zero: bool = False):
-    raise NotImplementedError("rolling_zscore is not implemented yet (SURVEY.md section 8f row f3)")
+def rolling_zscore(x: torch.Tensor, window: int, nan_to_zero: bool = False) -> torch.Tensor:
+    """ref: rolling_zscore.py:28-49: trailing window of ``window`` samples, min_periods=1, ddof=1."""
+    x = as_signal(x)
+    Cn, T = x.shape
+    mean, _ = row_stats(x)
+    nbytes = lib.ecog_rolling_workspace(Cn, T)
+    ws = workspace(nbytes, x.device, "rolling")
+    y = torch.empty((Cn, T), dtype=torch.float32, device=x.device)
+    nat.check(lib.ecog_rolling_zscore(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), int(window), _ptr(mean),
+                                      1 if nan_to_zero else 0, _ptr(ws), ws.numel(), _stream()))
+    return y
 
 
 # ------------------------------------------------------------------------ K5

@@ -75,7 +75,7 @@ def audio(session_idx: int, duration_s: float, sf: float = 24414.0625) -> np.nda
     return rng.standard_normal((1, int(sf * duration_s))).astype(np.float32)
 
 
-def device_session(C: int, T: int, fs: float, seed: int = 0, device="cuda"):
+def device_session(C: int, T: int, fs: float, seed: int = 0, device="cuda", channel_seed=None):
     """Full-size synthetic input generated ON the device for the bench: white
     noise + shared common-mode + 60/120/180 Hz line noise, float32 (C, T).
     Generated in channel blocks to bound temporaries."""
@@ -88,6 +88,8 @@ def device_session(C: int, T: int, fs: float, seed: int = 0, device="cuda"):
             + torch.sin(2 * np.pi * 180 * t)).to(torch.float32)
     del t
     common = 15.0 * torch.randn(T, generator=g, device=device, dtype=torch.float32)
+    if channel_seed is not None:          # channel shard: shared terms above, private channel noise below
+        g.manual_seed(SEED + 7919 * (int(channel_seed) + 1) + seed)
     blk = 16
     for c0 in range(0, C, blk):
         c1 = min(C, c0 + blk)

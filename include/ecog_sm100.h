@@ -164,6 +164,25 @@ int ecog_fir_decimate(const float* d_x, float* d_y, int64_t C, int64_t T, int64_
                       const float* h_taps, int32_t ntaps, int32_t offset, int32_t D,
                       ecog_stream_t stream);
 
+/* ------------------------------------------------------- K6: causal FIR (long)
+ * replaces preprocess/signal/frequency_filter.py:260-274 (`fir` band method).  The mean over
+ * centre frequencies of lfilter(firwin(order+1, ...), 1, x) is one causal FIR with the
+ * averaged taps h (zero initial state):  y[c,t] = sum_j h[j] x[c,t-j].
+ * d_taps_rev: DEVICE, 4*ntaps4 floats, g[i] = h[off - i] (0 where off - i is outside h) with
+ * off = 4*ntaps4 - 4 >= len(h) - 1, 16-byte aligned.                                    */
+int ecog_fir_causal(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                    const float* d_taps_rev, int32_t ntaps4, ecog_stream_t stream);
+
+/* ------------------------------------------------ K7: trailing-window z-score
+ * replaces preprocess/signal/rolling_zscore.py:28-49 (pandas rolling(window, min_periods=1)
+ * mean and std with ddof=1): z[t] = (x[t] - mean_w) / std_w over x[max(0,t+1-window) .. t];
+ * sample 0 of every row is NaN (0 when nan_to_zero).  d_shift: per-row float64 offset
+ * subtracted before the float64 prefix sums (the row mean from ecog_row_stats).          */
+size_t ecog_rolling_workspace(int64_t C, int64_t T);
+int ecog_rolling_zscore(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                        int64_t window, const double* d_shift, int nan_to_zero,
+                        void* d_workspace, size_t workspace_bytes, ecog_stream_t stream);
+
 /* ------------------------------------------------------- K8: epoch gather
  * replaces data_loading/text_align.py:290-304,331-340,380-394.
  *   out[n, c, 0:L] = src[c, start[n] : start[n]+L]    (bit copy; elem_bytes 4 or 8)

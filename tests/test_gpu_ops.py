@@ -176,6 +176,44 @@ def test_hilbert_low_band_is_declared_unsupported(ops):
         ops.hilbert(dev(np.zeros((1, 8000), np.float32)), 400.0, [0.5, 4.0])
 
 
+# ------------------------------------------------------------------ K6 / K7
+def test_fir_bank_golden(ops, golden):
+    g = golden("steps")
+    y = host(ops.fir_bank(dev(g["x"]), float(g["fs"]), 390, [80.0, 100.0, 120.0]))
+    assert max_rel(y, g["fir"]) < TOL
+
+
+@pytest.mark.parametrize("C,T,ntaps", [(3, 5000, 391), (2, 777, 5), (4, 20001, 1025), (1, 100, 300)])
+def test_fir_causal_vs_lfilter(ops, C, T, ntaps):
+    from scipy import signal as sp_signal
+    rng = np.random.default_rng(ntaps)
+    x = (rng.standard_normal((C, T)) * 10).astype(np.float32)
+    h = rng.standard_normal(ntaps) / ntaps
+    y = host(ops.fir_causal(dev(x), h))
+    assert max_rel(y, sp_signal.lfilter(h, 1.0, x.astype(np.float64), axis=-1)) < 2e-6
+
+
+def test_rolling_zscore_golden(ops, golden):
+    g = golden("steps")
+    fs = float(g["fs"])
+    y = host(ops.rolling_zscore(dev(g["x"]), int(1.5 * fs)))
+    ref = g["rolling_zscore"]
+    assert np.isnan(y[:, 0]).all() and np.isnan(ref[:, 0]).all()
+    assert max_rel(y[:, 1:], ref[:, 1:]) < TOL
+    z = host(ops.rolling_zscore(dev(g["x"]), int(1.5 * fs), nan_to_zero=True))
+    assert (z[:, 0] == 0).all() and np.array_equal(z[:, 1:], y[:, 1:])
+
+
+@pytest.mark.parametrize("C,T,W", [(3, 4097, 2), (2, 70000, 4000), (5, 9001, 20000), (2, 33, 16), (1, 50000, 4099)])
+def test_rolling_zscore_vs_oracle(ops, C, T, W):
+    from oracle import steps as S
+    rng = np.random.default_rng(W)
+    x = (np.cumsum(rng.standard_normal((C, T)), axis=1) + 30 * rng.standard_normal((C, T)) + 100).astype(np.float32)
+    y = host(ops.rolling_zscore(dev(x), W))
+    ref = S.rolling_zscore(x, 1.0, W)              # fs = 1: window_length is in samples
+    assert max_rel(y[:, 1:], ref[:, 1:]) < TOL
+
+
 # ------------------------------------------------------------------------ K5
 def test_resample_golden(ops, golden):
     g = golden("steps")

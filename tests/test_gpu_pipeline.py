@@ -50,6 +50,17 @@ def test_step_modules_numpy_contract(golden):
     assert max_rel(y, g["zscore_rereference"]) < 2e-6
     # float64 input is accepted like the reference and keeps its dtype where the reference does
     assert S.car_rereference(x.astype(np.float64), Namespace(signal_freq=fs)).dtype == np.float64
+    # the two secondary operators
+    y = S.frequency_filter(x, Namespace(signal_freq=fs, bands=[
+        {"method": "fir", "params": {"order": 390, "center_frequencies": [80.0, 100.0, 120.0]}}]))
+    assert y.dtype == np.float32 and max_rel(y, g["fir"]) < TOL          # an all-fir list keeps the input dtype
+    y = S.rolling_zscore(x, Namespace(signal_freq=fs, window_length=1.5))
+    assert y.dtype == np.float64 and np.isnan(y[:, 0]).all()
+    assert max_rel(y[:, 1:], g["rolling_zscore"][:, 1:]) < TOL
+    y = S.rolling_zscore(x, Namespace(signal_freq=fs, window_length=1.5, preserve_nans=False))
+    assert (y[:, 0] == 0).all()
+    with pytest.raises(ValueError):
+        S.rolling_zscore(x, Namespace(signal_freq=10, window_length=0.1))
 
 
 def test_step_errors_match_reference_types(golden):
