@@ -340,13 +340,90 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_c3(args):
+    """BASELINE configs[2]: ERP epoch extraction + discriminative / active channel selection,
+    256 ch x 20k events x 400 samples, source = one 60-min 400 Hz session resident in HBM.
+    One step = gather(ERP) + gather(rest) + ANOVA(tone, 4 groups) + ANOVA(syllable, 2) +
+    ANOVA(rest vs ERP) + the three run-length selections.  Not the driver's default line."""
+    import torch
+    from decode_tonal_langauge_b200 import _native as nat
+    from decode_tonal_langauge_b200 import ops, selection
+    torch.cuda.set_device(0)
+    C, T, sf, N, L = 256, 1_440_000, 400, 20_000, 400
+    g = torch.Generator(device="cuda"); g.manual_seed(7)
+    src = torch.randn((C, T), generator=g, device="cuda", dtype=torch.float32)
+    rng = np.random.default_rng(7)
+    onsets = np.sort(rng.choice(np.arange(300, 10 * (T // sf - 5)), N, replace=False)) / 10.0
+    starts = np.array([int(s * sf) for s in onsets], dtype=np.int64)
+    rest_starts = np.arange(0, int(25.0 * sf) - L + 1, L, dtype=np.int64)
+    tone = rng.integers(0, 4, N).astype(np.int64)
+    syl = rng.integers(0, 2, N).astype(np.int8)
+    params = {"p_threshold": 0.01, "active_time_threshold": 0.1}
+    peak, peak_src = measured_peaks()
+
+    def step(prof=None):
+        def timed(name, fn):
+            if prof is None:
+                return fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); r = fn(); e1.record()
+            prof.append((name, e0, e1))
+            return r
+        ep = timed("epoch_gather", lambda: ops.epoch_gather(src, starts, L))
+        rest = timed("epoch_gather_rest", lambda: ops.epoch_gather(src, rest_starts, L))
+        data = {"ecog": ep, "ecog_rest": rest, "ecog_sf": np.int64(sf), "tone": tone, "syllable": syl}
+        out = [timed("discriminative[tone]", lambda: selection.discriminative_run(data, dict(params, target="tone"))),
+               timed("discriminative[syllable]", lambda: selection.discriminative_run(data, dict(params, target="syllable"))),
+               timed("active", lambda: selection.active_run(data, params))]
+        return out
+
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        l0 = nat.launch_count()
+        profs = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            pr = []
+            step(pr)
+            profs.append(pr)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    step_ms = {}
+    for pr in profs:
+        for name, a, b in pr:
+            step_ms.setdefault(name, []).append(a.elapsed_time(b))
+    step_ms = {k: float(np.mean(v)) for k, v in step_ms.items()}
+    elems = N * C * L
+    alg = {"epoch_gather": 8.0 * elems, "discriminative[tone]": 4.0 * elems + 16.0 * C * L,
+           "discriminative[syllable]": 4.0 * elems + 16.0 * C * L, "active": 4.0 * (elems + len(rest_starts) * C * L) + 16.0 * C * L}
+    roof = {k: {"ms": step_ms[k], "alg_gb": v / 1e9, "achieved_gbs": v / (step_ms[k] * 1e-3) / 1e9,
+                "frac": v / (step_ms[k] * 1e-3) / 1e9 / peak} for k, v in alg.items()}
+    line = {"metric": "epoch_elements_per_sec", "value": elems / (ms * 1e-3), "unit": "epoch channel-samples/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 gather (bit copy) / f64 statistics", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[2]: ERP epoch extraction + discriminative channel selection, "
+                                   "256 ch x 20k events", "events": N, "channels": C, "epoch_samples": L,
+                       "l2": "epoch tensor 8.2 GB >> L2"},
+            "gpu_launches": int(nat.launch_count() - l0),
+            "roofline": {"bound": "hbm", "kernel": "anova_f_kernel (discriminative[tone])", "peak": peak, "unit": "GB/s",
+                         "achieved": roof["discriminative[tone]"]["achieved_gbs"], "frac": roof["discriminative[tone]"]["frac"],
+                         "traffic": None, "peak_source": peak_src, "steps": roof},
+            "step_ms": step_ms}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS) + ["C3"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -354,6 +431,8 @@ def main():
         print("note: fewer than 3 warm-up steps; numbers are not reportable", file=sys.stderr)
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "C3":
+        run_c3(args)
     else:
         run_ours(args)
 

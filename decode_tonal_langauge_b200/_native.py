@@ -16,7 +16,7 @@ ECOG_E_VALUE = -1
 ECOG_E_CUDA = -2
 ECOG_E_WORKSPACE = -3
 ECOG_E_UNSUPPORTED = -4
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_SECTIONS = 8
 SOS_SCAN = 0
 SOS_WARMUP = 1
@@ -76,7 +76,8 @@ PROTOTYPES = {
     "ecog_rolling_workspace": (_SZ, [_I64, _I64]),
     "ecog_rolling_zscore": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _I64, _P, C.c_int, _P, _SZ, _P]),
     "ecog_epoch_gather": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _I64, _I64, _I32, _P]),
-    "ecog_anova_f": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P, _P, _I32, _P, _P, _P]),
+    "ecog_anova_workspace": (_SZ, [_I64, _I64, _I64, _I32]),
+    "ecog_anova_f": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P, _P, _I32, _P, _P, _P, _SZ, _P]),
     "ecog_sig_runlength": (C.c_int, [_P, _I64, _I64, _F64, _P, _P]),
 }
 

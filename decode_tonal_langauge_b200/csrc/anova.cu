@@ -1,9 +1,11 @@
 // K9 per-(channel, timepoint) one-way ANOVA and K10 longest significant run.
 //
-// anova_f: one thread per (c, t); the event loop streams the (N, C, L) epoch tensor
-// with stride C*L (coalesced along t), float64 accumulators about the first event's
+// anova_f: one thread per (c, t) and event slab; the event loop streams the (N, C, L) epoch
+// tensor with stride C*L (coalesced along t), float64 accumulators about the first event's
 // value (the F statistic is shift invariant; scipy centres on the grand mean for the
-// same reason).  4 B read per epoch element -> HBM-bound.  p = fdtrc(G-1, N-G, F) is
+// same reason).  Events are cut into slabs (grid.y) so that enough loads are in flight to
+// reach HBM bandwidth when C*L alone is ~1e5 threads; the slab partials are combined in slab
+// order by a second kernel (deterministic).  4 B read per epoch element -> HBM-bound.  p = fdtrc(G-1, N-G, F) is
 // evaluated on the device with the continued fraction of the regularised incomplete
 // beta function (modified Lentz), so no host pass over the (C, L) result is needed.
 // sig_runlength: one warp per channel, ballot of p < threshold, longest run of ones.
@@ -59,45 +61,89 @@ __device__ double f_survival(double dfn, double dfd, double f) {
 
 struct GroupCounts { double n[16]; };
 
+// Partial accumulators of one event slab for one (channel, timepoint):
+//   sums[GMAX] (float64, about the shift), q = sum d^2 (float64), mn/mx[GMAX] (float32).
+// Stored as planes over idx so that the finalise pass reads coalesced.
+struct GroupStarts { int64_t at[17]; };     // events of group k are order[at[k] .. at[k+1])
+
+// Events arrive SORTED BY GROUP (d_order: stable argsort of the labels, built by the host), so a
+// thread accumulates one group at a time into scalars: load, convert, subtract, add, fma,
+// min, max -- no per-group selects.  A slab is a contiguous range of the sorted order.
 template <int GMAX>
 __global__ void __launch_bounds__(kAnovaThreads)
-anova_f_kernel(const float* __restrict__ ea, int64_t Na, const float* __restrict__ eb, int64_t Nb,
-               int64_t CL, const int32_t* __restrict__ group, GroupCounts cnt, int G,
-               double* __restrict__ Fout, double* __restrict__ Pout) {
-    __shared__ unsigned char lab[kLabelChunk];
+anova_partial_kernel(const float* __restrict__ ea, int64_t Na, const float* __restrict__ eb, int64_t Nb,
+                     int64_t CL, const int32_t* __restrict__ order, GroupStarts gs, int64_t slab,
+                     double* __restrict__ psum, float* __restrict__ pmin, float* __restrict__ pmax) {
+    __shared__ int32_t ord[kLabelChunk];
     const int64_t idx = (int64_t)blockIdx.x * kAnovaThreads + threadIdx.x;
     const bool live = idx < CL;
     const int64_t N = Na + Nb;
+    const int64_t nBeg = (int64_t)blockIdx.y * slab;
+    const int64_t nEnd = nBeg + slab < N ? nBeg + slab : N;
+    double s[GMAX];
+    float mn[GMAX], mx[GMAX];
+    double q = 0.0;
+    const double shift = live ? (double)(Na > 0 ? ea[idx] : eb[idx]) : 0.0;
+    const float* pa = ea + (live ? idx : 0);
+    const float* pb = eb ? eb + (live ? idx : 0) - Na * CL : pa;      // event n >= Na lives at eb[(n - Na) * CL]
+#pragma unroll
+    for (int k = 0; k < GMAX; ++k) {
+        double sk = 0.0;
+        float lo = INFINITY, hi = -INFINITY;
+        const int64_t g0 = gs.at[k] > nBeg ? gs.at[k] : nBeg;
+        const int64_t g1 = gs.at[k + 1] < nEnd ? gs.at[k + 1] : nEnd;
+        for (int64_t n0 = g0; n0 < g1; n0 += kLabelChunk) {
+            const int chunk = (int)(g1 - n0 < kLabelChunk ? g1 - n0 : kLabelChunk);
+            __syncthreads();
+            for (int i = threadIdx.x; i < chunk; i += kAnovaThreads) ord[i] = order[n0 + i];
+            __syncthreads();
+            if (!live) continue;
+#pragma unroll 8
+            for (int i = 0; i < chunk; ++i) {
+                const int64_t n = ord[i];
+                const float v = __ldg((n < Na ? pa : pb) + n * CL);
+                const double d = (double)v - shift;
+                sk += d;
+                q = fma(d, d, q);
+                lo = fminf(lo, v);
+                hi = fmaxf(hi, v);
+            }
+        }
+        s[k] = sk; mn[k] = lo; mx[k] = hi;
+    }
+    if (!live) return;
+    const int64_t base = (int64_t)blockIdx.y * (GMAX + 1) * CL;
+#pragma unroll
+    for (int k = 0; k < GMAX; ++k) psum[base + k * CL + idx] = s[k];
+    psum[base + GMAX * CL + idx] = q;
+    const int64_t fb = (int64_t)blockIdx.y * GMAX * CL;
+#pragma unroll
+    for (int k = 0; k < GMAX; ++k) { pmin[fb + k * CL + idx] = mn[k]; pmax[fb + k * CL + idx] = mx[k]; }
+}
+
+// combine the slabs in slab order (deterministic) and finish F, p
+template <int GMAX>
+__global__ void __launch_bounds__(kAnovaThreads)
+anova_final_kernel(int64_t CL, int64_t N, int nslab, GroupCounts cnt, int G,
+                   const double* __restrict__ psum, const float* __restrict__ pmin, const float* __restrict__ pmax,
+                   double* __restrict__ Fout, double* __restrict__ Pout) {
+    const int64_t idx = (int64_t)blockIdx.x * kAnovaThreads + threadIdx.x;
+    if (idx >= CL) return;
     double s[GMAX];
     float mn[GMAX], mx[GMAX];
 #pragma unroll
     for (int k = 0; k < GMAX; ++k) { s[k] = 0.0; mn[k] = INFINITY; mx[k] = -INFINITY; }
     double q = 0.0;
-    const double shift = live ? (double)(Na > 0 ? ea[idx] : eb[idx]) : 0.0;
-
-    for (int64_t n0 = 0; n0 < N; n0 += kLabelChunk) {
-        const int chunk = (int)(N - n0 < kLabelChunk ? N - n0 : kLabelChunk);
-        __syncthreads();
-        for (int i = threadIdx.x; i < chunk; i += kAnovaThreads) lab[i] = (unsigned char)group[n0 + i];
-        __syncthreads();
-        if (!live) continue;
-#pragma unroll 4
-        for (int i = 0; i < chunk; ++i) {
-            const int64_t n = n0 + i;
-            const float v = n < Na ? __ldg(ea + n * CL + idx) : __ldg(eb + (n - Na) * CL + idx);
-            const int g = lab[i];
-            const double d = (double)v - shift;
-            q = fma(d, d, q);
+    for (int b = 0; b < nslab; ++b) {
+        const int64_t base = (int64_t)b * (GMAX + 1) * CL, fb = (int64_t)b * GMAX * CL;
 #pragma unroll
-            for (int k = 0; k < GMAX; ++k) {
-                const bool hit = (g == k);
-                s[k] += hit ? d : 0.0;
-                mn[k] = hit ? fminf(mn[k], v) : mn[k];
-                mx[k] = hit ? fmaxf(mx[k], v) : mx[k];
-            }
+        for (int k = 0; k < GMAX; ++k) {
+            s[k] += psum[base + k * CL + idx];
+            mn[k] = fminf(mn[k], pmin[fb + k * CL + idx]);
+            mx[k] = fmaxf(mx[k], pmax[fb + k * CL + idx]);
         }
+        q += psum[base + GMAX * CL + idx];
     }
-    if (!live) return;
     double S = 0.0, ssb = 0.0;
     bool all_const = true;
     float gmn = INFINITY, gmx = -INFINITY;
@@ -120,6 +166,15 @@ anova_f_kernel(const float* __restrict__ ea, int64_t Na, const float* __restrict
     if (gmn == gmx) F = nan("");
     Fout[idx] = F;
     Pout[idx] = f_survival(dfb, dfw, F);
+}
+
+static int gmax_of(int G) { return G <= 2 ? 2 : (G <= 4 ? 4 : (G <= 8 ? 8 : 16)); }
+static int anova_slabs(int64_t CL, int64_t N) {
+    // enough (c,t)-threads x slabs to fill the machine with loads in flight; slabs of >= 256 events
+    int64_t want = ceil_div((int64_t)kNumSMs * 2048 * 2, CL);
+    int64_t cap = N / 256 > 1 ? N / 256 : 1;
+    int64_t sl = want < cap ? want : cap;
+    return (int)(sl < 1 ? 1 : (sl > 64 ? 64 : sl));
 }
 
 __global__ void __launch_bounds__(128)
@@ -147,31 +202,58 @@ sig_runlength_kernel(const double* __restrict__ p, int C, int64_t L, double thr,
 
 using namespace ecog;
 
+extern "C" size_t ecog_anova_workspace(int64_t C, int64_t L, int64_t N, int32_t G) {
+    const int64_t CL = C * L;
+    const int gm = gmax_of(G), ns = anova_slabs(CL, N);
+    return (size_t)ns * CL * ((gm + 1) * sizeof(double) + 2 * gm * sizeof(float)) + 256;
+}
+
 extern "C" int ecog_anova_f(const float* d_epochs_a, int64_t Na, const float* d_epochs_b, int64_t Nb,
-                            int64_t C, int64_t L, const int32_t* d_group, const int64_t* h_group_count,
-                            int32_t G, double* d_F, double* d_p, ecog_stream_t stream) {
+                            int64_t C, int64_t L, const int32_t* d_order, const int64_t* h_group_count,
+                            int32_t G, double* d_F, double* d_p, void* d_workspace, size_t workspace_bytes,
+                            ecog_stream_t stream) {
     if (C <= 0 || L <= 0 || Na < 0 || Nb < 0 || Na + Nb < 2) return fail(ECOG_E_VALUE, "ecog_anova_f: bad shape");
     if (G < 2) return fail(ECOG_E_VALUE, "ecog_anova_f: need at least two groups, got %d", G);
     if (G > 16) return fail(ECOG_E_UNSUPPORTED, "ecog_anova_f: at most 16 groups supported, got %d", G);
     if (Na + Nb <= G) return fail(ECOG_E_VALUE, "ecog_anova_f: need more events than groups");
     GroupCounts cnt;
+    GroupStarts gs;
     int64_t tot = 0;
     for (int k = 0; k < 16; ++k) {
         cnt.n[k] = k < G ? (double)h_group_count[k] : 1.0;
+        gs.at[k] = tot;
         if (k < G) {
             if (h_group_count[k] <= 0) return fail(ECOG_E_VALUE, "ecog_anova_f: empty group %d", k);
             tot += h_group_count[k];
         }
     }
-    if (tot != Na + Nb) return fail(ECOG_E_VALUE, "ecog_anova_f: group counts do not sum to the event count");
+    gs.at[16] = tot;
+    const int64_t N = Na + Nb;
+    if (tot != N) return fail(ECOG_E_VALUE, "ecog_anova_f: group counts do not sum to the event count");
+    if (workspace_bytes < ecog_anova_workspace(C, L, N, G))
+        return fail(ECOG_E_WORKSPACE, "ecog_anova_f: workspace %zu < %zu", workspace_bytes, ecog_anova_workspace(C, L, N, G));
     const int64_t CL = C * L;
-    unsigned grid = (unsigned)ceil_div(CL, kAnovaThreads);
+    const int gm = gmax_of(G), ns = anova_slabs(CL, N);
+    const int64_t slab = ceil_div(N, ns);
+    double* psum = (double*)d_workspace;
+    float* pmin = (float*)(psum + (size_t)ns * (gm + 1) * CL);
+    float* pmax = pmin + (size_t)ns * gm * CL;
+    dim3 grid((unsigned)ceil_div(CL, kAnovaThreads), (unsigned)ns);
+    const unsigned fgrid = (unsigned)ceil_div(CL, kAnovaThreads);
     cudaStream_t st = (cudaStream_t)stream;
-    if (G <= 2) anova_f_kernel<2><<<grid, kAnovaThreads, 0, st>>>(d_epochs_a, Na, d_epochs_b, Nb, CL, d_group, cnt, G, d_F, d_p);
-    else if (G <= 4) anova_f_kernel<4><<<grid, kAnovaThreads, 0, st>>>(d_epochs_a, Na, d_epochs_b, Nb, CL, d_group, cnt, G, d_F, d_p);
-    else if (G <= 8) anova_f_kernel<8><<<grid, kAnovaThreads, 0, st>>>(d_epochs_a, Na, d_epochs_b, Nb, CL, d_group, cnt, G, d_F, d_p);
-    else anova_f_kernel<16><<<grid, kAnovaThreads, 0, st>>>(d_epochs_a, Na, d_epochs_b, Nb, CL, d_group, cnt, G, d_F, d_p);
-    return check_launch("anova_f");
+#define ECOG_ANOVA(GM)                                                                                              \
+    do {                                                                                                            \
+        anova_partial_kernel<GM><<<grid, kAnovaThreads, 0, st>>>(d_epochs_a, Na, d_epochs_b, Nb, CL, d_order, gs, slab, \
+                                                                 psum, pmin, pmax);                                 \
+        ECOG_TRY(check_launch("anova_partial"));                                                                    \
+        anova_final_kernel<GM><<<fgrid, kAnovaThreads, 0, st>>>(CL, N, ns, cnt, G, psum, pmin, pmax, d_F, d_p);     \
+    } while (0)
+    if (gm == 2) ECOG_ANOVA(2);
+    else if (gm == 4) ECOG_ANOVA(4);
+    else if (gm == 8) ECOG_ANOVA(8);
+    else ECOG_ANOVA(16);
+#undef ECOG_ANOVA
+    return check_launch("anova_final");
 }
 
 extern "C" int ecog_sig_runlength(const double* d_p, int64_t C, int64_t L, double threshold,

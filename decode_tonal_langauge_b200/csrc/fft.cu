@@ -129,7 +129,7 @@ __device__ __forceinline__ void super_bfly(float2* col, int g, int j, int lp, co
 }
 
 template <int W>
-__global__ void __launch_bounds__(kFftThreads)
+__global__ void __launch_bounds__(kFftThreads, 3)
 fft_tile_kernel(const PassParams P) {
     constexpr int WP = W + 1;                           // padded pitch (float2)
     constexpr int LOGW = W == 8 ? 3 : 2;
@@ -142,6 +142,7 @@ fft_tile_kernel(const PassParams P) {
     const int cw = m - c0 < W ? m - c0 : W;             // valid columns in this tile
 
     // ---- load: row i (cw contiguous complex) -> tile[perm[i]]
+#pragma unroll 8
     for (int idx = tid; idx < n * W; idx += kFftThreads) {
         const int i = idx >> LOGW, c = idx & (W - 1);
         float2 v = make_float2(0.f, 0.f);
@@ -202,6 +203,7 @@ fft_tile_kernel(const PassParams P) {
             }
         }
     } else {
+#pragma unroll 4
         for (int idx = tid; idx < n * W; idx += kFftThreads) {
             const int q = idx >> LOGW, c = idx & (W - 1);
             if (c < cw && (q <= P.keep_lo || q >= P.keep_hi)) {

@@ -407,11 +407,13 @@ def anova_f(epochs: torch.Tensor, groups: np.ndarray, extra: Optional[torch.Tens
         raise ValueError("one group label per event is required")
     G = int(groups.max()) + 1 if groups.size else 0
     counts = np.bincount(groups, minlength=max(G, 1)).astype(np.int64)
-    d_groups = torch.from_numpy(groups).to(epochs.device)
+    order = np.argsort(groups, kind="stable").astype(np.int32)       # events sorted by group
+    d_groups = torch.from_numpy(order).to(epochs.device)
     F = torch.empty((Cn, L), dtype=torch.float64, device=epochs.device)
     P = torch.empty((Cn, L), dtype=torch.float64, device=epochs.device)
+    ws = workspace(lib.ecog_anova_workspace(Cn, L, Na + Nb, max(G, 2)), epochs.device, "anova")
     nat.check(lib.ecog_anova_f(_ptr(epochs), Na, _ptr(extra), Nb, Cn, L, _ptr(d_groups), _hptr(counts), G,
-                               _ptr(F), _ptr(P), _stream()))
+                               _ptr(F), _ptr(P), _ptr(ws), ws.numel(), _stream()))
     return F, P
 
 

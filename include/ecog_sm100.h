@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ECOG_ABI_VERSION 2
+#define ECOG_ABI_VERSION 3
 
 #define ECOG_OK 0
 #define ECOG_E_VALUE (-1)     /* bad argument (reference raises ValueError)          */
@@ -195,11 +195,15 @@ int ecog_epoch_gather(const void* d_src, void* d_out, int64_t C, int64_t T, int6
 /* --------------------------------------------- K9/K10: ANOVA F + run length
  * replaces channel_selection/discriminative.py:172-180, channel_selection/active.py:58-76,
  *          channel_selection/utils.py:4-30,63-75 (scipy.stats.f_oneway, equal_var).
- * Epochs may come from up to two tensors (ERP then rest, for active.run); d_group
- * maps every event to 0..G-1.  Outputs F and p = fdtrc(G-1, N-G, F) as (C, L) float64. */
+ * Epochs may come from up to two tensors (ERP then rest, for active.run, numbered 0..Na-1
+ * then Na..Na+Nb-1); d_order lists the event numbers SORTED BY GROUP (stable argsort of the
+ * group index 0..G-1) and h_group_count[k] says how many belong to group k.
+ * Outputs F and p = fdtrc(G-1, N-G, F) as (C, L) float64.                                */
+size_t ecog_anova_workspace(int64_t C, int64_t L, int64_t N, int32_t G);
 int ecog_anova_f(const float* d_epochs_a, int64_t Na, const float* d_epochs_b, int64_t Nb,
-                 int64_t C, int64_t L, const int32_t* d_group, const int64_t* h_group_count,
-                 int32_t G, double* d_F, double* d_p, ecog_stream_t stream);
+                 int64_t C, int64_t L, const int32_t* d_order, const int64_t* h_group_count,
+                 int32_t G, double* d_F, double* d_p, void* d_workspace, size_t workspace_bytes,
+                 ecog_stream_t stream);
 /* longest run of consecutive p < threshold per channel (NaN compares false) */
 int ecog_sig_runlength(const double* d_p, int64_t C, int64_t L, double threshold,
                        int32_t* d_maxrun, ecog_stream_t stream);

@@ -1,18 +1,6 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -x -q -m gpu > gpurun_out/t7_tests.log 2>&1; tail -6 gpurun_out/t7_tests.log
-python - <<'PY' > gpurun_out/t7_prof.log 2>&1
-import torch, sys
-sys.path.insert(0, '.')
-from decode_tonal_langauge_b200 import ops
-x = torch.randn((128, 1_200_000), device='cuda')*30
-def t(f, n=3):
-    f(); torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(n): y = f()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1)/n
-print("fir_bank 391 taps  128x1.2M: %.3f ms" % t(lambda: ops.fir_bank(x, 2000.0, 390, [80.,100.,120.])))
-print("rolling  W=20000   128x1.2M: %.3f ms" % t(lambda: ops.rolling_zscore(x, 20000)))
-PY
-cat gpurun_out/t7_prof.log
+python -m pytest tests -x -q -m gpu -k "anova or selection or runlength or yaml" > gpurun_out/t9.log 2>&1; tail -3 gpurun_out/t9.log
+python bench.py --workload C3 --steps 5 --warmup 3 > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_c3.json')); print(d['ms_per_step'], d['step_ms'])"; tail -5 gpurun_out/bench_c3.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_c3.csv python bench.py --workload C3 --steps 1 --warmup 3 > gpurun_out/ncu_c3.log 2>&1
+grep anova gpurun_out/launches_c3.csv | tail -6 | awk -F'","' '{print $5, $9, $NF}' | cut -c1-150
