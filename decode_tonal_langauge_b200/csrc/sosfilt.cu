@@ -25,6 +25,7 @@ constexpr int kSosThreads = 512;
 constexpr int kSub = 16;              // samples per stage per chunk
 constexpr int kPitch = kSub + 4;      // shared row pitch in floats (conflict-free LDS.128)
 constexpr int kRing = 2;
+constexpr int kWarmRing = 3;      // warm-up kernel: three tile slots, one barrier per stage
 
 struct SosCoef {
     double c[ECOG_MAX_SECTIONS][5];   // b0 b1 b2 a1 a2
@@ -325,13 +326,13 @@ sos_scan_kernel(const float* __restrict__ x, int64_t C, int64_t T, int64_t ldx,
 // The backward sweep cannot run in place (its warm-up reads the forward result of the
 // neighbouring chunk), so the forward result lives in the workspace.
 template <int NSEC, bool REV, bool VEC, int NT>
-__global__ void __launch_bounds__(NT, 1024 / NT)
+__global__ void __launch_bounds__(NT, 512 / NT)
 sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, int64_t T,
                 int64_t ldx, int64_t ldy, int L, int tail, int nChunks, int padlen, int zero_phase,
                 SosCoef coef, double* __restrict__ padbuf) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* tiles = reinterpret_cast<float*>(smem_raw);                                   // [kRing][NT][kPitch]
-    int64_t* soff = reinterpret_cast<int64_t*>(tiles + (size_t)kRing * NT * kPitch);     // [NT] x offset of the chunk edge
+    float* tiles = reinterpret_cast<float*>(smem_raw);                                   // [kWarmRing][NT][kPitch]
+    int64_t* soff = reinterpret_cast<int64_t*>(tiles + (size_t)kWarmRing * NT * kPitch); // [NT] x offset of the chunk edge
     int64_t* doff = soff + NT;                                                           // [NT] y offset of the chunk edge
     int2* lohi = reinterpret_cast<int2*>(doff + NT);                                     // [NT] valid logical offsets
     constexpr int PP = 4;                       // pieces per tile row: four samples each (one 16 B copy when VEC)
@@ -376,7 +377,7 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
     // logical offset of the first element of piece pc in stage st, and its distance from the chunk edge
     auto issue = [&](int stage) {
         if (stage < nStages) {
-            float* tile = tiles + (size_t)((stage - first) % kRing) * NT * kPitch;
+            float* tile = tiles + (size_t)((stage - first) % kWarmRing) * NT * kPitch;
             const int u0 = !REV ? stage * kSub + PE * pc : stage * kSub + (kSub - PE) - PE * pc;
             const int off = !REV ? u0 : -u0 - PE;
 #pragma unroll
@@ -401,11 +402,14 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
         cp_async_commit();
     };
 
+    // three tile slots, ONE barrier per stage: the barrier that publishes the results of stage st
+    // also publishes the tiles of stage st + 1 (every thread has waited for its own copies); the
+    // slot refilled after it (stage st + 2) was last read by the store of stage st - 1.
     issue(first);
+    issue(first + 1);
+    cp_async_wait<1>();
+    __syncthreads();
     for (int st = first; st < nStages; ++st) {
-        cp_async_wait<0>();
-        __syncthreads();
-        issue(st + 1);
         if (st == s_inject && zero_phase) {
             // filtfilt start-up: zi * ext[0], then the odd-extension pad (zero state for the causal filter)
             if (!REV) {
@@ -426,7 +430,7 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
                 for (int i = padlen - 1; i >= 0; --i) (void)sos_step<NSEC>(pb[i], c, s);
             }
         }
-        float* tile = tiles + (size_t)((st - first) % kRing) * NT * kPitch;
+        float* tile = tiles + (size_t)((st - first) % kWarmRing) * NT * kPitch;
         float* mine = tile + tid * kPitch;
         float4 xin[kSub / 4];
 #pragma unroll
@@ -469,8 +473,10 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
                 }
             }
         }
+        cp_async_wait<0>();                    // this thread's copies of stage st + 1 have landed
+        __syncthreads();
+        issue(st + 2);
         if (write) {
-            __syncthreads();
             const int u0 = !REV ? sbase + PE * pc : sbase + (kSub - PE) - PE * pc;
             const int off = !REV ? u0 : -u0 - PE;
 #pragma unroll
@@ -511,7 +517,7 @@ template <int NSEC, bool REV, int NT>
 static int launch_warm(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                        const ecog_sos_plan& p, int nChunks, const SosCoef& coef, double* padbuf, bool vec,
                        cudaStream_t st) {
-    const size_t smem = ((size_t)kRing * NT * kPitch) * sizeof(float) + (size_t)NT * (2 * sizeof(int64_t) + sizeof(int2));
+    const size_t smem = ((size_t)kWarmRing * NT * kPitch) * sizeof(float) + (size_t)NT * (2 * sizeof(int64_t) + sizeof(int2));
     const unsigned grid = (unsigned)ceil_div(C * nChunks, NT);
     if (vec) {
         auto k = sos_warm_kernel<NSEC, REV, true, NT>;

@@ -225,8 +225,11 @@ def hilbert_gain(cfs: np.ndarray, sds: np.ndarray, fs: float, envelope: bool = T
     return np.ascontiguousarray(out, dtype=np.float32), lo.astype(np.int32), rows
 
 
-def hilbert_halo(cfs: np.ndarray, sds: np.ndarray, fs: float, T: int, nsigma: float = 6.5) -> int:
-    """Samples of context each block needs.  Raises NotImplementedError when the bank cannot
+def hilbert_halo(cfs: np.ndarray, sds: np.ndarray, fs: float, T: int, nsigma: float = 5.0) -> int:
+    """Samples of context each block needs: nsigma standard deviations of the widest time-domain
+    Gaussian (5 sigma leaves erfc(5/sqrt 2) = 5.7e-7 of the kernel weight outside the halo, the
+    worst-case relative error; measured 1.6e-7 against the whole-record reference, the same as
+    with 6.5 sigma where the float32 tables dominate; 4.5 sigma measures 4.5e-6).  Raises NotImplementedError when the bank cannot
     be evaluated block-wise (kernels too long, or gain not negligible at DC / Nyquist)."""
     sigma_t = 1.0 / (2.0 * np.pi * sds)                 # seconds, per band
     halo = int(np.ceil(nsigma * sigma_t.max() * fs))

@@ -7,6 +7,7 @@ and the stream; all arithmetic happens in libecog_sm100.so.  No CPU path exists.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -149,7 +150,6 @@ def zscore(x: torch.Tensor, t0: int = 0, t1: Optional[int] = None, nan_to_zero: 
 
 # ------------------------------------------------------------------------ K3
 def _sos_threads_per_sm() -> int:
-    import os
     return int(os.environ.get("ECOG_SOS_TPS", "512"))
 
 
