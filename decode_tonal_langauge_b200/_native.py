@@ -46,6 +46,11 @@ class ResampleTables(C.Structure):
                 ("tw_T", C.c_void_p), ("tw_num", C.c_void_p), ("bin_gain", C.c_void_p)]
 
 
+class FftTables(C.Structure):
+    _fields_ = [("perm_a", C.c_void_p), ("perm_b", C.c_void_p), ("tw_a", C.c_void_p), ("tw_b", C.c_void_p),
+                ("tw_big_hi", C.c_void_p), ("tw_big_lo", C.c_void_p)]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _I32 = C.c_int32
@@ -71,6 +76,10 @@ PROTOTYPES = {
     "ecog_resample_workspace": (_SZ, [C.POINTER(ResamplePlan), _I64]),
     "ecog_fft_resample": (C.c_int, [_P, _P, _I64, _I64, _I64, C.POINTER(ResamplePlan),
                                     C.POINTER(ResampleTables), _P, _SZ, _P]),
+    "ecog_fft_c2c_workspace": (_SZ, [C.POINTER(FftAxis), C.POINTER(FftAxis), _I64]),
+    "ecog_fft_c2c": (C.c_int, [_P, _P, _I64, _I64, _I64, C.POINTER(FftAxis), C.POINTER(FftAxis),
+                               C.POINTER(FftTables), _I32, C.c_float, _P, _SZ, _P]),
+    "ecog_cplx_modulate": (C.c_int, [_P, _I32, _I64, _I64, _P, _P, _I32, _I64, _I64, _I64, _P]),
     "ecog_fir_decimate": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _I32, _I32, _I32, _P]),
     "ecog_fir_causal": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _I32, _P]),
     "ecog_rolling_workspace": (_SZ, [_I64, _I64]),

@@ -304,6 +304,56 @@ static int launch_pass(PassParams& P, int64_t C, cudaStream_t st, const char* wh
     return check_launch(what);
 }
 
+// out[c, i] = (i < in_len ? in[c, i] * table[i] : 0)  for i < out_len; real or complex input,
+// complex or real-part output.  The glue of the chirp-z path (zero padding + chirp / spectrum
+// multiplications); HBM-bound streaming.
+template <bool IN_CPLX, bool OUT_CPLX>
+__global__ void __launch_bounds__(256)
+cplx_modulate_kernel(const float* __restrict__ in, int64_t in_len, int64_t ld_in,
+                     const float2* __restrict__ table, float* __restrict__ out, int64_t out_len, int64_t ld_out) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= out_len) return;
+    const int64_t c = blockIdx.y;
+    float2 r = make_float2(0.f, 0.f);
+    if (i < in_len) {                                   // the table has in_len entries
+        float2 v = make_float2(0.f, 0.f);
+        if (IN_CPLX) v = reinterpret_cast<const float2*>(in)[c * ld_in + i];
+        else v.x = in[c * ld_in + i];
+        const float2 w = __ldg(&table[i]);
+        r = IN_CPLX ? cmulf(v, w) : make_float2(v.x * w.x, v.x * w.y);
+    }
+    if (OUT_CPLX) reinterpret_cast<float2*>(out)[c * ld_out + i] = r;
+    else out[c * ld_out + i] = r.x;
+}
+
+// generic complex four-step FFT of C rows of N = a.n * b.n points (forward, or inverse as
+// conj -> forward -> conj), natural order in and out
+static int run_c2c(const float2* in, float2* out, int64_t C, int64_t ld_in, int64_t ld_out,
+                   const ecog_fft_axis& fa, const ecog_fft_axis& fb, const ecog_fft_tables* tb,
+                   int inverse, float scale, float2* tmp, cudaStream_t st) {
+    const int64_t N = (int64_t)fa.n * fb.n;
+    PassParams P;
+    memset(&P, 0, sizeof(P));
+    P.in = in; P.in_ch_stride = ld_in;
+    P.n = fa.n; P.m = fb.n; P.perm = tb->perm_a; P.tw = (const float2*)tb->tw_a;
+    P.tw_hi = (const float2*)tb->tw_big_hi; P.tw_lo = (const float2*)tb->tw_big_lo;
+    P.conj_in = inverse ? 1 : 0; P.scale = 1.f; P.keep_lo = 1 << 30; P.keep_hi = 0;
+    ECOG_TRY(fill_axis(fa, P.ax));
+    if (fb.n == 1) {     // one pass: natural-order store, finish here
+        P.out = out; P.out_ch_stride = ld_out; P.transposed = 0; P.twiddle = 0;
+        P.conj_out = inverse ? 1 : 0; P.scale = scale;
+        return launch_pass(P, C, st, "fft_c2c");
+    }
+    P.out = tmp; P.out_ch_stride = N; P.transposed = 1; P.twiddle = 1;
+    ECOG_TRY(launch_pass(P, C, st, "fft_c2c_a"));
+    memset(&P, 0, sizeof(P));
+    P.in = tmp; P.in_ch_stride = N; P.out = out; P.out_ch_stride = ld_out;
+    P.n = fb.n; P.m = fa.n; P.perm = tb->perm_b; P.tw = (const float2*)tb->tw_b;
+    P.conj_out = inverse ? 1 : 0; P.scale = scale; P.keep_lo = 1 << 30; P.keep_hi = 0;
+    ECOG_TRY(fill_axis(fb, P.ax));
+    return launch_pass(P, C, st, "fft_c2c_b");
+}
+
 static size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 
 }  // namespace ecog
@@ -395,4 +445,40 @@ extern "C" int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_
     P.conj_out = 1; P.scale = (float)(1.0 / (double)Nh); P.keep_lo = 1 << 30; P.keep_hi = 0;
     ECOG_TRY(fill_axis(plan->ib, P.ax));
     return launch_pass(P, C, st, "fft_inv_b");
+}
+
+extern "C" size_t ecog_fft_c2c_workspace(const ecog_fft_axis* fa, const ecog_fft_axis* fb, int64_t C) {
+    if (!fa || !fb || fb->n <= 1) return 256;
+    return align256((size_t)C * fa->n * fb->n * sizeof(float2));
+}
+
+extern "C" int ecog_fft_c2c(const float* d_in, float* d_out, int64_t C, int64_t ld_in, int64_t ld_out,
+                            const ecog_fft_axis* fa, const ecog_fft_axis* fb, const ecog_fft_tables* tables,
+                            int32_t inverse, float scale, void* d_workspace, size_t workspace_bytes,
+                            ecog_stream_t stream) {
+    if (!fa || !fb || !tables) return fail(ECOG_E_VALUE, "ecog_fft_c2c: null plan");
+    const int64_t N = (int64_t)fa->n * fb->n;
+    if (C <= 0 || C > 65535 || N < 1 || ld_in < N || ld_out < N) return fail(ECOG_E_VALUE, "ecog_fft_c2c: bad shape");
+    if ((reinterpret_cast<uintptr_t>(d_in) & 7u) || (reinterpret_cast<uintptr_t>(d_out) & 7u))
+        return fail(ECOG_E_VALUE, "ecog_fft_c2c: rows must be 8-byte aligned");
+    if (workspace_bytes < ecog_fft_c2c_workspace(fa, fb, C))
+        return fail(ECOG_E_WORKSPACE, "ecog_fft_c2c: workspace %zu < %zu", workspace_bytes, ecog_fft_c2c_workspace(fa, fb, C));
+    return run_c2c(reinterpret_cast<const float2*>(d_in), reinterpret_cast<float2*>(d_out), C, ld_in, ld_out,
+                   *fa, *fb, tables, inverse, scale, reinterpret_cast<float2*>(d_workspace), (cudaStream_t)stream);
+}
+
+extern "C" int ecog_cplx_modulate(const float* d_in, int32_t in_is_complex, int64_t in_len, int64_t ld_in,
+                                  const float* d_table, float* d_out, int32_t out_is_complex, int64_t out_len,
+                                  int64_t ld_out, int64_t C, ecog_stream_t stream) {
+    if (C <= 0 || C > 65535 || out_len <= 0 || in_len < 0 || ld_out < out_len || ld_in < (in_len < out_len ? in_len : out_len))
+        return fail(ECOG_E_VALUE, "ecog_cplx_modulate: bad shape");
+    if (!d_in || !d_out || !d_table) return fail(ECOG_E_VALUE, "ecog_cplx_modulate: null pointer");
+    dim3 grid((unsigned)ceil_div(out_len, 256), (unsigned)C);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float2* tb = reinterpret_cast<const float2*>(d_table);
+    if (in_is_complex && out_is_complex) cplx_modulate_kernel<true, true><<<grid, 256, 0, st>>>(d_in, in_len, ld_in, tb, d_out, out_len, ld_out);
+    else if (in_is_complex) cplx_modulate_kernel<true, false><<<grid, 256, 0, st>>>(d_in, in_len, ld_in, tb, d_out, out_len, ld_out);
+    else if (out_is_complex) cplx_modulate_kernel<false, true><<<grid, 256, 0, st>>>(d_in, in_len, ld_in, tb, d_out, out_len, ld_out);
+    else cplx_modulate_kernel<false, false><<<grid, 256, 0, st>>>(d_in, in_len, ld_in, tb, d_out, out_len, ld_out);
+    return check_launch("cplx_modulate");
 }

@@ -21,6 +21,7 @@ from typing import List, Tuple
 import numpy as np
 
 MAX_AXIS = 2800          # longest in-shared-memory FFT: n * (8 + 1) * 8 B <= ~200 KB
+MAX_AXIS_NARROW = 5600   # with 4-column tiles (n * 5 * 8 B): only the chirp-z path goes this far
 TILE_W = 8
 BIG_SPLIT = 4096         # two-level table for the four-step twiddles W_N^e, e = hi*4096 + lo
 
@@ -61,24 +62,24 @@ def roots(n: int, sign: float = -1.0) -> np.ndarray:
     return np.stack([np.cos(ang), np.sin(ang)], axis=1).astype(np.float32)
 
 
-def split_size(N: int) -> Tuple[int, int]:
-    """N = n_a * n_b with both factors 2-3-5 smooth, <= MAX_AXIS, n_b a multiple of TILE_W
+def split_size(N: int, max_axis: int = MAX_AXIS) -> Tuple[int, int]:
+    """N = n_a * n_b with both factors 2-3-5 smooth, <= max_axis, n_b a multiple of TILE_W
     where possible and the pair as balanced as possible.  (n_a, 1) for short rows."""
     factorize(N)
     if N <= MAX_AXIS:
         return N, 1
     best = None
-    for na in range(2, MAX_AXIS + 1):
+    for na in range(2, max_axis + 1):
         if N % na:
             continue
         nb = N // na
-        if nb > MAX_AXIS:
+        if nb > max_axis:
             continue
         score = (0 if nb % TILE_W == 0 else 1, 0 if na % TILE_W == 0 else 1, abs(na - nb))
         if best is None or score < best[0]:
             best = (score, na, nb)
     if best is None:
-        raise NotImplementedError(f"FFT length {N} does not split into two factors <= {MAX_AXIS}")
+        raise NotImplementedError(f"FFT length {N} does not split into two factors <= {max_axis}")
     return best[1], best[2]
 
 
@@ -104,8 +105,8 @@ class BigPlan:
     tw_lo: np.ndarray       # float32 (BIG_SPLIT, 2):          W_N^{lo}
 
 
-def big_plan(N: int) -> BigPlan:
-    na, nb = split_size(N)
+def big_plan(N: int, max_axis: int = MAX_AXIS) -> BigPlan:
+    na, nb = split_size(N, max_axis)
     hi = np.arange(-(-N // BIG_SPLIT), dtype=np.float64) * BIG_SPLIT
     lo = np.arange(BIG_SPLIT, dtype=np.float64)
     f = lambda e: np.stack([np.cos(-2 * np.pi * e / N), np.sin(-2 * np.pi * e / N)], axis=1).astype(np.float32)
@@ -137,6 +138,95 @@ def resample_plan(T: int, num: int) -> ResamplePlan:
     return ResamplePlan(T, num, big_plan(T // 2), big_plan(Nh), tw_T, tw_num)
 
 
+# ------------------------------------------------------------ chirp-z resampling
+def next_smooth_even(n: int) -> int:
+    """Smallest even 2-3-5 smooth integer >= n that splits into two shared-memory axes."""
+    n = max(int(n), 2)
+    while True:
+        m = n
+        for p in (2, 3, 5):
+            while m % p == 0:
+                m //= p
+        if m == 1 and n % 2 == 0:
+            try:
+                split_size(n, MAX_AXIS_NARROW)
+                return n
+            except NotImplementedError:
+                pass
+        n += 1
+
+
+def _chirp(n: int, L: int) -> np.ndarray:
+    """exp(+i pi k^2 / L), k < n, with the phase reduced exactly (integers) modulo 2 L."""
+    k = np.arange(n, dtype=np.int64)
+    ph = (k * k) % (2 * L)
+    return np.exp(1j * np.pi * ph.astype(np.float64) / L)
+
+
+def _c2(a: np.ndarray) -> np.ndarray:
+    """complex128 -> (n, 2) float32"""
+    return np.ascontiguousarray(np.stack([a.real, a.imag], axis=1).astype(np.float32))
+
+
+@dataclass(frozen=True)
+class CztPlan:
+    """Bluestein realisation of scipy.signal.resample(x, num) for ANY row length T
+    (ref: preprocess/signal/downsample.py:21-27; real TDT rates give non-smooth, odd lengths).
+
+      forward  X[k] = conj(w[k]) * sum_n (x[n] conj(w[n])) w[k - n],   w[n] = exp(i pi n^2 / T),
+               k < K = min(num, T)//2 + 1, as a circular convolution of smooth length M1 >= T + K - 1;
+      inverse  y[m] = Re( v[m] * sum_k (G[k] v[k]) conj(v[m - k]) ),   v[j] = exp(i pi j^2 / num),
+               G[k] = X[k] * (num/T) * Nyquist rule * hermitian weight / num, length M2 >= K + num - 1.
+    All tables float64 -> float32 once; FB1 / FB2 are the FFTs of the chirp kernels (1/M folded in)."""
+    T: int
+    num: int
+    K: int
+    M1: int
+    M2: int
+    fft1: BigPlan
+    fft2: BigPlan
+    pre: np.ndarray      # (T, 2)   conj(w[n])
+    FB1: np.ndarray      # (M1, 2)
+    mid: np.ndarray      # (K, 2)   conj(w[k]) * scale[k] * h[k] / num * v[k]  (* bin_gain[k])
+    FB2: np.ndarray      # (M2, 2)
+    post: np.ndarray     # (num, 2) v[m]
+
+
+@functools.lru_cache(maxsize=8)
+def _czt_plan(T: int, num: int, gain_key) -> CztPlan:
+    from scipy import fft as sp_fft
+    if T < 2 or num < 2:
+        raise ValueError("resample needs at least two samples in and out")
+    m = min(num, T)
+    K = m // 2 + 1
+    M1 = next_smooth_even(T + K - 1)
+    M2 = next_smooth_even(K + num - 1)
+    w = _chirp(max(T, K), T)
+    b = np.zeros(M1, dtype=np.complex128)
+    b[:K] = w[:K]
+    b[M1 - np.arange(1, T)] = w[1:T]
+    FB1 = sp_fft.fft(b) / M1
+    scale = np.full(K, num / T)
+    if m % 2 == 0 and num != T:                     # scipy's unpaired-bin rule
+        scale[m // 2] *= 2.0 if num < T else 0.5
+    h = np.full(K, 2.0)
+    h[0] = 1.0
+    if num % 2 == 0 and K - 1 == num // 2:
+        h[K - 1] = 1.0                              # the output's own Nyquist bin is not doubled
+    v = _chirp(max(num, K), num)
+    mid = np.conj(w[:K]) * scale * h / num * v[:K]
+    b2 = np.zeros(M2, dtype=np.complex128)
+    b2[:num] = np.conj(v[:num])
+    b2[M2 - np.arange(1, K)] = np.conj(v[1:K])
+    FB2 = sp_fft.fft(b2) / M2
+    return CztPlan(T, num, K, M1, M2, big_plan(M1, MAX_AXIS_NARROW), big_plan(M2, MAX_AXIS_NARROW),
+                   _c2(np.conj(w[:T])), _c2(FB1), mid, _c2(FB2), _c2(v[:num]))
+
+
+def czt_plan(T: int, num: int) -> CztPlan:
+    return _czt_plan(int(T), int(num), None)
+
+
 # ------------------------------------------------------- two-stage resampling
 FIR_MAX_TAPS = 256
 FIR_ATTENUATION_DB = 120.0
@@ -160,10 +250,10 @@ def predecimation(T: int, num: int):
     rounded to float32 once; the compensation uses the ROUNDED taps' exact response."""
     from scipy import signal as sp_signal
     from scipy import fft as sp_fft
-    if num >= T or num % 2:
+    if num >= T:
         return None
     for D in (4, 2):
-        if T % D or (T // D) % 2:
+        if T % D:
             continue
         T1 = T // D
         if T1 < 1.15 * num:

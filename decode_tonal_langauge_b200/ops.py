@@ -344,6 +344,74 @@ def _fft_resample(x: torch.Tensor, num: int, bin_gain: Optional[np.ndarray], gai
     return y
 
 
+def _fft_tables(bp: FP.BigPlan, key, dev):
+    t = lambda name, arr: _dev_table(key + (name,), lambda: arr, dev)
+    tb = nat.FftTables()
+    keep = [t("perm_a", bp.a.perm), t("perm_b", bp.b.perm), t("tw_a", bp.a.tw), t("tw_b", bp.b.tw),
+            t("tw_hi", bp.tw_hi), t("tw_lo", bp.tw_lo)]
+    tb.perm_a, tb.perm_b, tb.tw_a, tb.tw_b, tb.tw_big_hi, tb.tw_big_lo = [k.data_ptr() for k in keep]
+    return tb, keep
+
+
+def fft_c2c(z: torch.Tensor, bp: FP.BigPlan, inverse: bool = False, scale: float = 1.0,
+            out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Complex FFT of every row of ``z`` ((C, N, 2) float32, N = bp.N), natural order."""
+    Cn, N, _ = z.shape
+    if N != bp.N:
+        raise ValueError(f"row length {N} does not match the plan ({bp.N})")
+    out = z if out is None else out
+    tb, keep = _fft_tables(bp, ("c2c", bp.N), z.device)
+    fa, fb = _axis(bp.a), _axis(bp.b)
+    ws = workspace(lib.ecog_fft_c2c_workspace(C.byref(fa), C.byref(fb), Cn), z.device, "fft")
+    nat.check(lib.ecog_fft_c2c(_ptr(z), _ptr(out), Cn, int(z.stride(0)) // 2, int(out.stride(0)) // 2, C.byref(fa),
+                               C.byref(fb), C.byref(tb), 1 if inverse else 0, float(scale), _ptr(ws), ws.numel(),
+                               _stream()))
+    return out
+
+
+def _modulate(src: torch.Tensor, in_len: int, table: torch.Tensor, dst: torch.Tensor, out_len: int) -> None:
+    """dst[c, i] = (i < in_len ? src[c, i] : 0) * table[i]; complex tensors are (C, n, 2) float32."""
+    in_c, out_c = src.dim() == 3, dst.dim() == 3
+    ld_in = int(src.stride(0)) // (2 if in_c else 1)
+    ld_out = int(dst.stride(0)) // (2 if out_c else 1)
+    nat.check(lib.ecog_cplx_modulate(_ptr(src), 1 if in_c else 0, int(in_len), ld_in, _ptr(table), _ptr(dst),
+                                     1 if out_c else 0, int(out_len), ld_out, int(src.shape[0]), _stream()))
+
+
+CZT_BLOCK_BYTES = 2 << 30        # channel block size of the chirp-z path (two complex buffers)
+
+
+def _czt_resample(x: torch.Tensor, num: int, bin_gain: Optional[np.ndarray] = None, gain_key=None) -> torch.Tensor:
+    """Any-length scipy.signal.resample via Bluestein (plan and tables: fftplan.czt_plan)."""
+    Cn, T = x.shape
+    p = FP.czt_plan(int(T), int(num))
+    dev = x.device
+    key = ("czt", T, num)
+    mid_h = p.mid if bin_gain is None else p.mid * np.asarray(bin_gain[:p.K], dtype=np.float64)
+    tab = {name: _dev_table(key + (name,), (lambda a=arr: a), dev)
+           for name, arr in (("pre", p.pre), ("FB1", p.FB1), ("FB2", p.FB2), ("post", p.post))}
+    tab["mid"] = _dev_table(key + ("mid", gain_key), lambda: FP._c2(mid_h), dev)
+    y = torch.empty((Cn, num), dtype=torch.float32, device=dev)
+    M = max(p.M1, p.M2)
+    blk = int(max(1, min(Cn, CZT_BLOCK_BYTES // (2 * M * 8))))
+    for c0 in range(0, Cn, blk):
+        c1 = min(Cn, c0 + blk)
+        a = torch.empty((c1 - c0, p.M1, 2), dtype=torch.float32, device=dev)
+        _modulate(x[c0:c1], T, tab["pre"], a, p.M1)                      # x conj(w), zero padded
+        fft_c2c(a, p.fft1)
+        _modulate(a, p.M1, tab["FB1"], a, p.M1)                          # times FFT of the chirp kernel
+        fft_c2c(a, p.fft1, inverse=True)
+        b = torch.empty((c1 - c0, p.M2, 2), dtype=torch.float32, device=dev)
+        _modulate(a, p.K, tab["mid"], b, p.M2)                           # resample rules, inverse chirp, padded
+        del a
+        fft_c2c(b, p.fft2)
+        _modulate(b, p.M2, tab["FB2"], b, p.M2)
+        fft_c2c(b, p.fft2, inverse=True)
+        _modulate(b, num, tab["post"], y[c0:c1], num)                    # Re(. v[m])
+        del b
+    return y
+
+
 def fft_resample(x: torch.Tensor, num: int, two_stage: Optional[bool] = None) -> torch.Tensor:
     """scipy.signal.resample(x, num, axis=1) for real rows (ref: downsample.py:21-27).
 
@@ -353,16 +421,25 @@ def fft_resample(x: torch.Tensor, num: int, two_stage: Optional[bool] = None) ->
     x = as_signal(x)
     Cn, T = x.shape
     num = int(num)
+    if num < 2 or T < 2:
+        raise ValueError("resample needs at least two samples in and out")
+
+    def smooth(n_in: int) -> bool:
+        try:
+            FP.resample_plan(n_in, num)
+            return True
+        except NotImplementedError:
+            return False
+
     pre = FP.predecimation(int(T), num) if two_stage in (None, True) else None
     if pre is not None:
-        try:
-            FP.resample_plan(int(T) // pre.D, num)
-        except NotImplementedError:
-            pre = None
-    if pre is None:
+        x1 = fir_decimate(x, pre.taps, pre.offset, pre.D)
+        if smooth(int(T) // pre.D):
+            return _fft_resample(x1, num, pre.bin_gain, gain_key=(int(T), pre.D))
+        return _czt_resample(x1, num, pre.bin_gain, gain_key=(int(T), pre.D))     # non-smooth T/D: Bluestein
+    if smooth(int(T)):
         return _fft_resample(x, num, None)
-    x1 = fir_decimate(x, pre.taps, pre.offset, pre.D)
-    return _fft_resample(x1, num, pre.bin_gain, gain_key=(int(T), pre.D))
+    return _czt_resample(x, num)
 
 
 # ------------------------------------------------------------------------ K8

@@ -152,6 +152,32 @@ int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_t ldx, int6
                       const ecog_resample_plan* plan, const ecog_resample_tables* tables,
                       void* d_workspace, size_t workspace_bytes, ecog_stream_t stream);
 
+/* ----------------------------- K5b: building blocks of the chirp-z (Bluestein) path
+ * downsample.py:21-27 for rows whose length is NOT 2-3-5 smooth (real TDT rates: T = 1 831 054,
+ * num = 239 999): X[k] = conj(w[k]) (x conj(w) * w)[k] with w[n] = exp(i pi n^2 / T), the
+ * convolution done with smooth-length complex FFTs; same for the inverse of `num` points.
+ * Host glue: decode_tonal_langauge_b200/fftplan.py::czt_plan, ops._czt_resample.
+ *   ecog_fft_c2c      : C rows of N = fa.n * fb.n complex points (interleaved float), natural
+ *                       order in and out; inverse = conj -> forward -> conj; out *= scale.
+ *                       Strides in complex elements; workspace from ecog_fft_c2c_workspace.
+ *   ecog_cplx_modulate: out[c,i] = (i < in_len ? in[c,i] * table[i] : 0), i < out_len (table has
+ *                       in_len complex entries), with real
+ *                       or complex input and complex or real-part output (zero padding, chirp
+ *                       and spectrum multiplications).  May run in place.                      */
+typedef struct {
+    const int32_t *perm_a, *perm_b;      /* digit reversal per axis                           */
+    const float *tw_a, *tw_b;            /* W_n^k per axis                                    */
+    const float *tw_big_hi, *tw_big_lo;  /* four-step twiddles, two-level table (split 4096)  */
+} ecog_fft_tables;
+size_t ecog_fft_c2c_workspace(const ecog_fft_axis* fa, const ecog_fft_axis* fb, int64_t C);
+int ecog_fft_c2c(const float* d_in, float* d_out, int64_t C, int64_t ld_in, int64_t ld_out,
+                 const ecog_fft_axis* fa, const ecog_fft_axis* fb, const ecog_fft_tables* tables,
+                 int32_t inverse, float scale, void* d_workspace, size_t workspace_bytes,
+                 ecog_stream_t stream);
+int ecog_cplx_modulate(const float* d_in, int32_t in_is_complex, int64_t in_len, int64_t ld_in,
+                       const float* d_table, float* d_out, int32_t out_is_complex, int64_t out_len,
+                       int64_t ld_out, int64_t C, ecog_stream_t stream);
+
 /* ------------------------------- K5a: circular FIR low-pass + integer decimation
  * First stage of the two-stage realisation of downsample.py:21-27 for large ratios:
  *   y[c, m] = sum_{j<ntaps} h[j] * x[c, (m*D + j - offset) mod T],  m = 0 .. T/D - 1.

@@ -186,6 +186,21 @@ def resample_model(x32: np.ndarray, plan, bin_gain=None) -> np.ndarray:
     return y
 
 
+def czt_resample_model(x32: np.ndarray, plan, bin_gain=None) -> np.ndarray:
+    """Model of ops._czt_resample for one row: the device runs exactly these steps with
+    ecog_cplx_modulate / ecog_fft_c2c (complex64 there, the plan's float32 tables here)."""
+    c = lambda t: t[:, 0].astype(np.float64) + 1j * t[:, 1].astype(np.float64)
+    A = np.zeros(plan.M1, dtype=np.complex128)
+    A[:plan.T] = x32.astype(np.float64) * c(plan.pre)
+    c1 = np.fft.ifft(np.fft.fft(A) * c(plan.FB1)) * plan.M1
+    mid = plan.mid if bin_gain is None else plan.mid * bin_gain[:plan.K].astype(np.float64)
+    mid = mid.astype(np.complex64).astype(np.complex128)
+    A2 = np.zeros(plan.M2, dtype=np.complex128)
+    A2[:plan.K] = c1[:plan.K] * mid
+    c2 = np.fft.ifft(np.fft.fft(A2) * c(plan.FB2)) * plan.M2
+    return (c2[:plan.num] * c(plan.post)).real.astype(np.float32)
+
+
 def fft4096_model(z: np.ndarray, tw: np.ndarray) -> np.ndarray:
     """Model of the 16x16x16 register FFT of csrc/hilbert.cu using the table from
     ecog_hilbert_twiddles (first two (16,256,2) float32 sections)."""

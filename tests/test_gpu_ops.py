@@ -263,9 +263,38 @@ def test_fir_decimate_matches_model(ops, T, D):
         assert y.shape == ref.shape and max_rel(y, ref64) < 2e-6
 
 
-def test_resample_odd_length_is_declared_unsupported(ops):
-    with pytest.raises(NotImplementedError):
-        ops.fft_resample(dev(np.zeros((1, 9001), np.float32)), 1800)
+def test_resample_odd_golden(ops, golden):
+    """Odd row length: the reference's own output for a 9001-sample row (chirp-z path)."""
+    g = golden("steps")
+    assert max_rel(host(ops.fft_resample(dev(g["x_odd"]), 1800)), g["downsample_odd"]) < TOL
+
+
+@pytest.mark.parametrize("T,num", [(9001, 1800), (18310, 2399), (7919, 1000), (1000, 1501), (4099, 4099),
+                                   (12002, 2400), (183_106, 23_999)])
+def test_resample_any_length_vs_oracle(ops, T, num):
+    """Non-smooth / odd / prime lengths (real TDT rates) through Bluestein, with and without the
+    FIR pre-decimation stage."""
+    from oracle import steps as S
+    rng = np.random.default_rng(T + num)
+    x = (np.cumsum(rng.standard_normal((3, T)), axis=1) * 0.3 + rng.standard_normal((3, T)) * 5).astype(np.float32)
+    ref = S.fft_resample(x.astype(np.float64), num)
+    assert max_rel(host(ops.fft_resample(dev(x), num)), ref) < TOL
+    assert max_rel(host(ops.fft_resample(dev(x), num, two_stage=False)), ref) < TOL
+
+
+def test_fft_c2c_matches_numpy(ops):
+    from decode_tonal_langauge_b200 import fftplan as FP
+    rng = np.random.default_rng(1)
+    for N in (360, 3600, 36000, 196608):
+        z = (rng.standard_normal((2, N)) + 1j * rng.standard_normal((2, N))).astype(np.complex64)
+        zd = torch.view_as_real(torch.from_numpy(z)).contiguous().cuda()
+        bp = FP.big_plan(N, FP.MAX_AXIS_NARROW)
+        Z = torch.view_as_complex(ops.fft_c2c(zd.clone(), bp)).cpu().numpy()
+        ref = np.fft.fft(z.astype(np.complex128), axis=1)
+        assert np.max(np.abs(Z - ref)) / np.max(np.abs(ref)) < 2e-6
+        back = torch.view_as_complex(ops.fft_c2c(zd.clone(), bp, inverse=True, scale=1.0 / N)).cpu().numpy()
+        ref = np.fft.ifft(z.astype(np.complex128), axis=1)
+        assert np.max(np.abs(back - ref)) / np.max(np.abs(ref)) < 2e-6
 
 
 # ------------------------------------------------------------------------ K8

@@ -71,12 +71,32 @@ def test_predecimation_declines_small_ratios():
     assert FP.predecimation(24000, 12000) is None       # T/2 == num: no transition band
     assert FP.predecimation(16000, 16000) is None
     assert FP.predecimation(6000, 9000) is None         # up-sampling
-    assert FP.predecimation(12002, 2400) is None        # T/2 odd: the FFT stage needs even rows
+    assert FP.predecimation(12001, 2400) is None        # odd T: no integer decimation of the circle
+    assert FP.predecimation(12002, 2400).D == 2         # T/2 odd: the chirp-z stage takes the 6001-sample rows
 
 
 def test_resample_odd_lengths_are_declared_unsupported():
     with pytest.raises(NotImplementedError):
-        FP.resample_plan(9001, 1800)
+        FP.resample_plan(9001, 1800)          # the smooth-length plan declines; the chirp-z plan takes over
+
+
+@pytest.mark.parametrize("T,num", [(9001, 1800), (18310, 2399), (12000, 2400), (1000, 1501), (4099, 4099),
+                                   (7919, 1000), (6000, 9001)])
+def test_czt_resample_model_vs_oracle(T, num):
+    """Bluestein plan (any length, odd, prime) == scipy.signal.resample of the whole row."""
+    rng = np.random.default_rng(T + num)
+    x = (np.cumsum(rng.standard_normal(T)) * 0.3 + rng.standard_normal(T) * 5).astype(np.float32)
+    p = FP.czt_plan(T, num)
+    assert p.M1 >= T + p.K - 1 and p.M2 >= p.K + num - 1 and p.M1 % 2 == 0 and p.M2 % 2 == 0
+    got = EM.czt_resample_model(x, p)
+    ref = S.fft_resample(x[None].astype(np.float64), num)[0]
+    assert max_rel(got, ref) < 2e-6
+
+
+def test_czt_plan_for_a_real_tdt_block():
+    p = FP.czt_plan(1_831_054, 239_999)       # 600 s at 3051.7578125 Hz -> 400 Hz (SURVEY C4)
+    assert p.M1 == p.fft1.a.n * p.fft1.b.n and max(p.fft1.a.n, p.fft1.b.n) <= FP.MAX_AXIS_NARROW
+    assert p.M2 == p.fft2.a.n * p.fft2.b.n
 
 
 def test_hilbert_models(golden):
