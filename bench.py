@@ -194,7 +194,19 @@ def run_ours(args):
         raise SystemExit("bench.py needs CUDA devices; there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner on stdout when the communicator is created; the contract
+        # is ONE JSON line on stdout, so the banner goes to stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     from decode_tonal_langauge_b200 import _native as nat
     from decode_tonal_langauge_b200 import runtime as rt

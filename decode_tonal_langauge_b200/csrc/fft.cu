@@ -315,15 +315,31 @@ cplx_modulate_kernel(const float* __restrict__ in, int64_t in_len, int64_t ld_in
     if (i >= out_len) return;
     const int64_t c = blockIdx.y;
     float2 r = make_float2(0.f, 0.f);
-    if (i < in_len) {                                   // the table has in_len entries
+    if (i < in_len) {                                   // the table (if any) has in_len entries
         float2 v = make_float2(0.f, 0.f);
         if (IN_CPLX) v = reinterpret_cast<const float2*>(in)[c * ld_in + i];
         else v.x = in[c * ld_in + i];
-        const float2 w = __ldg(&table[i]);
+        const float2 w = table ? __ldg(&table[i]) : make_float2(1.f, 0.f);
         r = IN_CPLX ? cmulf(v, w) : make_float2(v.x * w.x, v.x * w.y);
     }
     if (OUT_CPLX) reinterpret_cast<float2*>(out)[c * ld_out + i] = r;
     else out[c * ld_out + i] = r.x;
+}
+
+// acc[c, i] (+)= scale * |z[c, i]|  (or scale * Re z[c, i]): band accumulation of the whole-record
+// Gaussian-Hilbert path
+template <bool ENV>
+__global__ void __launch_bounds__(256)
+cplx_absacc_kernel(const float2* __restrict__ z, int64_t ld_z, float* __restrict__ acc, int64_t ld_acc,
+                   int64_t len, float scale, int accumulate) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= len) return;
+    const int64_t c = blockIdx.y;
+    const float2 v = z[c * ld_z + i];
+    float r = ENV ? sqrtf(fmaf(v.x, v.x, v.y * v.y)) : v.x;
+    r *= scale;
+    if (accumulate) r += acc[c * ld_acc + i];
+    acc[c * ld_acc + i] = r;
 }
 
 // generic complex four-step FFT of C rows of N = a.n * b.n points (forward, or inverse as
@@ -472,7 +488,7 @@ extern "C" int ecog_cplx_modulate(const float* d_in, int32_t in_is_complex, int6
                                   int64_t ld_out, int64_t C, ecog_stream_t stream) {
     if (C <= 0 || C > 65535 || out_len <= 0 || in_len < 0 || ld_out < out_len || ld_in < (in_len < out_len ? in_len : out_len))
         return fail(ECOG_E_VALUE, "ecog_cplx_modulate: bad shape");
-    if (!d_in || !d_out || !d_table) return fail(ECOG_E_VALUE, "ecog_cplx_modulate: null pointer");
+    if (!d_in || !d_out) return fail(ECOG_E_VALUE, "ecog_cplx_modulate: null pointer");
     dim3 grid((unsigned)ceil_div(out_len, 256), (unsigned)C);
     cudaStream_t st = (cudaStream_t)stream;
     const float2* tb = reinterpret_cast<const float2*>(d_table);
@@ -481,4 +497,17 @@ extern "C" int ecog_cplx_modulate(const float* d_in, int32_t in_is_complex, int6
     else if (out_is_complex) cplx_modulate_kernel<false, true><<<grid, 256, 0, st>>>(d_in, in_len, ld_in, tb, d_out, out_len, ld_out);
     else cplx_modulate_kernel<false, false><<<grid, 256, 0, st>>>(d_in, in_len, ld_in, tb, d_out, out_len, ld_out);
     return check_launch("cplx_modulate");
+}
+
+extern "C" int ecog_cplx_abs_accumulate(const float* d_z, int64_t ld_z, float* d_acc, int64_t ld_acc, int64_t len,
+                                        int64_t C, int32_t envelope, float scale, int32_t accumulate,
+                                        ecog_stream_t stream) {
+    if (C <= 0 || C > 65535 || len <= 0 || ld_z < len || ld_acc < len || !d_z || !d_acc)
+        return fail(ECOG_E_VALUE, "ecog_cplx_abs_accumulate: bad shape");
+    dim3 grid((unsigned)ceil_div(len, 256), (unsigned)C);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float2* z = reinterpret_cast<const float2*>(d_z);
+    if (envelope) cplx_absacc_kernel<true><<<grid, 256, 0, st>>>(z, ld_z, d_acc, ld_acc, len, scale, accumulate);
+    else cplx_absacc_kernel<false><<<grid, 256, 0, st>>>(z, ld_z, d_acc, ld_acc, len, scale, accumulate);
+    return check_launch("cplx_abs_accumulate");
 }

@@ -223,7 +223,10 @@ def hilbert(x: torch.Tensor, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0,
     cfs, sds = D.gaussian_bank(freq_ranges, f0, octspace, filterbank_bias, filterbank_slope)
     if len(cfs) == 0:
         raise ValueError("the frequency ranges contain no filter-bank centre frequency")
-    halo = FP.hilbert_halo(cfs, sds, float(fs), T)
+    try:
+        halo = FP.hilbert_halo(cfs, sds, float(fs), T)
+    except NotImplementedError:
+        return _hilbert_global(x, float(fs), cfs, sds, bool(envelope), out)      # low-frequency bands
     key = ("hilbert_gain", tuple(cfs.tolist()), tuple(sds.tolist()), float(fs), bool(envelope))
     plan = _hilbert_plans.get(key)
     if plan is None:
@@ -234,6 +237,53 @@ def hilbert(x: torch.Tensor, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0,
     nat.check(lib.ecog_hilbert_env(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), _ptr(gain), len(cfs), rows,
                                    _hptr(shift), halo, 1 if envelope else 0,
                                    _ptr(_hilbert_twiddles(x.device)), _stream()))
+    return y
+
+
+HILBERT_GLOBAL_BLOCK_BYTES = 3 << 30
+
+
+def _hilbert_global(x: torch.Tensor, fs: float, cfs, sds, envelope: bool, out: Optional[torch.Tensor]):
+    """Whole-record Gaussian-Hilbert bank, exactly as the reference does it (ref:
+    frequency_filter.py:154-184): FFT of the row, Gaussian x analytic mask per band, inverse FFT,
+    |.| or real part, mean over bands.  Used when the bands' time kernels do not fit the 4096-sample
+    blocks of the fused kernel (low-frequency bands).  Complex four-step FFTs of length T."""
+    Cn, T = x.shape
+    try:
+        bp = FP.big_plan(int(T), FP.MAX_AXIS_NARROW)
+    except NotImplementedError as e:
+        raise NotImplementedError(
+            f"low-frequency Gaussian bands need a whole-record FFT, and the row length {T} is not a "
+            f"product of two 2-3-5 smooth factors <= {FP.MAX_AXIS_NARROW} ({e})")
+    dev = x.device
+    nb = len(cfs)
+    freqs = np.fft.fftfreq(T, 1.0 / fs)
+    h = np.zeros(T)
+    if T % 2 == 0:
+        h[0] = h[T // 2] = 1.0
+        h[1:T // 2] = 2.0
+    else:
+        h[0] = 1.0
+        h[1:(T + 1) // 2] = 2.0
+    y = out if out is not None else torch.empty((Cn, T), dtype=torch.float32, device=dev)
+    blk = int(max(1, min(Cn, HILBERT_GLOBAL_BLOCK_BYTES // (3 * T * 8))))
+    for c0 in range(0, Cn, blk):
+        c1 = min(Cn, c0 + blk)
+        Z = torch.empty((c1 - c0, T, 2), dtype=torch.float32, device=dev)
+        W = torch.empty_like(Z)
+        nat.check(lib.ecog_cplx_modulate(_ptr(x[c0:c1]), 0, T, _ld(x), C.c_void_p(0), _ptr(Z), 1, T, T, c1 - c0,
+                                         _stream()))
+        fft_c2c(Z, bp)
+        for b in range(nb):
+            H = np.exp(-0.5 * ((freqs - cfs[b]) / sds[b]) ** 2)
+            H[0] = 0.0
+            g = torch.from_numpy(FP._c2((H * h / T).astype(np.complex128))).to(dev)     # 1/T of the inverse FFT
+            _modulate(Z, T, g, W, T)
+            fft_c2c(W, bp, inverse=True)
+            nat.check(lib.ecog_cplx_abs_accumulate(_ptr(W), T, _ptr(y[c0:c1]), _ld(y), T, c1 - c0,
+                                                   1 if envelope else 0, 1.0 / nb, 1 if b else 0, _stream()))
+            del g
+        del Z, W
     return y
 
 

@@ -175,8 +175,14 @@ int ecog_fft_c2c(const float* d_in, float* d_out, int64_t C, int64_t ld_in, int6
                  int32_t inverse, float scale, void* d_workspace, size_t workspace_bytes,
                  ecog_stream_t stream);
 int ecog_cplx_modulate(const float* d_in, int32_t in_is_complex, int64_t in_len, int64_t ld_in,
-                       const float* d_table, float* d_out, int32_t out_is_complex, int64_t out_len,
-                       int64_t ld_out, int64_t C, ecog_stream_t stream);
+                       const float* d_table /* NULL = 1 */, float* d_out, int32_t out_is_complex,
+                       int64_t out_len, int64_t ld_out, int64_t C, ecog_stream_t stream);
+/* acc[c,i] (+)= scale * |z[c,i]| (envelope) or scale * Re z[c,i]: band accumulation of the
+ * whole-record Gaussian-Hilbert path (frequency_filter.py:171-184) used for banks whose time
+ * kernels do not fit the 4096-sample block of ecog_hilbert_env (low-frequency bands).           */
+int ecog_cplx_abs_accumulate(const float* d_z, int64_t ld_z, float* d_acc, int64_t ld_acc, int64_t len,
+                             int64_t C, int32_t envelope, float scale, int32_t accumulate,
+                             ecog_stream_t stream);
 
 /* ------------------------------- K5a: circular FIR low-pass + integer decimation
  * First stage of the two-stage realisation of downsample.py:21-27 for large ratios:

@@ -171,9 +171,25 @@ def test_hilbert_shapes(ops, C, T, fs):
     assert max_rel(y, S.hilbert_filter(x, fs, [70.0, 150.0])) < TOL
 
 
-def test_hilbert_low_band_is_declared_unsupported(ops):
-    with pytest.raises(NotImplementedError):
-        ops.hilbert(dev(np.zeros((1, 8000), np.float32)), 400.0, [0.5, 4.0])
+@pytest.mark.parametrize("envelope", [True, False])
+def test_hilbert_low_frequency_bands_whole_record(ops, golden, envelope):
+    """Theta / alpha bands at 2 kHz: time kernels longer than the block -> whole-record FFT path."""
+    from oracle import steps as S
+    g = golden("steps")
+    x, fs = g["x"], float(g["fs"])
+    ref = S.hilbert_filter(x, fs, [[4.0, 8.0], [8.0, 13.0]], envelope=envelope)
+    y = host(ops.hilbert(dev(x), fs, [[4.0, 8.0], [8.0, 13.0]], envelope=envelope))
+    assert max_rel(y, ref) < TOL
+
+
+def test_hilbert_delta_band_and_its_declared_limit(ops):
+    from oracle import steps as S
+    rng = np.random.default_rng(2)
+    x = (np.cumsum(rng.standard_normal((2, 8000)), axis=1)).astype(np.float32)
+    y = host(ops.hilbert(dev(x), 400.0, [0.5, 4.0]))
+    assert max_rel(y, S.hilbert_filter(x, 400.0, [0.5, 4.0])) < TOL
+    with pytest.raises(NotImplementedError):          # whole-record path on a prime row length
+        ops.hilbert(dev(np.zeros((1, 8009), np.float32)), 400.0, [0.5, 4.0])
 
 
 # ------------------------------------------------------------------ K6 / K7
