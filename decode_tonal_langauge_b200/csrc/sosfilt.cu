@@ -33,12 +33,14 @@ struct SosCoef {
 };
 struct SosMatrix { double m[2 * ECOG_MAX_SECTIONS][2 * ECOG_MAX_SECTIONS]; };
 
-template <int NSEC>
+// B1Z: every section has b1 == 0 (numerator b0 + b2 z^-2, e.g. the (1 - z^-2) sections of a
+// Butterworth band-pass): one DFMA less per section and sample.
+template <int NSEC, bool B1Z = false>
 __device__ __forceinline__ double sos_step(double u, const double (&c)[NSEC][5], double (&s)[NSEC][2]) {
 #pragma unroll
     for (int j = 0; j < NSEC; ++j) {
         const double y = fma(c[j][0], u, s[j][0]);
-        s[j][0] = fma(-c[j][3], y, fma(c[j][1], u, s[j][1]));
+        s[j][0] = B1Z ? fma(-c[j][3], y, s[j][1]) : fma(-c[j][3], y, fma(c[j][1], u, s[j][1]));
         s[j][1] = fma(-c[j][4], y, c[j][2] * u);
         u = y;
     }
@@ -325,7 +327,7 @@ sos_scan_kernel(const float* __restrict__ x, int64_t C, int64_t T, int64_t ldx,
 // (few DRAM pages / TLB entries live per CTA).
 // The backward sweep cannot run in place (its warm-up reads the forward result of the
 // neighbouring chunk), so the forward result lives in the workspace.
-template <int NSEC, bool REV, bool VEC, int NT>
+template <int NSEC, bool REV, bool VEC, int NT, bool B1Z>
 __global__ void __launch_bounds__(NT, 512 / NT)
 sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, int64_t T,
                 int64_t ldx, int64_t ldy, int L, int tail, int nChunks, int padlen, int zero_phase,
@@ -420,14 +422,14 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
                 for (int j = 0; j < NSEC; ++j) { s[j][0] = coef.zi[j][0] * (double)e0; s[j][1] = coef.zi[j][1] * (double)e0; }
                 for (int i = 0; i < padlen; ++i) {
                     const float e = 2.0f * x0 - xr[padlen - i];
-                    (void)sos_step<NSEC>((double)e, c, s);
+                    (void)sos_step<NSEC, B1Z>((double)e, c, s);
                 }
             } else {
                 const double* pb = padbuf + row * padlen;
                 const double y0 = pb[padlen - 1];
 #pragma unroll
                 for (int j = 0; j < NSEC; ++j) { s[j][0] = coef.zi[j][0] * y0; s[j][1] = coef.zi[j][1] * y0; }
-                for (int i = padlen - 1; i >= 0; --i) (void)sos_step<NSEC>(pb[i], c, s);
+                for (int i = padlen - 1; i >= 0; --i) (void)sos_step<NSEC, B1Z>(pb[i], c, s);
             }
         }
         float* tile = tiles + (size_t)((st - first) % kWarmRing) * NT * kPitch;
@@ -448,10 +450,10 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
 #pragma unroll
             for (int v = 0; v < kSub / 4; ++v) {
                 float4 yv;
-                yv.x = (float)sos_step<NSEC>((double)xin[v].x, c, s);
-                yv.y = (float)sos_step<NSEC>((double)xin[v].y, c, s);
-                yv.z = (float)sos_step<NSEC>((double)xin[v].z, c, s);
-                yv.w = (float)sos_step<NSEC>((double)xin[v].w, c, s);
+                yv.x = (float)sos_step<NSEC, B1Z>((double)xin[v].x, c, s);
+                yv.y = (float)sos_step<NSEC, B1Z>((double)xin[v].y, c, s);
+                yv.z = (float)sos_step<NSEC, B1Z>((double)xin[v].z, c, s);
+                yv.w = (float)sos_step<NSEC, B1Z>((double)xin[v].w, c, s);
                 if (write) {
                     if (!REV) *reinterpret_cast<float4*>(mine + 4 * v) = yv;
                     else *reinterpret_cast<float4*>(mine + (kSub - 4 - 4 * v)) = make_float4(yv.w, yv.z, yv.y, yv.x);
@@ -465,7 +467,7 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int u = sbase + 4 * v + e;
-                    if (u >= ulo && u < uhi) yv[e] = (float)sos_step<NSEC>((double)xv[e], c, s);
+                    if (u >= ulo && u < uhi) yv[e] = (float)sos_step<NSEC, B1Z>((double)xv[e], c, s);
                 }
                 if (write) {
                     if (!REV) *reinterpret_cast<float4*>(mine + 4 * v) = make_float4(yv[0], yv[1], yv[2], yv[3]);
@@ -508,23 +510,23 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
         double* pb = padbuf + row * padlen;
         for (int i = 0; i < padlen; ++i) {
             const float e = 2.0f * xe - xr[T - 2 - i];
-            pb[i] = sos_step<NSEC>((double)e, c, s);
+            pb[i] = sos_step<NSEC, B1Z>((double)e, c, s);
         }
     }
 }
 
-template <int NSEC, bool REV, int NT>
+template <int NSEC, bool REV, int NT, bool B1Z>
 static int launch_warm(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                        const ecog_sos_plan& p, int nChunks, const SosCoef& coef, double* padbuf, bool vec,
                        cudaStream_t st) {
     const size_t smem = ((size_t)kWarmRing * NT * kPitch) * sizeof(float) + (size_t)NT * (2 * sizeof(int64_t) + sizeof(int2));
     const unsigned grid = (unsigned)ceil_div(C * nChunks, NT);
     if (vec) {
-        auto k = sos_warm_kernel<NSEC, REV, true, NT>;
+        auto k = sos_warm_kernel<NSEC, REV, true, NT, B1Z>;
         ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, NT, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, p.zero_phase, coef, padbuf);
     } else {
-        auto k = sos_warm_kernel<NSEC, REV, false, NT>;
+        auto k = sos_warm_kernel<NSEC, REV, false, NT, B1Z>;
         ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k<<<grid, NT, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, p.zero_phase, coef, padbuf);
     }
@@ -540,11 +542,17 @@ static int run_sos_warm(const float* x, float* y, int64_t C, int64_t T, int64_t 
     const int64_t ldm = p.zero_phase ? ldt : ldy;
     const bool vec = aligned16(x) && aligned16(y) && aligned16(mid) && T % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldm % 4 == 0;
     const bool wide = p.threads >= 512;
-    if (wide) ECOG_TRY((launch_warm<NSEC, false, 512>(x, mid, C, T, ldx, ldm, p, nChunks, coef, padbuf, vec, st)));
-    else      ECOG_TRY((launch_warm<NSEC, false, 256>(x, mid, C, T, ldx, ldm, p, nChunks, coef, padbuf, vec, st)));
+    bool b1z = true;
+    for (int j = 0; j < NSEC; ++j) b1z = b1z && coef.c[j][1] == 0.0;
+#define ECOG_WARM(REVV, NTT, Y_IN, Y_OUT, LD_IN, LD_OUT)                                                                   \
+    (b1z ? launch_warm<NSEC, REVV, NTT, true>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, padbuf, vec, st)        \
+         : launch_warm<NSEC, REVV, NTT, false>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, padbuf, vec, st))
+    if (wide) ECOG_TRY(ECOG_WARM(false, 512, x, mid, ldx, ldm));
+    else      ECOG_TRY(ECOG_WARM(false, 256, x, mid, ldx, ldm));
     if (!p.zero_phase) return ECOG_OK;
-    if (wide) return launch_warm<NSEC, true, 512>(mid, y, C, T, ldm, ldy, p, nChunks, coef, padbuf, vec, st);
-    return launch_warm<NSEC, true, 256>(mid, y, C, T, ldm, ldy, p, nChunks, coef, padbuf, vec, st);
+    if (wide) return ECOG_WARM(true, 512, mid, y, ldm, ldy);
+    return ECOG_WARM(true, 256, mid, y, ldm, ldy);
+#undef ECOG_WARM
 }
 
 static size_t sos_smem_bytes() {

@@ -296,6 +296,14 @@ def _butter_design(order: int, freqs: Tuple[float, ...], fs: float, btype: str, 
     # ref: frequency_filter.py:226-227 -- (b, a) + filtfilt defaults
     b, a = sp_signal.butter(order, wn, btype=btype)
     sos = ba_to_sos(b, a)
+    if btype == "bandpass":
+        # scipy's rounded numerator IS b[0] (1 - z^-2)^order to the last bit; use that factorisation
+        # ((1, 0, -1) sections, b1 == 0: one DFMA less per section) instead of the numerically
+        # split 4-fold roots at +1 and -1
+        ideal = b[0] * np.poly(np.r_[np.ones(order), -np.ones(order)])
+        if np.max(np.abs(ideal - b)) <= 4e-16 * np.max(np.abs(b)) and sos.shape[0] == order:
+            sos[:, :3] = [1.0, 0.0, -1.0]
+            sos[0, :3] *= b[0]
     zi_direct = sp_signal.lfilter_zi(b, a)          # the installed scipy's own arithmetic
     zi = zi_to_cascade(b, a, sos, zi_direct)
     padlen = 3 * max(len(a), len(b))

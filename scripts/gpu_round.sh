@@ -1,3 +1,4 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests/test_gpu_ops.py -x -q -m gpu -k "hilbert" > gpurun_out/t14.log 2>&1; tail -3 gpurun_out/t14.log
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 2 --steps 2 --warmup 3 --workload C4small > gpurun_out/b2.out 2> gpurun_out/b2.err; wc -l gpurun_out/b2.out; head -c 200 gpurun_out/b2.out
+python scripts/prof_ops.py notch,bandpass,notch 256 7200000 5 > gpurun_out/t15_prof.log 2>&1; cat gpurun_out/t15_prof.log
+python bench.py --steps 5 --warmup 3 > gpurun_out/bench_c2_d.json 2> gpurun_out/bench_c2_d.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_c2_d.json')); print(d['ms_per_step'], d['value'], d['e2e']['ms_per_step'], d['step_ms'], d['clocks'])"
