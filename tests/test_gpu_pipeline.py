@@ -250,3 +250,50 @@ def test_full_size_properties():
     assert (y[0].to(torch.float64) - torch.sin(2 * np.pi * 37.0 * t2)).abs().max().item() < 1e-5
     env = ops.hilbert(tone, fs, [30.0, 45.0])
     assert env.shape == tone.shape and torch.isfinite(env).all()
+    # envelope of a pure in-band tone (periodic over the row) is constant: mean_b G_b(f) (A1)
+    from decode_tonal_langauge_b200 import design as D
+    f_tone = 100.0
+    tone = torch.sin(2 * np.pi * f_tone * t).to(torch.float32)[None].repeat(2, 1)
+    env = ops.hilbert(tone, fs, [70.0, 150.0])
+    cfs, sds = D.gaussian_bank([70.0, 150.0])
+    want = float(np.mean(np.exp(-0.5 * ((f_tone - cfs) / sds) ** 2)))
+    assert (env.to(torch.float64) - want).abs().max().item() / want < 1e-5
+    # two-stage brick wall == whole-row FFT on white noise at full length
+    one = ops.fft_resample(a[:4], T // 5, two_stage=False)
+    two = ops.fft_resample(a[:4], T // 5, two_stage=True)
+    assert ((one - two).abs().amax(dim=1) / one.abs().amax(dim=1)).max().item() < 3e-6
+    # notch at full length: warm-up path against the exact carry scan
+    n1 = ops.butter(a[:4], [58, 62], fs, filter_type="bandstop", mode="warm")
+    n2 = ops.butter(a[:4], [58, 62], fs, filter_type="bandstop", mode="scan")
+    assert ((n1 - n2).abs().amax(dim=1) / n2.abs().amax(dim=1)).max().item() < 1e-6
+
+
+def test_full_size_gather_and_selection_properties():
+    """BASELINE configs[2] scale: 20k events x 256 ch x 400 samples.  Gather is a bit copy (random
+    rows checked against slicing, plus a whole-tensor checksum against the analytic multiplicity);
+    F is invariant to shifting / scaling the data and to relabelling the groups."""
+    from decode_tonal_langauge_b200 import ops
+    C, T, N, L = 256, 1_440_000, 20_000, 400
+    g = torch.Generator(device="cuda").manual_seed(3)
+    src = torch.randn((C, T), generator=g, device="cuda")
+    rng = np.random.default_rng(3)
+    starts = np.sort(rng.integers(0, T - L, N)).astype(np.int64)
+    ep = ops.epoch_gather(src, starts, L)
+    assert ep.shape == (N, C, L)
+    for n in rng.integers(0, N, 50):
+        c = int(rng.integers(0, C))
+        assert torch.equal(ep[n, c], src[c, starts[n]:starts[n] + L])
+    cover = np.zeros(T + 1)
+    np.add.at(cover, starts, 1.0)
+    np.add.at(cover, starts + L, -1.0)
+    mult = torch.from_numpy(np.cumsum(cover)[:T]).cuda()
+    total = (src.to(torch.float64) * mult[None]).sum().item()
+    assert abs(ep.sum(dtype=torch.float64).item() - total) < 1e-6 * max(1.0, abs(total)) + 1e-3
+    labels = rng.integers(0, 4, N)
+    F, P = ops.anova_f(ep, labels)
+    F2, _ = ops.anova_f(ep * 3.0 + 7.0, (labels + 1) % 4)
+    ok = torch.isfinite(F)
+    assert ((F - F2).abs()[ok] / F.abs().clamp_min(1e-3)[ok]).max().item() < 1e-4
+    assert ((P >= 0) & (P <= 1)).all()
+    runs = ops.sig_runlength(P, 0.01 / L)
+    assert runs.shape == (C,) and int(runs.max()) <= L
