@@ -86,6 +86,7 @@ PROTOTYPES = {
     "ecog_rolling_workspace": (_SZ, [_I64, _I64]),
     "ecog_rolling_zscore": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _I64, _P, C.c_int, _P, _SZ, _P]),
     "ecog_epoch_gather": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _I64, _I64, _I32, _P]),
+    "ecog_channel_select": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, _I64, _I32, _P]),
     "ecog_anova_workspace": (_SZ, [_I64, _I64, _I64, _I32]),
     "ecog_anova_f": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P, _P, _I32, _P, _P, _P, _SZ, _P]),
     "ecog_sig_runlength": (C.c_int, [_P, _I64, _I64, _F64, _P, _P]),

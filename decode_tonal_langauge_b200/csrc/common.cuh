@@ -62,6 +62,11 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async8_zfill(void* smem, const void* gmem, bool valid) {
+    unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    int n = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(s), "l"(gmem), "r"(n) : "memory");
+}
 // 4-byte copy with zero fill when !valid (src-size 0)
 __device__ __forceinline__ void cp_async4_zfill(void* smem, const void* gmem, bool valid) {
     unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));

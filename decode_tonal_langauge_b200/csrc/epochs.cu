@@ -35,9 +35,49 @@ epoch_gather_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ out
     }
 }
 
+// K8b channel selection of an epoch tensor: out[n, j, :] = src[n, channels[j], :] (bit copy).
+// One warp per (event, selected channel) row, same word-wise copy as the gather.
+__global__ void __launch_bounds__(kGatherWarps * 32)
+channel_select_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ out, int64_t N, int64_t C,
+                      int64_t K, int64_t Lw, const int32_t* __restrict__ channels, bool vec) {
+    const int lane = threadIdx.x & 31;
+    const int64_t rows = N * K;
+    for (int64_t r = (int64_t)blockIdx.x * kGatherWarps + (threadIdx.x >> 5); r < rows;
+         r += (int64_t)gridDim.x * kGatherWarps) {
+        const int64_t n = r / K, j = r - n * K;
+        const uint32_t* s = src + (n * C + channels[j]) * Lw;
+        uint32_t* d = out + r * Lw;
+        if (vec) {
+            for (int64_t i = 4 * lane; i < Lw; i += 128)
+                *reinterpret_cast<uint4*>(d + i) = *reinterpret_cast<const uint4*>(s + i);
+        } else {
+            for (int64_t i = lane; i < Lw; i += 32) d[i] = s[i];
+        }
+    }
+}
+
 }  // namespace ecog
 
 using namespace ecog;
+
+extern "C" int ecog_channel_select(const void* d_src, void* d_out, int64_t N, int64_t C, int64_t L,
+                                   const int32_t* d_channels, const int32_t* h_channels, int64_t K,
+                                   int32_t elem_bytes, ecog_stream_t stream) {
+    if (elem_bytes != 4 && elem_bytes != 8) return fail(ECOG_E_VALUE, "ecog_channel_select: elem_bytes must be 4 or 8");
+    if (N < 0 || C <= 0 || L <= 0 || K < 0) return fail(ECOG_E_VALUE, "ecog_channel_select: bad shape");
+    for (int64_t j = 0; j < K; ++j)
+        if (h_channels[j] < 0 || h_channels[j] >= C)
+            return fail(ECOG_E_VALUE, "index %d is out of bounds for axis 1 with size %lld", h_channels[j], (long long)C);
+    if (N == 0 || K == 0) return ECOG_OK;
+    const int64_t Lw = L * (elem_bytes / 4);
+    const bool vec = aligned16(d_src) && aligned16(d_out) && (Lw % 4 == 0);
+    int64_t blocks = ceil_div(N * K, kGatherWarps);
+    if (blocks > (int64_t)kNumSMs * 32) blocks = (int64_t)kNumSMs * 32;
+    channel_select_kernel<<<(unsigned)blocks, kGatherWarps * 32, 0, (cudaStream_t)stream>>>(
+        (const uint32_t*)d_src, (uint32_t*)d_out, N, C, K, Lw, d_channels, vec);
+    return check_launch("channel_select");
+}
+
 
 extern "C" int ecog_epoch_gather(const void* d_src, void* d_out, int64_t C, int64_t T, int64_t ld,
                                  const int64_t* d_start, const int64_t* h_start, int64_t N, int64_t L,

@@ -141,16 +141,29 @@ fft_tile_kernel(const PassParams P) {
     float2* out = P.out + (long long)blockIdx.y * P.out_ch_stride;
     const int cw = m - c0 < W ? m - c0 : W;             // valid columns in this tile
 
-    // ---- load: row i (cw contiguous complex) -> tile[perm[i]]
-#pragma unroll 8
-    for (int idx = tid; idx < n * W; idx += kFftThreads) {
-        const int i = idx >> LOGW, c = idx & (W - 1);
-        float2 v = make_float2(0.f, 0.f);
-        if (c < cw) {
-            v = in[(long long)i * m + c0 + c];
-            if (P.conj_in) v.y = -v.y;
+    // ---- load: row i (cw contiguous complex) -> tile[perm[i]].  Asynchronous copies: the whole tile
+    // is in flight at once and no register waits on a load (one DRAM latency per tile, not one per
+    // unrolled batch).  A conjugated input goes through registers.
+    if (!P.conj_in) {
+#pragma unroll 4
+        for (int idx = tid; idx < n * W; idx += kFftThreads) {
+            const int i = idx >> LOGW, c = idx & (W - 1);
+            const bool ok = c < cw;
+            cp_async8_zfill(&tile[__ldg(&P.perm[i]) * WP + c], in + (long long)i * m + c0 + (ok ? c : 0), ok);
         }
-        tile[__ldg(&P.perm[i]) * WP + c] = v;
+        cp_async_commit();
+        cp_async_wait<0>();
+    } else {
+#pragma unroll 8
+        for (int idx = tid; idx < n * W; idx += kFftThreads) {
+            const int i = idx >> LOGW, c = idx & (W - 1);
+            float2 v = make_float2(0.f, 0.f);
+            if (c < cw) {
+                v = in[(long long)i * m + c0 + c];
+                v.y = -v.y;
+            }
+            tile[__ldg(&P.perm[i]) * WP + c] = v;
+        }
     }
     __syncthreads();
 
@@ -247,8 +260,9 @@ resample_repack_kernel(const float2* __restrict__ Z, float2* __restrict__ G, lon
     const float2 ym = make_float2(yr.x, -yr.y);
     const float2 E = make_float2(0.5f * (yk.x + ym.x), 0.5f * (yk.y + ym.y));
     const float2 O = cmulf(make_float2(0.5f * (yk.x - ym.x), 0.5f * (yk.y - ym.y)), __ldg(&twNum[k]));
-    // G = E + i O
-    G[(long long)blockIdx.y * g_stride + k] = make_float2(E.x - O.y, E.y + O.x);
+    // G = E + i O, stored CONJUGATED: the inverse runs as conj(FFT(conj(G))) and the first pass
+    // then takes its input as is (asynchronous tile copies)
+    G[(long long)blockIdx.y * g_stride + k] = make_float2(E.x - O.y, -(E.y + O.x));
 }
 
 static bool pair_ok(int ra, int rb) {
@@ -447,7 +461,7 @@ extern "C" int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_
     P.out = two ? bufI : reinterpret_cast<float2*>(d_y); P.out_ch_stride = two ? Nh : ldy / 2;
     P.n = plan->ia.n; P.m = plan->ib.n; P.perm = tb->perm_ia; P.tw = (const float2*)tb->tw_ia;
     P.tw_hi = (const float2*)tb->tw_big_i_hi; P.tw_lo = (const float2*)tb->tw_big_i_lo;
-    P.conj_in = 1; P.twiddle = two; P.transposed = 1; P.scale = 1.f; P.keep_lo = 1 << 30; P.keep_hi = 0;
+    P.conj_in = 0; P.twiddle = two; P.transposed = 1; P.scale = 1.f; P.keep_lo = 1 << 30; P.keep_hi = 0;
     ECOG_TRY(fill_axis(plan->ia, P.ax));
     if (!two) {
         // single pass: the transposed store has m == 1, so it IS natural order; finish here

@@ -511,6 +511,29 @@ def epoch_gather(src: torch.Tensor, starts: np.ndarray, length: int) -> torch.Te
     return out
 
 
+def channel_select(epochs: torch.Tensor, channels) -> torch.Tensor:
+    """out[n, j, :] = epochs[n, channels[j], :] (bit copy, 4- and 8-byte dtypes)."""
+    if not epochs.is_cuda or epochs.dim() != 3:
+        raise TypeError("expected an (events, channels, time) CUDA tensor")
+    if epochs.element_size() not in (4, 8):
+        raise TypeError(f"channel_select supports 4- and 8-byte element types, got {epochs.dtype}")
+    epochs = epochs.contiguous()
+    N, Cn, L = epochs.shape
+    ch = np.ascontiguousarray(channels, dtype=np.int64)
+    if ch.ndim != 1:
+        raise IndexError("channel indices must be one-dimensional")
+    ch = np.where(ch < 0, ch + Cn, ch).astype(np.int32)              # numpy-style negative indices
+    K = int(ch.shape[0])
+    out = torch.empty((N, K, L), dtype=epochs.dtype, device=epochs.device)
+    d_ch = torch.from_numpy(ch).to(epochs.device) if K else None
+    try:
+        nat.check(lib.ecog_channel_select(_ptr(epochs), _ptr(out), N, Cn, L, _ptr(d_ch), _hptr(ch), K,
+                                          epochs.element_size(), _stream()))
+    except ValueError as e:
+        raise IndexError(str(e))                                      # numpy raises IndexError here
+    return out
+
+
 # -------------------------------------------------------------------- K9 / K10
 def anova_f(epochs: torch.Tensor, groups: np.ndarray, extra: Optional[torch.Tensor] = None):
     """One-way ANOVA over events for every (channel, timepoint).

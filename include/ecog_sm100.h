@@ -224,6 +224,13 @@ int ecog_epoch_gather(const void* d_src, void* d_out, int64_t C, int64_t T, int6
                       const int64_t* d_start, const int64_t* h_start, int64_t N, int64_t L,
                       int32_t elem_bytes, ecog_stream_t stream);
 
+/* ------------------------------------------- K8b: channel selection of epochs
+ * replaces data_loading/sample_loading.py:77-79 (features[:, channels, :], the consumer of the
+ * channel-selection JSON): out[n, j, 0:L] = src[n, channels[j], 0:L], bit copy.            */
+int ecog_channel_select(const void* d_src, void* d_out, int64_t N, int64_t C, int64_t L,
+                        const int32_t* d_channels, const int32_t* h_channels, int64_t K,
+                        int32_t elem_bytes, ecog_stream_t stream);
+
 /* --------------------------------------------- K9/K10: ANOVA F + run length
  * replaces channel_selection/discriminative.py:172-180, channel_selection/active.py:58-76,
  *          channel_selection/utils.py:4-30,63-75 (scipy.stats.f_oneway, equal_var).

@@ -297,3 +297,39 @@ def test_full_size_gather_and_selection_properties():
     assert ((P >= 0) & (P <= 1)).all()
     runs = ops.sig_runlength(P, 0.01 / L)
     assert runs.shape == (C,) and int(runs.max()) <= L
+
+
+def test_sample_handler_matches_reference_semantics(tmp_path):
+    """ref: data_loading/sample_loading.py:34-123: channel union from the selection JSON, joint label
+    code, features[:, channels, :] -- here gathered on the device, bit exact."""
+    import json
+    from decode_tonal_langauge_b200.samples import ClassificationSampleHandler
+    from decode_tonal_langauge_b200 import ops
+    rng = np.random.default_rng(0)
+    N, C, L = 37, 19, 50
+    ecog = rng.standard_normal((N, C, L))
+    tone = rng.integers(0, 4, N)
+    syl = rng.integers(0, 2, N).astype(np.int8)
+    np.savez(tmp_path / "subject_1.npz", ecog=ecog, tone=tone, syllable=syl, ecog_sf=np.int64(400))
+    sel = {"tone_discriminative": [3, 7, 11], "syllable_discriminative": [7, 2], "active": [1]}
+    with open(tmp_path / "subject_1.json", "w") as f:
+        json.dump(sel, f)
+    p = Namespace(sample_path=str(tmp_path / "subject_1.npz"), channel_file=str(tmp_path / "subject_1.json"),
+                  targets=["tone", "syllable"], features="ecog")
+    d = ClassificationSampleHandler(p).load_data()
+    assert d["selected_channels"].tolist() == [2, 3, 7, 11]
+    assert d["features"].is_cuda and d["features"].dtype == torch.float64
+    assert np.array_equal(d["features"].cpu().numpy(), ecog[:, [2, 3, 7, 11], :])
+    assert np.array_equal(d["labels"], tone + 4 * syl.astype(int)) and d["n_classes_dict"] == {"tone": 4, "syllable": 2}
+    h = ClassificationSampleHandler(Namespace(sample_path=p.sample_path, targets="tone", features="ecog"))
+    d = h.load_data(as_numpy=True)
+    assert np.array_equal(d["features"], ecog) and d["selected_channels"].tolist() == list(range(C))
+    ds = h.prepare_torch_dataset(d["features"], d["labels"], "cuda")
+    assert ds.tensors[0].dtype == torch.float32 and ds.tensors[0].shape == (N, C, L)
+    with pytest.raises(KeyError):
+        ClassificationSampleHandler(Namespace(sample_path=p.sample_path, channel_file=p.channel_file,
+                                              targets=["nope"], features="ecog")).load_data()
+    with pytest.raises(IndexError):
+        ops.channel_select(torch.zeros((2, 3, 4), device="cuda"), [5])
+    x32 = torch.randn((5, 6, 7), device="cuda")
+    assert torch.equal(ops.channel_select(x32, [5, 0, -1]), x32[:, [5, 0, 5], :])
