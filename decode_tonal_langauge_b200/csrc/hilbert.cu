@@ -83,7 +83,7 @@ __device__ __forceinline__ void fft4096_finish(float2 (&v)[16], float2* buf, con
     for (int k1 = 0; k1 < 16; ++k1) v[k1] = cmul(v[k1], t2[k1]);
 #pragma unroll
     for (int k1 = 0; k1 < 16; ++k1) p2[17 * k1] = v[k1];
-    __syncthreads();
+    __syncwarp();                                // this exchange stays inside the half-warp that shares k0
     const float2* p3 = buf + 17 * tid;           // padi(16 tid + j) = 17 tid + j
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = p3[j];
@@ -152,7 +152,7 @@ __device__ __forceinline__ void dft16_rows(float2 (&v)[16]) {
 
 __device__ __forceinline__ float fast_sqrt(float x) {
     float r;
-    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
 
@@ -355,7 +355,12 @@ hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t 
 
     const int n0 = k1;                                   // pass-2 role of this thread: (k0, n0)
     float* yr = y + ch * ldy;
-    int flip = 0;
+    // The pass-2 -> pass-3 exchange of an inverse stays inside the 16 threads that share k0
+    // (elements 272 k0 + 17 k1 + n0): one half-warp, so a warp-level barrier orders it and
+    // every warp owns its slice of bufA.  bufB (free once SG is built) stages the two output
+    // blocks in natural order, one half each, so the CTA meets at one barrier per block.
+    float2* p2 = bufA + 272 * k0 + n0;
+    const float2* p3 = bufA + 17 * tid;
     for (int sel = 0; sel < 2; ++sel) {
         float acc[16];
 #pragma unroll
@@ -367,13 +372,10 @@ hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t 
             dft16(v);
 #pragma unroll
             for (int e = 1; e < 16; ++e) v[e] = cmul(v[e], twBs[e * 16 + n0]);
-            float2* buf = (flip & 1) ? bufB : bufA;
-            ++flip;
-            float2* p2 = buf + 272 * k0 + n0;
+            __syncwarp();                                // previous pass-3 reads of this slice are done
 #pragma unroll
             for (int e = 0; e < 16; ++e) p2[17 * e] = v[e];
-            __syncthreads();
-            const float2* p3 = buf + 17 * tid;
+            __syncwarp();
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = p3[j];
             dft16(v);
@@ -386,9 +388,7 @@ hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t 
                 for (int j = 0; j < 16; ++j) acc[j] += v[j].x;
             }
         }
-        // the buffer the NEXT transform would use was last read before the latest barrier: free
-        float* ob = reinterpret_cast<float*>((flip & 1) ? bufB : bufA);
-        ++flip;
+        float* ob = reinterpret_cast<float*>(bufB) + sel * (kN + kN / 16);
 #pragma unroll
         for (int k2 = 0; k2 < 16; ++k2) ob[nat0 + 272 * k2] = acc[k2];
         __syncthreads();

@@ -25,7 +25,9 @@ constexpr int kSosThreads = 512;
 constexpr int kSub = 16;              // samples per stage per chunk
 constexpr int kPitch = kSub + 4;      // shared row pitch in floats (conflict-free LDS.128)
 constexpr int kRing = 2;
-constexpr int kWarmRing = 3;      // warm-up kernel: three tile slots, one barrier per stage
+constexpr int kWarmRing = 5;      // warm-up kernel: tile slots (prefetch distance kWarmRing - 1), one barrier per stage
+constexpr int kWSub = 16;         // warm-up kernel: samples per stage per chunk (64 B per chunk and stage; 128 B measured no faster)
+constexpr int kWPitch = kWSub;   // no padding: the 16-byte pieces of a row are XOR-swizzled (conflict-free LDS.128)
 
 struct SosCoef {
     double c[ECOG_MAX_SECTIONS][5];   // b0 b1 b2 a1 a2
@@ -33,15 +35,24 @@ struct SosCoef {
 };
 struct SosMatrix { double m[2 * ECOG_MAX_SECTIONS][2 * ECOG_MAX_SECTIONS]; };
 
-// B1Z: every section has b1 == 0 (numerator b0 + b2 z^-2, e.g. the (1 - z^-2) sections of a
-// Butterworth band-pass): one DFMA less per section and sample.
-template <int NSEC, bool B1Z = false>
+// Numerator forms (NUM):
+//   0  general b0 b1 b2                                   5 FP64 ops per section and sample
+//   1  b1 == 0                                            4
+//   2  unit form  g * (1 + beta1 z^-1 + z^-2) per section: the gain g of the cascade is applied
+//      once to the input, sections are monic with b2 == +1 (Butterworth band-stop / low-pass /
+//      high-pass: zeros on the unit circle)               4, and one multiply per sample
+//   5  unit form with b1 == 0 and b2 == -1, the (1 - z^-2) sections of a Butterworth band-pass
+//                                                         3, and one multiply per sample
+// In the unit forms c[j][1] holds beta1 = b1 / b0; the states are those of the general form.
+template <int NSEC, int NUM = 0>
 __device__ __forceinline__ double sos_step(double u, const double (&c)[NSEC][5], double (&s)[NSEC][2]) {
+    constexpr bool B1Z = (NUM & 1) != 0;
+    constexpr int UNIT = NUM >> 1;              // 0 general, 1: b0 = 1, b2 = +1, 2: b0 = 1, b2 = -1
 #pragma unroll
     for (int j = 0; j < NSEC; ++j) {
-        const double y = fma(c[j][0], u, s[j][0]);
+        const double y = UNIT ? u + s[j][0] : fma(c[j][0], u, s[j][0]);
         s[j][0] = B1Z ? fma(-c[j][3], y, s[j][1]) : fma(-c[j][3], y, fma(c[j][1], u, s[j][1]));
-        s[j][1] = fma(-c[j][4], y, c[j][2] * u);
+        s[j][1] = UNIT == 1 ? fma(-c[j][4], y, u) : UNIT == 2 ? fma(-c[j][4], y, -u) : fma(-c[j][4], y, c[j][2] * u);
         u = y;
     }
     return u;
@@ -327,18 +338,19 @@ sos_scan_kernel(const float* __restrict__ x, int64_t C, int64_t T, int64_t ldx,
 // (few DRAM pages / TLB entries live per CTA).
 // The backward sweep cannot run in place (its warm-up reads the forward result of the
 // neighbouring chunk), so the forward result lives in the workspace.
-template <int NSEC, bool REV, bool VEC, int NT, bool B1Z>
+template <int NSEC, bool REV, bool VEC, int NT, int NUM>
 __global__ void __launch_bounds__(NT, 512 / NT)
 sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, int64_t T,
                 int64_t ldx, int64_t ldy, int L, int tail, int nChunks, int padlen, int zero_phase,
-                SosCoef coef, double* __restrict__ padbuf) {
+                SosCoef coef, double* __restrict__ padbuf, double gain) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float* tiles = reinterpret_cast<float*>(smem_raw);                                   // [kWarmRing][NT][kPitch]
-    int64_t* soff = reinterpret_cast<int64_t*>(tiles + (size_t)kWarmRing * NT * kPitch); // [NT] x offset of the chunk edge
+    float* tiles = reinterpret_cast<float*>(smem_raw);                                   // [kWarmRing][NT][kWPitch]
+    int64_t* soff = reinterpret_cast<int64_t*>(tiles + (size_t)kWarmRing * NT * kWPitch); // [NT] x offset of the chunk edge
     int64_t* doff = soff + NT;                                                           // [NT] y offset of the chunk edge
     int2* lohi = reinterpret_cast<int2*>(doff + NT);                                     // [NT] valid logical offsets
-    constexpr int PP = 4;                       // pieces per tile row: four samples each (one 16 B copy when VEC)
-    constexpr int PE = kSub / PP;
+    constexpr int PE = 4;                       // samples per piece (one 16 B copy when VEC)
+    constexpr int PP = kWSub / PE;              // pieces per tile row
+    constexpr int RPB = 32 / kWSub;             // tile rows per 128 bytes of shared memory (swizzle period)
     constexpr int NJ = PP;                      // pieces each thread moves per stage
 
     const int tid = threadIdx.x;
@@ -363,6 +375,8 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
     const int pc = tid % PP;                    // this thread moves piece pc of tile rows tid / PP + j * (NT / PP)
 
     double c[NSEC][5], s[NSEC][2];
+    // unit forms take the cascade gain on the input
+#define IN(v) ((NUM >> 1) ? gain * (v) : (v))
 #pragma unroll
     for (int j = 0; j < NSEC; ++j) {
 #pragma unroll
@@ -371,23 +385,23 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
     }
     // chunks that see the row edge get the exact start-up at the stage where the row starts
     const int64_t before = REV ? T - edge : edge;
-    const int s_inject = valid && before <= tail ? -(int)(before / kSub) : (1 << 30);
+    const int s_inject = valid && before <= tail ? -(int)(before / kWSub) : (1 << 30);
 
-    const int nStages = L / kSub;
-    const int first = -(tail / kSub);
+    const int nStages = L / kWSub;
+    const int first = -(tail / kWSub);
 
     // logical offset of the first element of piece pc in stage st, and its distance from the chunk edge
     auto issue = [&](int stage) {
         if (stage < nStages) {
-            float* tile = tiles + (size_t)((stage - first) % kWarmRing) * NT * kPitch;
-            const int u0 = !REV ? stage * kSub + PE * pc : stage * kSub + (kSub - PE) - PE * pc;
+            float* tile = tiles + (size_t)((stage - first) % kWarmRing) * NT * kWPitch;
+            const int u0 = !REV ? stage * kWSub + PE * pc : stage * kWSub + (kWSub - PE) - PE * pc;
             const int off = !REV ? u0 : -u0 - PE;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 const int r = tid / PP + j * (NT / PP);
                 const int2 lh = lohi[r];
                 const float* g = x + soff[r];
-                float* d = tile + r * kPitch + PE * pc;
+                float* d = tile + r * kWPitch + PE * (pc ^ ((r / RPB) & (PP - 1)));
                 if (VEC) {
                     const bool ok = u0 >= lh.x && u0 + PE <= lh.y;
                     cp_async16_zfill(d, ok ? g + off : g, ok);
@@ -404,12 +418,14 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
         cp_async_commit();
     };
 
-    // three tile slots, ONE barrier per stage: the barrier that publishes the results of stage st
+    // kWarmRing tile slots, ONE barrier per stage: the barrier that publishes the results of stage st
     // also publishes the tiles of stage st + 1 (every thread has waited for its own copies); the
-    // slot refilled after it (stage st + 2) was last read by the store of stage st - 1.
-    issue(first);
-    issue(first + 1);
-    cp_async_wait<1>();
+    // slot refilled after it (stage st + kWarmRing - 1) was last read by the store of stage st - 1.
+    // Four stages of loads stay in flight per CTA, so neither the copy wait nor the barrier sees
+    // DRAM latency.
+#pragma unroll
+    for (int i = 0; i < kWarmRing - 1; ++i) issue(first + i);
+    cp_async_wait<kWarmRing - 2>();
     __syncthreads();
     for (int st = first; st < nStages; ++st) {
         if (st == s_inject && zero_phase) {
@@ -422,71 +438,72 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
                 for (int j = 0; j < NSEC; ++j) { s[j][0] = coef.zi[j][0] * (double)e0; s[j][1] = coef.zi[j][1] * (double)e0; }
                 for (int i = 0; i < padlen; ++i) {
                     const float e = 2.0f * x0 - xr[padlen - i];
-                    (void)sos_step<NSEC, B1Z>((double)e, c, s);
+                    (void)sos_step<NSEC, NUM>(IN((double)e), c, s);
                 }
             } else {
                 const double* pb = padbuf + row * padlen;
                 const double y0 = pb[padlen - 1];
 #pragma unroll
                 for (int j = 0; j < NSEC; ++j) { s[j][0] = coef.zi[j][0] * y0; s[j][1] = coef.zi[j][1] * y0; }
-                for (int i = padlen - 1; i >= 0; --i) (void)sos_step<NSEC, B1Z>(pb[i], c, s);
+                for (int i = padlen - 1; i >= 0; --i) (void)sos_step<NSEC, NUM>(IN(pb[i]), c, s);
             }
         }
-        float* tile = tiles + (size_t)((st - first) % kWarmRing) * NT * kPitch;
-        float* mine = tile + tid * kPitch;
-        float4 xin[kSub / 4];
+        float* tile = tiles + (size_t)((st - first) % kWarmRing) * NT * kWPitch;
+        float* mine = tile + tid * kWPitch;
+        const int swz = (tid / RPB) & (PP - 1);
+        float4 xin[kWSub / 4];
 #pragma unroll
-        for (int v = 0; v < kSub / 4; ++v) {
+        for (int v = 0; v < kWSub / 4; ++v) {
             if (!REV) {
-                xin[v] = *reinterpret_cast<const float4*>(mine + 4 * v);
+                xin[v] = *reinterpret_cast<const float4*>(mine + 4 * (v ^ swz));
             } else {
-                float4 t4 = *reinterpret_cast<const float4*>(mine + (kSub - 4 - 4 * v));
+                float4 t4 = *reinterpret_cast<const float4*>(mine + 4 * ((PP - 1 - v) ^ swz));
                 xin[v] = make_float4(t4.w, t4.z, t4.y, t4.x);
             }
         }
         const bool write = st >= 0;
-        const int sbase = st * kSub;
-        if (sbase >= ulo && sbase + kSub <= uhi) {          // whole stage inside the row: the common case
+        const int sbase = st * kWSub;
+        if (sbase >= ulo && sbase + kWSub <= uhi) {          // whole stage inside the row: the common case
 #pragma unroll
-            for (int v = 0; v < kSub / 4; ++v) {
+            for (int v = 0; v < kWSub / 4; ++v) {
                 float4 yv;
-                yv.x = (float)sos_step<NSEC, B1Z>((double)xin[v].x, c, s);
-                yv.y = (float)sos_step<NSEC, B1Z>((double)xin[v].y, c, s);
-                yv.z = (float)sos_step<NSEC, B1Z>((double)xin[v].z, c, s);
-                yv.w = (float)sos_step<NSEC, B1Z>((double)xin[v].w, c, s);
+                yv.x = (float)sos_step<NSEC, NUM>(IN((double)xin[v].x), c, s);
+                yv.y = (float)sos_step<NSEC, NUM>(IN((double)xin[v].y), c, s);
+                yv.z = (float)sos_step<NSEC, NUM>(IN((double)xin[v].z), c, s);
+                yv.w = (float)sos_step<NSEC, NUM>(IN((double)xin[v].w), c, s);
                 if (write) {
-                    if (!REV) *reinterpret_cast<float4*>(mine + 4 * v) = yv;
-                    else *reinterpret_cast<float4*>(mine + (kSub - 4 - 4 * v)) = make_float4(yv.w, yv.z, yv.y, yv.x);
+                    if (!REV) *reinterpret_cast<float4*>(mine + 4 * (v ^ swz)) = yv;
+                    else *reinterpret_cast<float4*>(mine + 4 * ((PP - 1 - v) ^ swz)) = make_float4(yv.w, yv.z, yv.y, yv.x);
                 }
             }
         } else {                                            // outside the row / ragged chunk end: state frozen
 #pragma unroll
-            for (int v = 0; v < kSub / 4; ++v) {
+            for (int v = 0; v < kWSub / 4; ++v) {
                 const float xv[4] = {xin[v].x, xin[v].y, xin[v].z, xin[v].w};
                 float yv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int u = sbase + 4 * v + e;
-                    if (u >= ulo && u < uhi) yv[e] = (float)sos_step<NSEC, B1Z>((double)xv[e], c, s);
+                    if (u >= ulo && u < uhi) yv[e] = (float)sos_step<NSEC, NUM>(IN((double)xv[e]), c, s);
                 }
                 if (write) {
-                    if (!REV) *reinterpret_cast<float4*>(mine + 4 * v) = make_float4(yv[0], yv[1], yv[2], yv[3]);
-                    else *reinterpret_cast<float4*>(mine + (kSub - 4 - 4 * v)) = make_float4(yv[3], yv[2], yv[1], yv[0]);
+                    if (!REV) *reinterpret_cast<float4*>(mine + 4 * (v ^ swz)) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+                    else *reinterpret_cast<float4*>(mine + 4 * ((PP - 1 - v) ^ swz)) = make_float4(yv[3], yv[2], yv[1], yv[0]);
                 }
             }
         }
-        cp_async_wait<0>();                    // this thread's copies of stage st + 1 have landed
+        cp_async_wait<kWarmRing - 3>();        // this thread's copies of stage st + 1 have landed
         __syncthreads();
-        issue(st + 2);
+        issue(st + kWarmRing - 1);
         if (write) {
-            const int u0 = !REV ? sbase + PE * pc : sbase + (kSub - PE) - PE * pc;
+            const int u0 = !REV ? sbase + PE * pc : sbase + (kWSub - PE) - PE * pc;
             const int off = !REV ? u0 : -u0 - PE;
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
                 const int r = tid / PP + j * (NT / PP);
                 const int hi = lohi[r].y;
                 float* g = y + doff[r] + off;
-                const float4 v4 = *reinterpret_cast<const float4*>(tile + r * kPitch + PE * pc);
+                const float4 v4 = *reinterpret_cast<const float4*>(tile + r * kWPitch + PE * (pc ^ ((r / RPB) & (PP - 1))));
                 if (VEC) {
                     if (u0 + PE <= hi) *reinterpret_cast<float4*>(g) = v4;
                 } else {
@@ -510,43 +527,61 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
         double* pb = padbuf + row * padlen;
         for (int i = 0; i < padlen; ++i) {
             const float e = 2.0f * xe - xr[T - 2 - i];
-            pb[i] = sos_step<NSEC, B1Z>((double)e, c, s);
+            pb[i] = sos_step<NSEC, NUM>(IN((double)e), c, s);
         }
     }
 }
+#undef IN
 
-template <int NSEC, bool REV, int NT, bool B1Z>
+template <int NSEC, bool REV, int NT, int NUM>
 static int launch_warm(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
-                       const ecog_sos_plan& p, int nChunks, const SosCoef& coef, double* padbuf, bool vec,
+                       const ecog_sos_plan& p, int nChunks, const SosCoef& coef, double gain, double* padbuf, bool vec,
                        cudaStream_t st) {
-    const size_t smem = ((size_t)kWarmRing * NT * kPitch) * sizeof(float) + (size_t)NT * (2 * sizeof(int64_t) + sizeof(int2));
+    const size_t smem = ((size_t)kWarmRing * NT * kWPitch) * sizeof(float) + (size_t)NT * (2 * sizeof(int64_t) + sizeof(int2));
     const unsigned grid = (unsigned)ceil_div(C * nChunks, NT);
     if (vec) {
-        auto k = sos_warm_kernel<NSEC, REV, true, NT, B1Z>;
+        auto k = sos_warm_kernel<NSEC, REV, true, NT, NUM>;
         ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, NT, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, p.zero_phase, coef, padbuf);
+        k<<<grid, NT, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, p.zero_phase, coef, padbuf, gain);
     } else {
-        auto k = sos_warm_kernel<NSEC, REV, false, NT, B1Z>;
+        auto k = sos_warm_kernel<NSEC, REV, false, NT, NUM>;
         ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, NT, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, p.zero_phase, coef, padbuf);
+        k<<<grid, NT, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, p.zero_phase, coef, padbuf, gain);
     }
     return check_launch(REV ? "sos_warm_bwd" : "sos_warm_fwd");
 }
 
 template <int NSEC>
 static int run_sos_warm(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
-                        const ecog_sos_plan& p, const SosCoef& coef, float* tmp, int64_t ldt, double* padbuf,
+                        const ecog_sos_plan& p, const SosCoef& coef_in, float* tmp, int64_t ldt, double* padbuf,
                         cudaStream_t st) {
     const int nChunks = (int)ceil_div(T, p.chunk);
     float* mid = p.zero_phase ? tmp : y;
     const int64_t ldm = p.zero_phase ? ldt : ldy;
     const bool vec = aligned16(x) && aligned16(y) && aligned16(mid) && T % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldm % 4 == 0;
     const bool wide = p.threads >= 512;
-    bool b1z = true;
-    for (int j = 0; j < NSEC; ++j) b1z = b1z && coef.c[j][1] == 0.0;
-#define ECOG_WARM(REVV, NTT, Y_IN, Y_OUT, LD_IN, LD_OUT)                                                                   \
-    (b1z ? launch_warm<NSEC, REVV, NTT, true>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, padbuf, vec, st)        \
-         : launch_warm<NSEC, REVV, NTT, false>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, padbuf, vec, st))
+    // numerator form: unit sections g (1 + beta1 z^-1 +- z^-2) with the gain on section 0 only
+    SosCoef coef = coef_in;
+    bool b1z = true, unit_p = true, unit_m = true;
+    for (int j = 0; j < NSEC; ++j) {
+        const double b0 = coef.c[j][0], b2 = coef.c[j][2];
+        b1z = b1z && coef.c[j][1] == 0.0;
+        const bool b0ok = b0 != 0.0 && (j == 0 || b0 == 1.0);
+        unit_p = unit_p && b0ok && b2 == b0;
+        unit_m = unit_m && b0ok && b2 == -b0;
+    }
+    int num = 0;
+    double gain = 1.0;
+    if (unit_p) num = 2;
+    else if (unit_m && b1z) num = 5;
+    if (num) {
+        gain = coef.c[0][0];
+        coef.c[0][1] /= gain;
+    }
+#define ECOG_WARM(REVV, NTT, Y_IN, Y_OUT, LD_IN, LD_OUT)                                                                         \
+    (num == 2 ? launch_warm<NSEC, REVV, NTT, 2>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, vec, st)       \
+     : num == 5 ? launch_warm<NSEC, REVV, NTT, 5>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, vec, st)     \
+                : launch_warm<NSEC, REVV, NTT, 0>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, vec, st))
     if (wide) ECOG_TRY(ECOG_WARM(false, 512, x, mid, ldx, ldm));
     else      ECOG_TRY(ECOG_WARM(false, 256, x, mid, ldx, ldm));
     if (!p.zero_phase) return ECOG_OK;

@@ -217,7 +217,7 @@ def chunk_matrix(sos, chunk: int) -> np.ndarray:
 
 
 def response_tail(sos, limit: int, eps: float = 1e-18) -> int:
-    """Smallest multiple of 16 samples after which the zero-input response is < eps (<= limit)."""
+    """Smallest multiple of SUB samples after which the zero-input response is < eps (<= limit)."""
     with mp.workdps(30):
         A, _, _, _ = cascade_state_space(sos)
         An = np.array([[float(A[i, j]) for j in range(A.cols)] for i in range(A.rows)])
@@ -259,7 +259,7 @@ def choose_warm_chunk(C: int, T: int, threads_per_sm: int = 512) -> int:
 
 
 def warm_tail(design: "SosDesign", limit: int) -> int:
-    """Warm-up length (multiple of 16) after which max|A^n| < WARM_EPS, or -1 if > limit."""
+    """Warm-up length (multiple of SUB) after which max|A^n| < WARM_EPS, or -1 if > limit."""
     t = _warm_tail(design.sos.tobytes(), design.nsec, int(limit))
     return t
 
@@ -303,6 +303,20 @@ def _butter_design(order: int, freqs: Tuple[float, ...], fs: float, btype: str, 
         ideal = b[0] * np.poly(np.r_[np.ones(order), -np.ones(order)])
         if np.max(np.abs(ideal - b)) <= 4e-16 * np.max(np.abs(b)) and sos.shape[0] == order:
             sos[:, :3] = [1.0, 0.0, -1.0]
+            sos[0, :3] *= b[0]
+    elif btype in ("bandstop", "lowpass", "highpass") and sos.shape[0] * 2 == len(b) - 1:
+        # likewise b[0] (1 + beta z^-1 + z^-2)^nsec with the zeros ON the unit circle (beta = -2 cos w0
+        # for a band-stop, +2 / -2 for low- / high-pass).  The roots of the ROUNDED polynomial are a
+        # ring of radius ~(1e-16)^(1/nsec) around them; the unit-circle sections reproduce the
+        # reference's coefficients to rounding and cost one FP64 operation less per section
+        # (b2 == b0: csrc/sosfilt.cu, numerator form 2).
+        nsec = sos.shape[0]
+        beta = b[1] / (nsec * b[0])
+        ideal = np.array([1.0])
+        for _ in range(nsec):
+            ideal = np.convolve(ideal, [1.0, beta, 1.0])
+        if np.max(np.abs(b[0] * ideal - b)) <= 2e-15 * np.max(np.abs(b)):
+            sos[:, :3] = [1.0, beta, 1.0]
             sos[0, :3] *= b[0]
     zi_direct = sp_signal.lfilter_zi(b, a)          # the installed scipy's own arithmetic
     zi = zi_to_cascade(b, a, sos, zi_direct)

@@ -1,2 +1,5 @@
 cd $GRAFT_REPO_ROOT
-python -m pytest tests -x -q -m gpu > gpurun_out/t18.log 2>&1; tail -4 gpurun_out/t18.log
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/t26.log 2>&1; tail -3 gpurun_out/t26.log
+timeout 300 python scripts/prof_ops.py car,bandpass,notch,bandpass,notch 256 7200000 3 > gpurun_out/ops26.log 2>&1
+cat gpurun_out/ops26.log
