@@ -16,7 +16,7 @@ ECOG_E_VALUE = -1
 ECOG_E_CUDA = -2
 ECOG_E_WORKSPACE = -3
 ECOG_E_UNSUPPORTED = -4
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_SECTIONS = 8
 SOS_SCAN = 0
 SOS_WARMUP = 1
@@ -43,12 +43,13 @@ class ResampleTables(C.Structure):
                 ("tw_big_f_hi", C.c_void_p), ("tw_big_f_lo", C.c_void_p),
                 ("tw_big_i_hi", C.c_void_p), ("tw_big_i_lo", C.c_void_p),
                 ("big_f_split", C.c_int32), ("big_i_split", C.c_int32),
-                ("tw_T", C.c_void_p), ("tw_num", C.c_void_p), ("bin_gain", C.c_void_p)]
+                ("tw_T", C.c_void_p), ("tw_num", C.c_void_p), ("bin_gain", C.c_void_p),
+                ("tw_q_f", C.c_void_p), ("tw_q_i", C.c_void_p)]
 
 
 class FftTables(C.Structure):
     _fields_ = [("perm_a", C.c_void_p), ("perm_b", C.c_void_p), ("tw_a", C.c_void_p), ("tw_b", C.c_void_p),
-                ("tw_big_hi", C.c_void_p), ("tw_big_lo", C.c_void_p)]
+                ("tw_big_hi", C.c_void_p), ("tw_big_lo", C.c_void_p), ("tw_q", C.c_void_p)]
 
 
 _P = C.c_void_p

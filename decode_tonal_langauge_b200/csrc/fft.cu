@@ -20,7 +20,7 @@
 
 namespace ecog {
 
-constexpr int kFftThreads = 256;
+constexpr int kFftThreads = 384;   // two CTAs per SM; tile + root table in shared memory
 constexpr int kBigShift = 12;     // two-level twiddle split: e = hi * 4096 + lo
 
 // One shared-memory sweep = one or two fused DIT stages done in registers.
@@ -41,7 +41,9 @@ struct PassParams {
     const float2* tw;
     const float2* tw_hi;
     const float2* tw_lo;
+    const double2* tw_q;                     // W_N^q, q < n, float64 (four-step twiddle base)
     int conj_in, twiddle, transposed, conj_out;
+    int tw_shared;                           // root table staged in shared memory (it fits beside the tile)
     float scale;
     int keep_lo, keep_hi;                    // non-transposed store keeps rows q <= keep_lo or q >= keep_hi
     AxisDev ax;
@@ -103,7 +105,7 @@ __device__ __forceinline__ void super_bfly(float2* col, int g, int j, int lp, co
     if (j) {
 #pragma unroll
         for (int qa = 1; qa < RA; ++qa) {
-            const float2 w = __ldg(&tw[j * qa * tws_a]);
+            const float2 w = tw[j * qa * tws_a];
 #pragma unroll
             for (int qb = 0; qb < RB; ++qb) a[qa * RB + qb] = cmulf(a[qa * RB + qb], w);
         }
@@ -117,7 +119,7 @@ __device__ __forceinline__ void super_bfly(float2* col, int g, int j, int lp, co
             if (jp) {
 #pragma unroll
                 for (int qb = 1; qb < RB; ++qb)
-                    a[pa * RB + qb] = cmulf(a[pa * RB + qb], __ldg(&tw[jp * qb * tws_b]));
+                    a[pa * RB + qb] = cmulf(a[pa * RB + qb], tw[jp * qb * tws_b]);
             }
             bfly<RB, 1>(a + pa * RB);                                  // over qb, stride 1
         }
@@ -129,13 +131,17 @@ __device__ __forceinline__ void super_bfly(float2* col, int g, int j, int lp, co
 }
 
 template <int W>
-__global__ void __launch_bounds__(kFftThreads, 3)
+__global__ void __launch_bounds__(kFftThreads, 2)
 fft_tile_kernel(const PassParams P) {
     constexpr int WP = W + 1;                           // padded pitch (float2)
     constexpr int LOGW = W == 8 ? 3 : 2;
-    extern __shared__ __align__(16) float2 tile[];      // [n][WP]
+    extern __shared__ __align__(16) float2 tile[];      // [n][WP] | roots of unity [n]
     const int tid = threadIdx.x;
     const int n = P.n, m = P.m;
+    // W_n^k: the sweeps read their twiddles from shared memory (the L1 left beside two resident
+    // tiles is too small to keep the table), or from global memory for axes too long for that
+    const float2* tws = P.tw_shared ? tile + (size_t)n * WP : P.tw;
+    float2* tws_w = tile + (size_t)n * WP;
     const int c0 = blockIdx.x * W;
     const float2* in = P.in + (long long)blockIdx.y * P.in_ch_stride;
     float2* out = P.out + (long long)blockIdx.y * P.out_ch_stride;
@@ -145,15 +151,17 @@ fft_tile_kernel(const PassParams P) {
     // is in flight at once and no register waits on a load (one DRAM latency per tile, not one per
     // unrolled batch).  A conjugated input goes through registers.
     if (!P.conj_in) {
-#pragma unroll 4
+#pragma unroll 8
         for (int idx = tid; idx < n * W; idx += kFftThreads) {
             const int i = idx >> LOGW, c = idx & (W - 1);
             const bool ok = c < cw;
             cp_async8_zfill(&tile[__ldg(&P.perm[i]) * WP + c], in + (long long)i * m + c0 + (ok ? c : 0), ok);
         }
         cp_async_commit();
+        if (P.tw_shared) for (int k = tid; k < n; k += kFftThreads) tws_w[k] = __ldg(&P.tw[k]);
         cp_async_wait<0>();
     } else {
+        if (P.tw_shared) for (int k = tid; k < n; k += kFftThreads) tws_w[k] = __ldg(&P.tw[k]);
 #pragma unroll 8
         for (int idx = tid; idx < n * W; idx += kFftThreads) {
             const int i = idx >> LOGW, c = idx & (W - 1);
@@ -181,19 +189,19 @@ fft_tile_kernel(const PassParams P) {
             const int j = b - g * lp;
             float2* col = tile + c;
             switch (code) {
-                case 4 * 8 + 4: super_bfly<4, 4, WP>(col, g, j, lp, P.tw, ta, tb); break;
-                case 4 * 8 + 2: super_bfly<4, 2, WP>(col, g, j, lp, P.tw, ta, tb); break;
-                case 4 * 8 + 3: super_bfly<4, 3, WP>(col, g, j, lp, P.tw, ta, tb); break;
-                case 4 * 8 + 5: super_bfly<4, 5, WP>(col, g, j, lp, P.tw, ta, tb); break;
-                case 2 * 8 + 3: super_bfly<2, 3, WP>(col, g, j, lp, P.tw, ta, tb); break;
-                case 2 * 8 + 5: super_bfly<2, 5, WP>(col, g, j, lp, P.tw, ta, tb); break;
-                case 3 * 8 + 3: super_bfly<3, 3, WP>(col, g, j, lp, P.tw, ta, tb); break;
-                case 3 * 8 + 5: super_bfly<3, 5, WP>(col, g, j, lp, P.tw, ta, tb); break;
-                case 5 * 8 + 5: super_bfly<5, 5, WP>(col, g, j, lp, P.tw, ta, tb); break;
-                case 2 * 8 + 1: super_bfly<2, 1, WP>(col, g, j, lp, P.tw, ta, tb); break;
-                case 3 * 8 + 1: super_bfly<3, 1, WP>(col, g, j, lp, P.tw, ta, tb); break;
-                case 4 * 8 + 1: super_bfly<4, 1, WP>(col, g, j, lp, P.tw, ta, tb); break;
-                default:        super_bfly<5, 1, WP>(col, g, j, lp, P.tw, ta, tb); break;
+                case 4 * 8 + 4: super_bfly<4, 4, WP>(col, g, j, lp, tws, ta, tb); break;
+                case 4 * 8 + 2: super_bfly<4, 2, WP>(col, g, j, lp, tws, ta, tb); break;
+                case 4 * 8 + 3: super_bfly<4, 3, WP>(col, g, j, lp, tws, ta, tb); break;
+                case 4 * 8 + 5: super_bfly<4, 5, WP>(col, g, j, lp, tws, ta, tb); break;
+                case 2 * 8 + 3: super_bfly<2, 3, WP>(col, g, j, lp, tws, ta, tb); break;
+                case 2 * 8 + 5: super_bfly<2, 5, WP>(col, g, j, lp, tws, ta, tb); break;
+                case 3 * 8 + 3: super_bfly<3, 3, WP>(col, g, j, lp, tws, ta, tb); break;
+                case 3 * 8 + 5: super_bfly<3, 5, WP>(col, g, j, lp, tws, ta, tb); break;
+                case 5 * 8 + 5: super_bfly<5, 5, WP>(col, g, j, lp, tws, ta, tb); break;
+                case 2 * 8 + 1: super_bfly<2, 1, WP>(col, g, j, lp, tws, ta, tb); break;
+                case 3 * 8 + 1: super_bfly<3, 1, WP>(col, g, j, lp, tws, ta, tb); break;
+                case 4 * 8 + 1: super_bfly<4, 1, WP>(col, g, j, lp, tws, ta, tb); break;
+                default:        super_bfly<5, 1, WP>(col, g, j, lp, tws, ta, tb); break;
             }
         }
         __syncthreads();
@@ -201,19 +209,31 @@ fft_tile_kernel(const PassParams P) {
 
     // ---- store
     if (P.transposed) {
-        // out[(c0 + c) * n + q]: contiguous along q; the odd pitch keeps the shared reads conflict free
-        for (int c = 0; c < cw; ++c) {
-            const long long col = c0 + c;
-            for (int q = tid; q < n; q += kFftThreads) {
-                float2 v = tile[q * WP + c];
-                if (P.twiddle) {
-                    const long long e = (long long)q * col;              // < N
-                    const float2 wh = __ldg(&P.tw_hi[e >> kBigShift]);
-                    const float2 wl = __ldg(&P.tw_lo[e & ((1 << kBigShift) - 1)]);
-                    v = cmulf(v, cmulf(wh, wl));
+        // out[(c0 + c) * n + q]: one thread per q walks the W columns of its tile row (pitch WP: the
+        // 64-bit shared reads of consecutive q are conflict free), stores are contiguous along q.
+        // Four-step twiddle W_N^{q (c0 + c)} = W_N^{q c0} (W_N^q)^c: ONE two-level table look-up per
+        // row and tile, the column powers run in float64 from the float64 root W_N^q.
+        for (int q = tid; q < n; q += kFftThreads) {
+            float2 v[W];
+#pragma unroll
+            for (int c = 0; c < W; ++c) v[c] = tile[q * WP + c];
+            if (P.twiddle) {
+                const long long e = (long long)q * c0;                   // < N
+                const float2 wh = __ldg(&P.tw_hi[e >> kBigShift]);
+                const float2 wl = __ldg(&P.tw_lo[e & ((1 << kBigShift) - 1)]);
+                const double2 w1 = __ldg(&P.tw_q[q]);
+                const float2 w0 = cmulf(wh, wl);
+                double2 wp = w1;
+                v[0] = cmulf(v[0], w0);
+#pragma unroll
+                for (int c = 1; c < W; ++c) {
+                    v[c] = cmulf(v[c], cmulf(w0, make_float2((float)wp.x, (float)wp.y)));
+                    wp = make_double2(fma(wp.x, w1.x, -wp.y * w1.y), fma(wp.x, w1.y, wp.y * w1.x));
                 }
-                out[col * n + q] = v;
             }
+#pragma unroll
+            for (int c = 0; c < W; ++c)
+                if (c < cw) out[(long long)(c0 + c) * n + q] = v[c];
         }
     } else {
 #pragma unroll 4
@@ -303,17 +323,23 @@ static int fill_axis(const ecog_fft_axis& a, AxisDev& d) {
 }
 
 static int launch_pass(PassParams& P, int64_t C, cudaStream_t st, const char* what) {
-    // 8-column tiles (64-byte segments) when two CTAs still fit an SM, else 4-column tiles
-    const size_t smem8 = (size_t)P.n * 9 * sizeof(float2), smem4 = (size_t)P.n * 5 * sizeof(float2);
-    const bool use8 = smem8 <= 100 * 1024 || smem4 > 110 * 1024 ? smem8 <= 220 * 1024 : false;
+    // 8-column tiles (64-byte segments) when two CTAs still fit an SM, else 4-column tiles;
+    // shared memory = padded tile + the axis' root table (when that still fits)
+    const size_t tw_bytes = (size_t)P.n * sizeof(float2);
+    const size_t tile8 = (size_t)P.n * 9 * sizeof(float2), tile4 = (size_t)P.n * 5 * sizeof(float2);
+    const size_t two = 110 * 1024, one = 220 * 1024;
+    const bool use8 = tile8 + tw_bytes <= two || (tile4 + tw_bytes > two && tile8 + tw_bytes <= one);
+    const size_t tile_bytes = use8 ? tile8 : tile4;
+    P.tw_shared = tile_bytes + tw_bytes <= one ? 1 : 0;
+    const size_t smem = tile_bytes + (P.tw_shared ? tw_bytes : 0);
     if (use8) {
-        ECOG_CUDA(cudaFuncSetAttribute(fft_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
+        ECOG_CUDA(cudaFuncSetAttribute(fft_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)ceil_div(P.m, 8), (unsigned)C);
-        fft_tile_kernel<8><<<grid, kFftThreads, smem8, st>>>(P);
+        fft_tile_kernel<8><<<grid, kFftThreads, smem, st>>>(P);
     } else {
-        ECOG_CUDA(cudaFuncSetAttribute(fft_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+        ECOG_CUDA(cudaFuncSetAttribute(fft_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((unsigned)ceil_div(P.m, 4), (unsigned)C);
-        fft_tile_kernel<4><<<grid, kFftThreads, smem4, st>>>(P);
+        fft_tile_kernel<4><<<grid, kFftThreads, smem, st>>>(P);
     }
     return check_launch(what);
 }
@@ -367,6 +393,7 @@ static int run_c2c(const float2* in, float2* out, int64_t C, int64_t ld_in, int6
     P.in = in; P.in_ch_stride = ld_in;
     P.n = fa.n; P.m = fb.n; P.perm = tb->perm_a; P.tw = (const float2*)tb->tw_a;
     P.tw_hi = (const float2*)tb->tw_big_hi; P.tw_lo = (const float2*)tb->tw_big_lo;
+    P.tw_q = (const double2*)tb->tw_q;
     P.conj_in = inverse ? 1 : 0; P.scale = 1.f; P.keep_lo = 1 << 30; P.keep_hi = 0;
     ECOG_TRY(fill_axis(fa, P.ax));
     if (fb.n == 1) {     // one pass: natural-order store, finish here
@@ -431,6 +458,7 @@ extern "C" int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_
     P.out = plan->fb.n > 1 ? bufA : bufZ; P.out_ch_stride = N;
     P.n = plan->fa.n; P.m = plan->fb.n; P.perm = tb->perm_fa; P.tw = (const float2*)tb->tw_fa;
     P.tw_hi = (const float2*)tb->tw_big_f_hi; P.tw_lo = (const float2*)tb->tw_big_f_lo;
+    P.tw_q = (const double2*)tb->tw_q_f;
     P.twiddle = plan->fb.n > 1; P.transposed = 1; P.scale = 1.f; P.keep_lo = 1 << 30; P.keep_hi = 0;
     ECOG_TRY(fill_axis(plan->fa, P.ax));
     ECOG_TRY(launch_pass(P, C, st, "fft_fwd_a"));
@@ -461,6 +489,7 @@ extern "C" int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_
     P.out = two ? bufI : reinterpret_cast<float2*>(d_y); P.out_ch_stride = two ? Nh : ldy / 2;
     P.n = plan->ia.n; P.m = plan->ib.n; P.perm = tb->perm_ia; P.tw = (const float2*)tb->tw_ia;
     P.tw_hi = (const float2*)tb->tw_big_i_hi; P.tw_lo = (const float2*)tb->tw_big_i_lo;
+    P.tw_q = (const double2*)tb->tw_q_i;
     P.conj_in = 0; P.twiddle = two; P.transposed = 1; P.scale = 1.f; P.keep_lo = 1 << 30; P.keep_hi = 0;
     ECOG_TRY(fill_axis(plan->ia, P.ax));
     if (!two) {

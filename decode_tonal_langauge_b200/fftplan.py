@@ -103,6 +103,7 @@ class BigPlan:
     b: AxisPlan             # second pass, length n_b
     tw_hi: np.ndarray       # float32 (ceil(N / BIG_SPLIT), 2): W_N^{hi * BIG_SPLIT}
     tw_lo: np.ndarray       # float32 (BIG_SPLIT, 2):          W_N^{lo}
+    tw_q: np.ndarray        # float64 (n_a, 2):                W_N^q (base of the column powers)
 
 
 def big_plan(N: int, max_axis: int = MAX_AXIS) -> BigPlan:
@@ -110,7 +111,9 @@ def big_plan(N: int, max_axis: int = MAX_AXIS) -> BigPlan:
     hi = np.arange(-(-N // BIG_SPLIT), dtype=np.float64) * BIG_SPLIT
     lo = np.arange(BIG_SPLIT, dtype=np.float64)
     f = lambda e: np.stack([np.cos(-2 * np.pi * e / N), np.sin(-2 * np.pi * e / N)], axis=1).astype(np.float32)
-    return BigPlan(N, axis_plan(na), axis_plan(nb), f(hi), f(lo))
+    q = np.arange(na, dtype=np.float64)
+    tw_q = np.stack([np.cos(-2 * np.pi * q / N), np.sin(-2 * np.pi * q / N)], axis=1)
+    return BigPlan(N, axis_plan(na), axis_plan(nb), f(hi), f(lo), np.ascontiguousarray(tw_q))
 
 
 @dataclass(frozen=True)

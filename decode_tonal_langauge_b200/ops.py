@@ -371,7 +371,7 @@ def _fft_resample(x: torch.Tensor, num: int, bin_gain: Optional[np.ndarray], gai
                       ("perm_ib", rp.inv.b.perm), ("tw_fa", rp.fwd.a.tw), ("tw_fb", rp.fwd.b.tw),
                       ("tw_ia", rp.inv.a.tw), ("tw_ib", rp.inv.b.tw), ("tw_big_f_hi", rp.fwd.tw_hi),
                       ("tw_big_f_lo", rp.fwd.tw_lo), ("tw_big_i_hi", rp.inv.tw_hi), ("tw_big_i_lo", rp.inv.tw_lo),
-                      ("tw_T", rp.tw_T), ("tw_num", rp.tw_num)):
+                      ("tw_T", rp.tw_T), ("tw_num", rp.tw_num), ("tw_q_f", rp.fwd.tw_q), ("tw_q_i", rp.inv.tw_q)):
         dt = t(name, arr)
         keep.append(dt)
         setattr(tables, name, dt.data_ptr())
@@ -398,8 +398,8 @@ def _fft_tables(bp: FP.BigPlan, key, dev):
     t = lambda name, arr: _dev_table(key + (name,), lambda: arr, dev)
     tb = nat.FftTables()
     keep = [t("perm_a", bp.a.perm), t("perm_b", bp.b.perm), t("tw_a", bp.a.tw), t("tw_b", bp.b.tw),
-            t("tw_hi", bp.tw_hi), t("tw_lo", bp.tw_lo)]
-    tb.perm_a, tb.perm_b, tb.tw_a, tb.tw_b, tb.tw_big_hi, tb.tw_big_lo = [k.data_ptr() for k in keep]
+            t("tw_hi", bp.tw_hi), t("tw_lo", bp.tw_lo), t("tw_q", bp.tw_q)]
+    tb.perm_a, tb.perm_b, tb.tw_a, tb.tw_b, tb.tw_big_hi, tb.tw_big_lo, tb.tw_q = [k.data_ptr() for k in keep]
     return tb, keep
 
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ECOG_ABI_VERSION 3
+#define ECOG_ABI_VERSION 4
 
 #define ECOG_OK 0
 #define ECOG_E_VALUE (-1)     /* bad argument (reference raises ValueError)          */
@@ -146,6 +146,8 @@ typedef struct {
     const float *tw_T, *tw_num;
     const float *bin_gain;   /* optional (NULL = none): num/2 + 1 per-bin gains applied to the kept
                                 spectrum, i.e. 1 / H1[k] of the FIR pre-decimator (ecog_fir_decimate) */
+    const double *tw_q_f, *tw_q_i;   /* double2 W_N^q, q < fa.n (resp. W_N'^q, q < ia.n): float64 base of
+                                        the column powers of the four-step twiddle                      */
 } ecog_resample_tables;
 size_t ecog_resample_workspace(const ecog_resample_plan* plan, int64_t C);
 int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_t ldx, int64_t ldy,
@@ -168,6 +170,7 @@ typedef struct {
     const int32_t *perm_a, *perm_b;      /* digit reversal per axis                           */
     const float *tw_a, *tw_b;            /* W_n^k per axis                                    */
     const float *tw_big_hi, *tw_big_lo;  /* four-step twiddles, two-level table (split 4096)  */
+    const double *tw_q;                  /* double2 W_N^q, q < fa.n                           */
 } ecog_fft_tables;
 size_t ecog_fft_c2c_workspace(const ecog_fft_axis* fa, const ecog_fft_axis* fb, int64_t C);
 int ecog_fft_c2c(const float* d_in, float* d_out, int64_t C, int64_t ld_in, int64_t ld_out,
