@@ -156,7 +156,7 @@ __device__ __forceinline__ float fast_sqrt(float x) {
     return r;
 }
 
-struct BandShift { int s[64]; };
+struct BandShift { int s[64]; int nz[64]; };   // spectral shift and non-zero 16-bin groups per band
 
 template <int CNT>
 __global__ void __launch_bounds__(kHT, 2)
@@ -303,17 +303,26 @@ __device__ __forceinline__ void tw_bfly1(float2 a, float2 b, float2 wb, float2& 
     t1 = make_float2(fmaf(2.f, a.x, -t0.x), fmaf(2.f, a.y, -t0.y));
 }
 
-// forward 16-point DFT of v[i] * w[i] (W0ONE: w[0] == 1), natural order in and out: the input
-// twiddles ride in the first butterfly layer
-template <bool W0ONE>
+// forward 16-point DFT of v[i] * w[i], natural order in and out: the input twiddles ride in the
+// first butterfly layer.  W0ONE: w[0] == 1.  NZ: inputs v[NZ..15] are zero (8 <= NZ <= 16) and are
+// neither read nor multiplied.
+template <bool W0ONE, int NZ>
 __device__ __forceinline__ void dft16_tw(float2 (&v)[16], const float2 (&w)[16]) {
     const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         float2 t0, t1, t2, t3;
-        if (W0ONE && m == 0) tw_bfly1(v[0], v[8], w[8], t0, t1);
-        else tw_bfly(v[m], w[m], v[m + 8], w[m + 8], t0, t1);
-        tw_bfly(v[m + 4], w[m + 4], v[m + 12], w[m + 12], t2, t3);
+        if (m + 8 < NZ) {
+            if (W0ONE && m == 0) tw_bfly1(v[0], v[8], w[8], t0, t1);
+            else tw_bfly(v[m], w[m], v[m + 8], w[m + 8], t0, t1);
+        } else {
+            t0 = t1 = (W0ONE && m == 0) ? v[0] : cmul(v[m], w[m]);
+        }
+        if (m + 12 < NZ) {
+            tw_bfly(v[m + 4], w[m + 4], v[m + 12], w[m + 12], t2, t3);
+        } else {
+            t2 = t3 = cmul(v[m + 4], w[m + 4]);
+        }
         t3 = mul_mi(t3);
         v[m] = cadd(t0, t2); v[m + 8] = csub(t0, t2); v[m + 4] = cadd(t1, t3); v[m + 12] = csub(t1, t3);
     }
@@ -332,6 +341,20 @@ __device__ __forceinline__ void dft16_tw(float2 (&v)[16], const float2 (&w)[16])
     for (int p = 0; p < 4; ++p)
 #pragma unroll
         for (int r = p + 1; r < 4; ++r) { float2 t = v[4 * p + r]; v[4 * p + r] = v[4 * r + p]; v[4 * r + p] = t; }
+}
+
+// pass 2 of an inverse whose gained band spectrum has NZ * 16 non-zero bins: thread (k0, n0) reads
+// SG[n0][n1 < NZ] (128-bit loads) and transforms over n1 with W_256^{n1 k0} W_4096^{n0 k0} folded in
+template <int NZ>
+__device__ __forceinline__ void inverse_pass2(float2 (&v)[16], const float2* __restrict__ sgrow, const float2 (&twA)[16]) {
+    const float4* sg = reinterpret_cast<const float4*>(sgrow);
+#pragma unroll
+    for (int i = 0; i < (NZ + 1) / 2; ++i) {
+        const float4 q = sg[i];
+        v[2 * i] = make_float2(q.x, q.y);
+        v[2 * i + 1] = make_float2(q.z, q.w);
+    }
+    dft16_tw<false, NZ>(v, twA);
 }
 
 constexpr int kP18 = 18;                                  // pitch (float2) of 16-entry rows read with LDS.128
@@ -419,14 +442,16 @@ hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t 
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = 0.f;
         for (int band = 0; band < nb; ++band) {
-            const float4* sg = reinterpret_cast<const float4*>(SG + (sel * kFastBands + band) * kSgBand + n0 * kP18);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 q = sg[i];
-                v[2 * i] = make_float2(q.x, q.y);
-                v[2 * i + 1] = make_float2(q.z, q.w);
+            const float2* sgrow = SG + (sel * kFastBands + band) * kSgBand + n0 * kP18;
+            switch (shift.nz[band]) {                    // uniform: bins >= 16 nz of this band's table are zero
+                case 8: inverse_pass2<8>(v, sgrow, twA); break;
+                case 9: inverse_pass2<9>(v, sgrow, twA); break;
+                case 10: inverse_pass2<10>(v, sgrow, twA); break;
+                case 11: inverse_pass2<11>(v, sgrow, twA); break;
+                case 12: inverse_pass2<12>(v, sgrow, twA); break;
+                case 13: inverse_pass2<13>(v, sgrow, twA); break;
+                default: inverse_pass2<16>(v, sgrow, twA); break;
             }
-            dft16_tw<false>(v, twA);
             __syncwarp();                                // previous pass-3 reads of this slice are done
 #pragma unroll
             for (int e = 0; e < 16; ++e) p2[kP18 * e] = v[e];
@@ -440,7 +465,7 @@ hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t 
                 wb[2 * i] = make_float2(t.x, t.y);
                 wb[2 * i + 1] = make_float2(t.z, t.w);
             }
-            dft16_tw<true>(v, wb);
+            dft16_tw<true, 16>(v, wb);
             // v[k2] = conj(z[t]) (times a unit phasor when shifted), t = k0 + 16 k1 + 256 k2
             if (ENV) {
 #pragma unroll
@@ -499,7 +524,8 @@ extern "C" int ecog_hilbert_twiddles(float* h_out) {
 
 extern "C" int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                                 const float* d_gain, int32_t nbands, int32_t rows, const int32_t* h_shift,
-                                int32_t halo, int32_t envelope, const float* d_twiddle, ecog_stream_t stream) {
+                                const int32_t* h_nz, int32_t halo, int32_t envelope, const float* d_twiddle,
+                                ecog_stream_t stream) {
     if (C <= 0 || T <= 0 || ldx < T || ldy < T || C > 65535) return fail(ECOG_E_VALUE, "ecog_hilbert_env: bad shape");
     if (nbands < 1 || nbands > 64) return fail(ECOG_E_VALUE, "ecog_hilbert_env: 1..64 bands supported, got %d", nbands);
     if (rows != 1 && rows != 2 && rows != 4 && rows != 8)
@@ -510,6 +536,11 @@ extern "C" int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t
     BandShift sh;
     for (int b = 0; b < 64; ++b) {
         sh.s[b] = (b < nbands && h_shift) ? h_shift[b] : 0;
+        sh.nz[b] = (b < nbands && h_nz && rows == 1) ? h_nz[b] : 16;     // only the one-row fast path prunes
+        if (sh.nz[b] < 1 || sh.nz[b] > 16)
+            return fail(ECOG_E_VALUE, "ecog_hilbert_env: band %d: nz %d outside 1..16", b, sh.nz[b]);
+        if (sh.nz[b] < 8) sh.nz[b] = 8;
+        else if (sh.nz[b] > 13) sh.nz[b] = 16;
         if (sh.s[b] < 0 || sh.s[b] + rows * 256 > kHalf)
             return fail(ECOG_E_VALUE, "ecog_hilbert_env: band %d shift %d leaves the half spectrum", b, sh.s[b]);
         if (!envelope && sh.s[b] != 0)

@@ -294,14 +294,16 @@ def hilbert_gain(cfs: np.ndarray, sds: np.ndarray, fs: float, envelope: bool = T
 
     Returns (gain (nb, rows*256) float32, shift (nb,) int32, rows).  gain = Gaussian x analytic
     factor 2, times 1/2 (conjugate-symmetry split), 1/N (inverse FFT) and 1/nb (mean over
-    bands); ref: frequency_filter.py:158-175,184 -- H[0] = 0.  Bins whose gain is below 1e-12
-    of the band peak are dropped; for the envelope each band is shifted down to its first kept
-    bin (|z| is invariant to a spectral shift) so that it fits rows*256 bins."""
+    bands); ref: frequency_filter.py:158-175,184 -- H[0] = 0.  Bins whose gain is below 1e-9
+    of the band peak are dropped (6.4 sigma; the dropped tails carry < 1e-9 of a line's amplitude,
+    two orders below the float32 arithmetic); for the envelope each band is shifted down to its
+    first kept bin (|z| is invariant to a spectral shift) so that it fits rows*256 bins and the
+    kernel can skip the zero tail of the window (hilbert_nz)."""
     N = HILBERT_N
     f = np.arange(N // 2, dtype=np.float64) * fs / N
     g = np.exp(-0.5 * ((f[None, :] - cfs[:, None]) / sds[:, None]) ** 2)
     g[:, 0] = 0.0
-    keep = g >= 1e-12 * g.max(axis=1, keepdims=True)
+    keep = g >= 1e-9 * g.max(axis=1, keepdims=True)
     lo = np.array([np.argmax(k) for k in keep])
     hi = np.array([len(k) - np.argmax(k[::-1]) for k in keep])       # one past the last kept bin
     if not envelope:
@@ -316,6 +318,13 @@ def hilbert_gain(cfs: np.ndarray, sds: np.ndarray, fs: float, envelope: bool = T
         out[b] = seg
     out *= 2.0 * 0.5 / N / len(cfs)
     return np.ascontiguousarray(out, dtype=np.float32), lo.astype(np.int32), rows
+
+
+def hilbert_nz(gain: np.ndarray) -> np.ndarray:
+    """Per band: number of leading 16-bin groups of the gain table that hold a non-zero entry
+    (the `h_nz` promise of ecog_hilbert_env; at least 1)."""
+    nzb = np.array([(np.flatnonzero(g)[-1] + 1 if np.any(g) else 1) for g in gain])
+    return np.maximum(-(-nzb // 16), 1).astype(np.int32)
 
 
 def hilbert_halo(cfs: np.ndarray, sds: np.ndarray, fs: float, T: int, nsigma: float = 5.0) -> int:

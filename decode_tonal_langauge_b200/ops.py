@@ -230,12 +230,13 @@ def hilbert(x: torch.Tensor, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0,
     key = ("hilbert_gain", tuple(cfs.tolist()), tuple(sds.tolist()), float(fs), bool(envelope))
     plan = _hilbert_plans.get(key)
     if plan is None:
-        plan = _hilbert_plans[key] = FP.hilbert_gain(cfs, sds, float(fs), bool(envelope))
-    gain_h, shift, rows = plan
+        g_h, sh, rw = FP.hilbert_gain(cfs, sds, float(fs), bool(envelope))
+        plan = _hilbert_plans[key] = (g_h, sh, rw, FP.hilbert_nz(g_h))
+    gain_h, shift, rows, nz = plan
     gain = _dev_table(key, lambda: gain_h, x.device)
     y = out if out is not None else torch.empty((Cn, T), dtype=torch.float32, device=x.device)
     nat.check(lib.ecog_hilbert_env(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), _ptr(gain), len(cfs), rows,
-                                   _hptr(shift), halo, 1 if envelope else 0,
+                                   _hptr(shift), _hptr(nz), halo, 1 if envelope else 0,
                                    _ptr(_hilbert_twiddles(x.device)), _stream()))
     return y
 

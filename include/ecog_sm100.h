@@ -111,13 +111,16 @@ int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx
  * Band b uses bins [h_shift[b], h_shift[b] + rows*256) of the block's half spectrum;
  * d_gain is nbands x (rows*256) float32 = Gaussian x analytic mask / (4096 * nbands) on
  * those bins (host, float64 -> float32).  rows in {1,2,4,8}.  With envelope=0 (real part)
- * every h_shift must be 0.  d_twiddle: table from ecog_hilbert_twiddles.              */
+ * every h_shift must be 0.  h_nz (optional, NULL = 16 per band; used when rows == 1): the
+ * caller's promise that d_gain[b][k] == 0 for k >= 16 * h_nz[b] -- the inverse transforms then
+ * skip the zero bins.  d_twiddle: table from ecog_hilbert_twiddles.                    */
 #define ECOG_HILBERT_N 4096
 size_t ecog_hilbert_twiddle_floats(void);
 int ecog_hilbert_twiddles(float* h_out);   /* host helper: fills the per-thread twiddle table */
 int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                      const float* d_gain, int32_t nbands, int32_t rows, const int32_t* h_shift,
-                     int32_t halo, int32_t envelope, const float* d_twiddle, ecog_stream_t stream);
+                     const int32_t* h_nz, int32_t halo, int32_t envelope, const float* d_twiddle,
+                     ecog_stream_t stream);
 
 /* ------------------------------------------------- K5: whole-row FFT resample
  * replaces preprocess/signal/downsample.py:21-27 (scipy.signal.resample, real input).
