@@ -248,14 +248,16 @@ fft_tile_kernel(const PassParams P) {
     }
 }
 
-// rfft untangle + resample bin rules + fold for the half-length inverse (one thread per k < N')
+// rfft untangle + resample bin rules + fold for the half-length inverse.  One thread per pair
+// (k, N' - k), k <= N'/2: both folded bins come from the same four spectrum values,
+// G[N' - k] = conj(E) + i conj(O) when G[k] = E + i O (W_num^{-(N'-k)} = -conj(W_num^{-k})).
 __global__ void __launch_bounds__(256)
 resample_repack_kernel(const float2* __restrict__ Z, float2* __restrict__ G, long long z_stride,
                        long long g_stride, int N, int Nh, long long T, long long num,
                        const float2* __restrict__ twT, const float2* __restrict__ twNum,
                        const float* __restrict__ gain) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= Nh) return;
+    if (k > Nh / 2) return;
     const float2* z = Z + (long long)blockIdx.y * z_stride;
     const long long m = num < T ? num : T;
     const int mh = (int)(m / 2);
@@ -282,7 +284,9 @@ resample_repack_kernel(const float2* __restrict__ Z, float2* __restrict__ G, lon
     const float2 O = cmulf(make_float2(0.5f * (yk.x - ym.x), 0.5f * (yk.y - ym.y)), __ldg(&twNum[k]));
     // G = E + i O, stored CONJUGATED: the inverse runs as conj(FFT(conj(G))) and the first pass
     // then takes its input as is (asynchronous tile copies)
-    G[(long long)blockIdx.y * g_stride + k] = make_float2(E.x - O.y, -(E.y + O.x));
+    float2* g = G + (long long)blockIdx.y * g_stride;
+    g[k] = make_float2(E.x - O.y, -(E.y + O.x));
+    if (k > 0 && 2 * k != Nh) g[Nh - k] = make_float2(E.x + O.y, E.y - O.x);
 }
 
 static bool pair_ok(int ra, int rb) {
@@ -476,7 +480,7 @@ extern "C" int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_
     }
     // ---- repack
     {
-        dim3 grid((unsigned)ceil_div(Nh, 256), (unsigned)C);
+        dim3 grid((unsigned)ceil_div(Nh / 2 + 1, 256), (unsigned)C);
         resample_repack_kernel<<<grid, 256, 0, st>>>(bufZ, bufG, N, Nh, (int)N, (int)Nh, T, num,
                                                      (const float2*)tb->tw_T, (const float2*)tb->tw_num,
                                                      tb->bin_gain);
