@@ -30,6 +30,7 @@ struct AxisDev {
     int lprev[16];                // sub-transform length before the pass
     int tws_a[16], tws_b[16];     // table strides n / L_t, n / L_{t+1}
     unsigned magic[16];           // ceil(2^32 / lprev)
+    unsigned magic_nsb[16];       // ceil(2^32 / (n / (ra * rb))): super-butterflies per column
 };
 
 struct PassParams {
@@ -182,9 +183,17 @@ fft_tile_kernel(const PassParams P) {
         const unsigned magic = P.ax.magic[s];
         const int nsb = n / (ra * rb);                   // super-butterflies per column
         const int code = ra * 8 + rb;
+        // Work item -> (column, super-butterfly).  First sweep (lp == 1): columns fastest, the W
+        // columns of a tile row are one contiguous segment.  Later sweeps: butterflies fastest --
+        // consecutive lanes then touch consecutive tile rows of ONE column, and with the odd pitch
+        // WP a half-warp's 64-bit accesses fall in 16 different bank pairs (columns-fastest puts two
+        // 64-byte rows per half-warp, which overlap in the banks: two-way conflicts on every access).
+        const bool col_fast = lp == 1 || nsb == 1;
+        const unsigned mnsb = P.ax.magic_nsb[s];
         for (int w = tid; w < nsb * W; w += kFftThreads) {
-            const int c = w & (W - 1);
-            const int b = w >> LOGW;
+            int c, b;
+            if (col_fast) { c = w & (W - 1); b = w >> LOGW; }
+            else { c = (int)__umulhi((unsigned)w, mnsb); b = w - c * nsb; }
             const int g = lp == 1 ? b : (int)__umulhi((unsigned)b, magic);
             const int j = b - g * lp;
             float2* col = tile + c;
@@ -312,6 +321,10 @@ static int fill_axis(const ecog_fft_axis& a, AxisDev& d) {
         if (s + 1 < a.nstage && pair_ok(ra, a.radix[s + 1])) rb = a.radix[s + 1];
         d.ra[np] = ra; d.rb[np] = rb; d.lprev[np] = (int)L;
         d.magic[np] = (unsigned)((0x100000000ull + (unsigned long long)L - 1) / (unsigned long long)L);
+        {
+            const unsigned long long nsb = (unsigned long long)a.n / (unsigned long long)(ra * rb);
+            d.magic_nsb[np] = (unsigned)((0x100000000ull + nsb - 1) / nsb);
+        }
         d.tws_a[np] = (int)(a.n / (L * ra));
         d.tws_b[np] = (int)(a.n / (L * ra * rb));
         L *= (long long)ra * rb;

@@ -171,6 +171,17 @@ def test_hilbert_shapes(ops, C, T, fs):
     assert max_rel(y, S.hilbert_filter(x, fs, [70.0, 150.0])) < TOL
 
 
+@pytest.mark.parametrize("fs,rng_hz", [(3000.0, [70.0, 150.0]), (2000.0, [80.0, 120.0]), (3000.0, [100.0, 140.0])])
+def test_hilbert_pruned_windows(ops, fs, rng_hz):
+    """Banks whose windows use fewer than 16 bin groups (3 kHz: clamped to 8) and odd band counts."""
+    from oracle import steps as S
+    rng = np.random.default_rng(17)
+    x = (rng.standard_normal((3, 30011)) * 20).astype(np.float32)
+    x += (5 * np.sin(2 * np.pi * 120.0 * np.arange(30011) / fs)).astype(np.float32)      # a line inside the bank
+    y = host(ops.hilbert(dev(x), fs, rng_hz))
+    assert max_rel(y, S.hilbert_filter(x, fs, rng_hz)) < TOL
+
+
 @pytest.mark.parametrize("envelope", [True, False])
 def test_hilbert_low_frequency_bands_whole_record(ops, golden, envelope):
     """Theta / alpha bands at 2 kHz: time kernels longer than the block -> whole-record FFT path."""

@@ -199,3 +199,40 @@ def test_choose_chunk_fills_one_wave():
     n_chunks = -(-7_200_000 // L)
     assert L % 16 == 0 and 256 * n_chunks <= 148 * 2 * 512
     assert D.choose_chunk(4, 12000) >= 1024
+
+
+def test_unit_circle_numerator_sections():
+    """Butterworth band-stop / low- / high-pass: the cascade uses b0 (1 + beta z^-1 + z^-2) sections
+    (csrc/sosfilt.cu numerator form 2) and their product is the reference's rounded numerator."""
+    from scipy import signal as S
+    for freqs, fs, btype in (([58, 62], 2000.0, "bandstop"), ([58, 62], 3051.7578125, "bandstop"),
+                             (200.0, 2000.0, "lowpass"), (1.0, 400.0, "highpass")):
+        d = D.butter_design(freqs, fs, 4, False, btype)
+        sos = d.sos
+        assert np.array_equal(sos[:, 2], sos[:, 0]) and np.all(sos[1:, 0] == 1.0)
+        assert np.all(sos[:, 1] / sos[:, 0] == sos[1, 1])                     # one beta for every section
+        b, _ = S.butter(4, np.asarray(freqs, dtype=float) / (fs / 2), btype=btype)
+        prod = np.array([1.0])
+        for sec in sos:
+            prod = np.convolve(prod, sec[:3])
+        assert np.max(np.abs(prod - b)) <= 4e-15 * np.max(np.abs(b))
+    d = D.butter_design([70, 150], 2000.0, 4, False, "bandpass")
+    assert np.array_equal(d.sos[:, 2], -d.sos[:, 0]) and np.all(d.sos[:, 1] == 0.0)
+
+
+def test_hilbert_nz_marks_the_zero_tail():
+    cfs, sds = D.gaussian_bank([70.0, 150.0])
+    for fs in (2000.0, 3000.0):
+        gain, shift, rows = FP.hilbert_gain(cfs, sds, fs, True)
+        assert rows == 1
+        nz = FP.hilbert_nz(gain)
+        assert nz.shape == (8,) and nz.min() >= 1 and nz.max() <= 16
+        for g, n in zip(gain, nz):
+            assert not np.any(g[16 * n:]) and np.any(g[16 * (n - 1):16 * n])
+        # the dropped tails are below 1e-9 of the band peak
+        f = np.arange(2048) * fs / 4096
+        for b in range(8):
+            full = np.exp(-0.5 * ((f - cfs[b]) / sds[b]) ** 2)
+            kept = np.zeros(2048, dtype=bool)
+            kept[shift[b]:shift[b] + 256] = gain[b] != 0
+            assert full[~kept].max() < 1e-9 * full.max()
