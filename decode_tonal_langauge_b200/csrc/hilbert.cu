@@ -362,7 +362,9 @@ constexpr int kXchg = 16 * 16 * kP18;                     // 4608: exchange buff
 constexpr int kSgBand = 16 * kP18;                        // 288: one gained band spectrum, layout [n0][n1]
 constexpr size_t kFastSmem = ((size_t)kXchg + (kN + kN / 16) + 2 * kFastBands * kSgBand + kSgBand) * sizeof(float2);
 
-template <bool ENV>
+// EDGE: the output samples t < 256 and t >= 3840 of a block (k2 = 0 and 15) are needed, i.e. the
+// halo is shorter than 256 samples; otherwise they are never computed.
+template <bool ENV, bool EDGE>
 __global__ void __launch_bounds__(kHT, 2)
 hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t ldx, int64_t ldy,
                     const float* __restrict__ gain, int nb, BandShift shift, int halo,
@@ -436,7 +438,9 @@ hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t 
     // two output blocks in natural order, one half each: one CTA barrier per block.
     float2* p2 = bufA + 16 * kP18 * k0 + n0;
     const float4* p3 = reinterpret_cast<const float4*>(bufA + kP18 * tid);
-    const float4* tb4 = reinterpret_cast<const float4*>(twBs + kP18 * k1);
+    float2 wb[16];                                       // W_256^{n0 k1}, n0 = 0..15: registers for the whole CTA
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wb[i] = twBs[kP18 * k1 + i];
     for (int sel = 0; sel < 2; ++sel) {
         float acc[16];
 #pragma unroll
@@ -456,28 +460,25 @@ hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t 
 #pragma unroll
             for (int e = 0; e < 16; ++e) p2[kP18 * e] = v[e];
             __syncwarp();
-            float2 wb[16];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float4 q = p3[i], t = tb4[i];
+                const float4 q = p3[i];
                 v[2 * i] = make_float2(q.x, q.y);
                 v[2 * i + 1] = make_float2(q.z, q.w);
-                wb[2 * i] = make_float2(t.x, t.y);
-                wb[2 * i + 1] = make_float2(t.z, t.w);
             }
             dft16_tw<true, 16>(v, wb);
             // v[k2] = conj(z[t]) (times a unit phasor when shifted), t = k0 + 16 k1 + 256 k2
             if (ENV) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += fast_sqrt(fmaf(v[j].x, v[j].x, v[j].y * v[j].y));
+                for (int j = EDGE ? 0 : 1; j < (EDGE ? 16 : 15); ++j) acc[j] += fast_sqrt(fmaf(v[j].x, v[j].x, v[j].y * v[j].y));
             } else {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) acc[j] += v[j].x;
+                for (int j = EDGE ? 0 : 1; j < (EDGE ? 16 : 15); ++j) acc[j] += v[j].x;
             }
         }
         float* ob = reinterpret_cast<float*>(bufB) + sel * (kN + kN / 16);
 #pragma unroll
-        for (int k2 = 0; k2 < 16; ++k2) ob[nat0 + 272 * k2] = acc[k2];
+        for (int k2 = EDGE ? 0 : 1; k2 < (EDGE ? 16 : 15); ++k2) ob[nat0 + 272 * k2] = acc[k2];
         __syncthreads();
         const int64_t bb = sel == 0 ? b0 : b1;
         if (bb < nBlocks) {
@@ -554,13 +555,19 @@ extern "C" int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t
     cudaStream_t st = (cudaStream_t)stream;
     if (rows == 1 && nbands <= kFastBands) {
         const size_t smem8 = kFastSmem;
-        if (envelope) {
-            ECOG_CUDA(cudaFuncSetAttribute(hilbert_env8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-            hilbert_env8_kernel<true><<<grid, kHT, smem8, st>>>(d_x, d_y, T, ldx, ldy, d_gain, nbands, sh, halo, tw, nBlocks);
-        } else {
-            ECOG_CUDA(cudaFuncSetAttribute(hilbert_env8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem8));
-            hilbert_env8_kernel<false><<<grid, kHT, smem8, st>>>(d_x, d_y, T, ldx, ldy, d_gain, nbands, sh, halo, tw, nBlocks);
-        }
+#define ECOG_HILBERT8(ENVV, EDGEV)                                                                                  \
+    do {                                                                                                            \
+        ECOG_CUDA(cudaFuncSetAttribute(hilbert_env8_kernel<ENVV, EDGEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                       (int)smem8));                                                                \
+        hilbert_env8_kernel<ENVV, EDGEV><<<grid, kHT, smem8, st>>>(d_x, d_y, T, ldx, ldy, d_gain, nbands, sh, halo,  \
+                                                                   tw, nBlocks);                                    \
+    } while (0)
+        const bool edge = halo < 256;
+        if (envelope && edge) ECOG_HILBERT8(true, true);
+        else if (envelope) ECOG_HILBERT8(true, false);
+        else if (edge) ECOG_HILBERT8(false, true);
+        else ECOG_HILBERT8(false, false);
+#undef ECOG_HILBERT8
         return check_launch("hilbert_env8");
     }
 #define ECOG_HILBERT_LAUNCH(R)                                                                                   \
