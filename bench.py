@@ -341,8 +341,8 @@ def run_ours(args):
                          "traffic_source": traffic["source"] if traffic else None,
                          "algorithmic_gb_per_launch": HILBERT_BYTES_PER_SAMPLE * C_local * T / 1e9,
                          "peak_source": peak_src,
-                         "note": "FP32 / shared-memory-pipe bound kernel (8.5 FFTs of 4096 points per 3422 samples; ncu: "
-                                 "LSU data pipe 71 %, issue 68 %, FMA pipe 53 %, DRAM 6.8 %), not HBM bound; "
+                         "note": "issue / shared-memory-pipe / FP32 bound kernel (8.5 FFTs of 4096 points per 3422 samples; ncu: "
+                                 "issue 71 %, LSU data pipe 62 %, FMA pipe 56 %, DRAM 7.3 %), not HBM bound; "
                                  "see DESIGN.md section 3",
                          "chain_achieved": chain_gbs, "chain_frac": chain_gbs / peak,
                          "chain_bytes_per_sample": FULL6_BYTES_PER_SAMPLE, "steps": step_roofline},

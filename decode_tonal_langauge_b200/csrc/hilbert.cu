@@ -482,10 +482,11 @@ hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t 
         __syncthreads();
         const int64_t bb = sel == 0 ? b0 : b1;
         if (bb < nBlocks) {
-            for (int i = tid; i < U; i += kHT) {
-                const int64_t t = bb * U + i;
-                if (t < T) yr[t] = ob[padi(halo + i)];
-            }
+            float* yo = yr + bb * U;
+            const int64_t left = T - bb * U;
+            const int lim = left < U ? (int)left : U;
+            const float* os = ob + halo;
+            for (int i = tid; i < lim; i += kHT) yo[i] = os[i + ((halo + i) >> 4)];     // padi(halo + i)
         }
     }
 }
