@@ -53,6 +53,13 @@ int main() {
     printf("75776 streams x 128 B, 4 in flight  %.3f ms  %.0f GB/s\n", ms, gb / ms * 1e3);
     ms = timeit([&] { streams<16, 2><<<296, 256>>>(in, out, L / 4, (int)(L / 64)); });
     printf("75776 streams x 256 B, 2 in flight  %.3f ms  %.0f GB/s\n", ms, gb / ms * 1e3);
+    // fewer, longer streams (same bytes)
+    ms = timeit([&] { streams<4, 8><<<148, 256>>>(in, out, 2 * L / 4, (int)(2 * L / 16)); });
+    printf("37888 streams x  64 B, 8 in flight  %.3f ms  %.0f GB/s\n", ms, gb / ms * 1e3);
+    ms = timeit([&] { streams<4, 8><<<74, 256>>>(in, out, 4 * L / 4, (int)(4 * L / 16)); });
+    printf("18944 streams x  64 B, 8 in flight  %.3f ms  %.0f GB/s\n", ms, gb / ms * 1e3);
+    ms = timeit([&] { streams<4, 4><<<592, 256>>>(in, out, L / 2 / 4, (int)(L / 2 / 16)); });
+    printf("151552 streams x 64 B, 4 in flight  %.3f ms  %.0f GB/s\n", ms, gb / ms * 1e3);
     printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
