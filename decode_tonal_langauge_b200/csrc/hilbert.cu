@@ -41,30 +41,57 @@ __device__ __forceinline__ void dft4(float2& a0, float2& a1, float2& a2, float2&
     a0 = cadd(t0, t2); a2 = csub(t0, t2); a1 = cadd(t1, t3); a3 = csub(t1, t3);
 }
 
-// forward 16-point DFT in place, natural order in and out
-__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+// 4-point DFT of (x0, w1 y1, w2 y2, w3 y3) with the twiddles w_m = s_m (1 + i tau_m) folded into
+// the butterflies: z_m = y_m (1 + i tau_m) costs two FMAs, and every scale s_m rides in an FMA that
+// would have been an addition (rho = s3 / s1):  22 operations instead of 28 (3 complex products +
+// 8 complex additions).  NEGI2: w2 = -i exactly (no scale).
+template <bool NEGI2>
+__device__ __forceinline__ void dft4_tw(float2& x0, float2& y1, float2& y2, float2& y3,
+                                        float tau1, float s1, float tau2, float s2, float tau3, float rho) {
+    const float2 z1 = make_float2(fmaf(-tau1, y1.y, y1.x), fmaf(tau1, y1.x, y1.y));
+    const float2 z3 = make_float2(fmaf(-tau3, y3.y, y3.x), fmaf(tau3, y3.x, y3.y));
+    float2 t0, t1;
+    if (NEGI2) {
+        const float2 x2 = make_float2(y2.y, -y2.x);
+        t0 = cadd(x0, x2); t1 = csub(x0, x2);
+    } else {
+        const float2 z2 = make_float2(fmaf(-tau2, y2.y, y2.x), fmaf(tau2, y2.x, y2.y));
+        t0 = make_float2(fmaf(s2, z2.x, x0.x), fmaf(s2, z2.y, x0.y));
+        t1 = make_float2(fmaf(-s2, z2.x, x0.x), fmaf(-s2, z2.y, x0.y));
+    }
+    const float2 u = make_float2(fmaf(rho, z3.x, z1.x), fmaf(rho, z3.y, z1.y));
+    const float2 d = make_float2(fmaf(-rho, z3.x, z1.x), fmaf(-rho, z3.y, z1.y));
+    x0 = make_float2(fmaf(s1, u.x, t0.x), fmaf(s1, u.y, t0.y));
+    y2 = make_float2(fmaf(-s1, u.x, t0.x), fmaf(-s1, u.y, t0.y));
+    y1 = make_float2(fmaf(s1, d.y, t1.x), fmaf(-s1, d.x, t1.y));          // t1 + s1 (-i d)
+    y3 = make_float2(fmaf(-s1, d.y, t1.x), fmaf(s1, d.x, t1.y));
+}
+
+// second half of the 16-point DFT: inter-stage twiddles W16^(m p) + the four DFT4 over m + the
+// transposition to natural order; element (m, p) lives at v[m + 4p] on entry
+__device__ __forceinline__ void dft16_stage2(float2 (&v)[16]) {
     const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
-    // stage 1: for each m, DFT4 over q of v[m + 4q]  -> a[m][p] kept at v[m + 4p]
-#pragma unroll
-    for (int m = 0; m < 4; ++m) dft4(v[m], v[m + 4], v[m + 8], v[m + 12]);
-    // twiddle W16^(m p), element (m, p) lives at v[m + 4p]
-    v[1 + 4] = cmul(v[1 + 4], make_float2(C1, -S1));        // m=1,p=1 : W^1
-    v[1 + 8] = cmul(v[1 + 8], make_float2(C2, -C2));        // m=1,p=2 : W^2
-    v[1 + 12] = cmul(v[1 + 12], make_float2(S1, -C1));      // m=1,p=3 : W^3
-    v[2 + 4] = cmul(v[2 + 4], make_float2(C2, -C2));        // m=2,p=1 : W^2
-    v[2 + 8] = mul_mi(v[2 + 8]);                            // m=2,p=2 : W^4 = -i
-    v[2 + 12] = cmul(v[2 + 12], make_float2(-C2, -C2));     // m=2,p=3 : W^6
-    v[3 + 4] = cmul(v[3 + 4], make_float2(S1, -C1));        // m=3,p=1 : W^3
-    v[3 + 8] = cmul(v[3 + 8], make_float2(-C2, -C2));       // m=3,p=2 : W^6
-    v[3 + 12] = cmul(v[3 + 12], make_float2(-C1, S1));      // m=3,p=3 : W^9
-    // stage 2: for each p, DFT4 over m of v[m + 4p] -> X[p + 4r] at v[4p + r]
-#pragma unroll
-    for (int p = 0; p < 4; ++p) dft4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
-    // now v[4p + r] = X[p + 4r]; transpose the 4x4 index to natural order
+    const float T1 = 0.41421356237309503f, T3 = 2.4142135623730951f;    // tan(pi/8), tan(3 pi/8)
+    dft4(v[0], v[1], v[2], v[3]);
+    // p = 1: W^1 = C1 (1 - i T1), W^2 = C2 (1 - i), W^3 = S1 (1 - i T3)
+    dft4_tw<false>(v[4], v[5], v[6], v[7], -T1, C1, -1.f, C2, -T3, S1 / C1);
+    // p = 2: W^2 = C2 (1 - i), W^4 = -i, W^6 = -C2 (1 + i)
+    dft4_tw<true>(v[8], v[9], v[10], v[11], -1.f, C2, 0.f, 0.f, 1.f, -1.f);
+    // p = 3: W^3 = S1 (1 - i T3), W^6 = -C2 (1 + i), W^9 = -C1 (1 - i T1)
+    dft4_tw<false>(v[12], v[13], v[14], v[15], -T3, S1, 1.f, -C2, -T1, -C1 / S1);
 #pragma unroll
     for (int p = 0; p < 4; ++p)
 #pragma unroll
         for (int r = p + 1; r < 4; ++r) { float2 t = v[4 * p + r]; v[4 * p + r] = v[4 * r + p]; v[4 * r + p] = t; }
+}
+
+// forward 16-point DFT in place, natural order in and out
+__device__ __forceinline__ void dft16(float2 (&v)[16]) {
+    // stage 1: for each m, DFT4 over q of v[m + 4q]  -> a[m][p] kept at v[m + 4p]
+#pragma unroll
+    for (int m = 0; m < 4; ++m) dft4(v[m], v[m + 4], v[m + 8], v[m + 12]);
+    // twiddles W16^(m p) + stage 2 (for each p, DFT4 over m of v[m + 4p] -> X[p + 4r]) + transposition
+    dft16_stage2(v);
 }
 
 // passes 2 and 3 of the 4096-point forward FFT; pass-1 output must already be in `buf`
@@ -308,7 +335,6 @@ __device__ __forceinline__ void tw_bfly1(float2 a, float2 b, float2 wb, float2& 
 // neither read nor multiplied.
 template <bool W0ONE, int NZ>
 __device__ __forceinline__ void dft16_tw(float2 (&v)[16], const float2 (&w)[16]) {
-    const float C1 = 0.92387953251128674f, S1 = 0.38268343236508977f, C2 = 0.70710678118654752f;
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
         float2 t0, t1, t2, t3;
@@ -326,21 +352,7 @@ __device__ __forceinline__ void dft16_tw(float2 (&v)[16], const float2 (&w)[16])
         t3 = mul_mi(t3);
         v[m] = cadd(t0, t2); v[m + 8] = csub(t0, t2); v[m + 4] = cadd(t1, t3); v[m + 12] = csub(t1, t3);
     }
-    v[1 + 4] = cmul(v[1 + 4], make_float2(C1, -S1));
-    v[1 + 8] = cmul(v[1 + 8], make_float2(C2, -C2));
-    v[1 + 12] = cmul(v[1 + 12], make_float2(S1, -C1));
-    v[2 + 4] = cmul(v[2 + 4], make_float2(C2, -C2));
-    v[2 + 8] = mul_mi(v[2 + 8]);
-    v[2 + 12] = cmul(v[2 + 12], make_float2(-C2, -C2));
-    v[3 + 4] = cmul(v[3 + 4], make_float2(S1, -C1));
-    v[3 + 8] = cmul(v[3 + 8], make_float2(-C2, -C2));
-    v[3 + 12] = cmul(v[3 + 12], make_float2(-C1, S1));
-#pragma unroll
-    for (int p = 0; p < 4; ++p) dft4(v[4 * p], v[4 * p + 1], v[4 * p + 2], v[4 * p + 3]);
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int r = p + 1; r < 4; ++r) { float2 t = v[4 * p + r]; v[4 * p + r] = v[4 * r + p]; v[4 * r + p] = t; }
+    dft16_stage2(v);
 }
 
 // pass 2 of an inverse whose gained band spectrum has NZ * 16 non-zero bins: thread (k0, n0) reads

@@ -1,4 +1,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-for nt in 128 256 128 256; do ECOG_SOS_NT=$nt timeout 120 python scripts/prof_ops.py car,bandpass,notch,bandpass,notch 256 7200000 5 | sed "s/^/nt=$nt /"; done > gpurun_out/ops45.log 2>&1
-grep -v car gpurun_out/ops45.log
+timeout 900 python -m pytest tests -x -q -m gpu -k "hilbert or chain or full6 or smoke or pipeline" > gpurun_out/t46.log 2>&1; tail -3 gpurun_out/t46.log
+timeout 300 python scripts/prof_ops.py car,hilbert,hilbert 256 7200000 5 > gpurun_out/ops46.log 2>&1
+cat gpurun_out/ops46.log
