@@ -342,7 +342,7 @@ def run_ours(args):
                          "algorithmic_gb_per_launch": HILBERT_BYTES_PER_SAMPLE * C_local * T / 1e9,
                          "peak_source": peak_src,
                          "note": "issue / shared-memory-pipe / FP32 bound kernel (8.5 FFTs of 4096 points per 3422 samples; ncu: "
-                                 "issue 71 %, LSU data pipe 62 %, FMA pipe 56 %, DRAM 7.3 %), not HBM bound; "
+                                 "issue 68 %, LSU data pipe 63 %, FMA pipe 53 %, DRAM 7.5 %), not HBM bound; "
                                  "see DESIGN.md section 3",
                          "chain_achieved": chain_gbs, "chain_frac": chain_gbs / peak,
                          "chain_bytes_per_sample": FULL6_BYTES_PER_SAMPLE, "steps": step_roofline},
