@@ -193,6 +193,10 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs CUDA devices; there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
+    host_cpus = None
+    if os.environ.get("ECOG_NO_AFFINITY") is None:
+        from decode_tonal_langauge_b200 import runtime as _rt
+        host_cpus = _rt.bind_host_to_gpu(local)       # pinned staging buffers next to this GPU's PCIe root
     if world > 1:
         # NCCL prints its version banner on stdout when the communicator is created; the contract
         # is ONE JSON line on stdout, so the banner goes to stderr
@@ -311,7 +315,8 @@ def run_ours(args):
                "steps": e2e_steps, "ms_per_step": 1e3 * float(dt.item()) / e2e_steps,
                "api": "preprocess_signal(numpy (C,T) float32 pinned) -> numpy float64 (reference dtype); "
                       "channel-chunked copies overlapped with the kernels",
-               "out_dtype": out_dtype}
+               "out_dtype": out_dtype,
+               "host_cpus": len(host_cpus) if host_cpus else None}     # cores this rank is pinned to (GPU-local NUMA node)
         del host_in
 
     cpu = None

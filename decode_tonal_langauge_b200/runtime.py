@@ -30,6 +30,31 @@ def device() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def bind_host_to_gpu(index: Optional[int] = None) -> Optional[list]:
+    """Pin this process to the CPU cores NVML reports as local to the GPU (its NUMA node), so that
+    the pinned staging buffers it allocates afterwards are first-touched next to the GPU's PCIe
+    root and the copies of several ranks do not cross the socket interconnect.  Best effort:
+    returns the core list, or None when NVML / sched_setaffinity is unavailable."""
+    try:
+        import pynvml
+        if index is None:
+            index = torch.cuda.current_device()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(visible.split(",")[index]) if visible and all(v.strip().isdigit() for v in visible.split(",")) else index
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return allowed
+    except Exception:
+        pass
+    return None
+
+
 def to_device(x: ArrayLike, dtype: Optional[torch.dtype] = torch.float32) -> torch.Tensor:
     """numpy / CPU tensor -> CUDA tensor.  float64 sources are narrowed on the DEVICE so the
     PCIe copy is the only host-side pass; pinned sources are copied asynchronously."""
