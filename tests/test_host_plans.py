@@ -236,3 +236,13 @@ def test_hilbert_nz_marks_the_zero_tail():
             kept = np.zeros(2048, dtype=bool)
             kept[shift[b]:shift[b] + 256] = gain[b] != 0
             assert full[~kept].max() < 1e-9 * full.max()
+
+
+def test_bind_host_to_gpu_is_best_effort():
+    """No GPU / no NVML here: the affinity helper must decline quietly and leave the mask alone."""
+    import os
+    from decode_tonal_langauge_b200 import runtime as rt
+    before = os.sched_getaffinity(0)
+    got = rt.bind_host_to_gpu(0)
+    assert got is None or set(got) <= before
+    assert os.sched_getaffinity(0) == (set(got) if got else before)
