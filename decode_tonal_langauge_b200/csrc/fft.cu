@@ -31,6 +31,8 @@ struct AxisDev {
     int tws_a[16], tws_b[16];     // table strides n / L_t, n / L_{t+1}
     unsigned magic[16];           // ceil(2^32 / lprev)
     unsigned magic_nsb[16];       // ceil(2^32 / (n / (ra * rb))): super-butterflies per column
+    int nrest;                    // radix stages after the first sweep ...
+    int rest[16];                 // ... and their radices (digit order of the super-butterfly index g)
 };
 
 struct PassParams {
@@ -131,6 +133,47 @@ __device__ __forceinline__ void super_bfly(float2* col, int g, int j, int lp, co
         for (int pa = 0; pa < RA; ++pa) e0[(pa * lp + pb * Lt) * WP] = a[pa * RB + pb];
 }
 
+// First sweep (lp == 1) of one column fed straight from global memory: super-butterfly g owns the
+// tile rows g R + qa + qb RA (R = RA RB), i.e. the input rows i0 + qa n/RA + qb n/R, where i0 is g
+// with its mixed-radix digits reversed (the digit-reversal permutation of the DIT transform, built
+// here instead of being read from a table).  Only the inner twiddles W_{RA RB}^{pa qb} appear (j == 0);
+// they come from global memory, the shared root table is not published yet.
+template <int RA, int RB, int WP>
+__device__ __forceinline__ void super_bfly_first(float2* col, const float2* __restrict__ src, bool ok, bool conj,
+                                                 int g, long long i0m, long long stride_a, long long stride_b,
+                                                 const float2* __restrict__ twg, int tws_b) {
+    float2 a[RA * RB];                       // a[qa * RB + qb]
+#pragma unroll
+    for (int qb = 0; qb < RB; ++qb)
+#pragma unroll
+        for (int qa = 0; qa < RA; ++qa) {
+            float2 v = make_float2(0.f, 0.f);
+            if (ok) v = __ldg(src + i0m + qa * stride_a + qb * stride_b);
+            a[qa * RB + qb] = v;
+        }
+    if (conj) {
+#pragma unroll
+        for (int e = 0; e < RA * RB; ++e) a[e].y = -a[e].y;
+    }
+#pragma unroll
+    for (int qb = 0; qb < RB; ++qb) bfly<RA, RB>(a + qb);              // over qa, stride RB
+    if (RB > 1) {
+#pragma unroll
+        for (int pa = 0; pa < RA; ++pa) {
+            if (pa) {
+#pragma unroll
+                for (int qb = 1; qb < RB; ++qb) a[pa * RB + qb] = cmulf(a[pa * RB + qb], __ldg(&twg[pa * qb * tws_b]));   // W_{RA RB}^{pa qb}
+            }
+            bfly<RB, 1>(a + pa * RB);                                  // over qb, stride 1
+        }
+    }
+    float2* e0 = col + (g * RA * RB) * WP;
+#pragma unroll
+    for (int pb = 0; pb < RB; ++pb)
+#pragma unroll
+        for (int pa = 0; pa < RA; ++pa) e0[(pa + pb * RA) * WP] = a[pa * RB + pb];
+}
+
 template <int W>
 __global__ void __launch_bounds__(kFftThreads, 2)
 fft_tile_kernel(const PassParams P) {
@@ -148,36 +191,58 @@ fft_tile_kernel(const PassParams P) {
     float2* out = P.out + (long long)blockIdx.y * P.out_ch_stride;
     const int cw = m - c0 < W ? m - c0 : W;             // valid columns in this tile
 
-    // ---- load: row i (cw contiguous complex) -> tile[perm[i]].  Asynchronous copies: the whole tile
-    // is in flight at once and no register waits on a load (one DRAM latency per tile, not one per
-    // unrolled batch).  A conjugated input goes through registers.
-    if (!P.conj_in) {
-#pragma unroll 8
-        for (int idx = tid; idx < n * W; idx += kFftThreads) {
-            const int i = idx >> LOGW, c = idx & (W - 1);
-            const bool ok = c < cw;
-            cp_async8_zfill(&tile[__ldg(&P.perm[i]) * WP + c], in + (long long)i * m + c0 + (ok ? c : 0), ok);
-        }
-        cp_async_commit();
-        if (P.tw_shared) for (int k = tid; k < n; k += kFftThreads) tws_w[k] = __ldg(&P.tw[k]);
-        cp_async_wait<0>();
-    } else {
-        if (P.tw_shared) for (int k = tid; k < n; k += kFftThreads) tws_w[k] = __ldg(&P.tw[k]);
-#pragma unroll 8
-        for (int idx = tid; idx < n * W; idx += kFftThreads) {
-            const int i = idx >> LOGW, c = idx & (W - 1);
+    // ---- first sweep, fed from global memory (no separate tile fill): work item -> (column, butterfly g),
+    // columns fastest so that the W columns of an input row are one contiguous segment
+    if (P.tw_shared) for (int k = tid; k < n; k += kFftThreads) tws_w[k] = __ldg(&P.tw[k]);
+    if (P.ax.npass == 0) {                               // n == 1: the transform is the identity
+        if (tid < W) {
             float2 v = make_float2(0.f, 0.f);
-            if (c < cw) {
-                v = in[(long long)i * m + c0 + c];
-                v.y = -v.y;
+            if (tid < cw) v = in[c0 + tid];
+            if (P.conj_in) v.y = -v.y;
+            tile[tid] = v;
+        }
+    } else {
+        const int ra = P.ax.ra[0], rb = P.ax.rb[0];
+        const int R0 = ra * rb;
+        const int nsb = n / R0;
+        const long long stride_a = (long long)(n / ra) * m, stride_b = (long long)(n / R0) * m;
+        const int tb = P.ax.tws_b[0];
+        const int code = ra * 8 + rb;
+        for (int w = tid; w < nsb * W; w += kFftThreads) {
+            const int c = w & (W - 1);
+            const int g = w >> LOGW;
+            int i0 = 0, gg = g;                          // digits of g reversed (Horner over the later radices)
+            for (int k = 0; k < P.ax.nrest; ++k) {
+                const int r = P.ax.rest[k];
+                const int q = gg / r;
+                i0 = i0 * r + (gg - q * r);
+                gg = q;
             }
-            tile[__ldg(&P.perm[i]) * WP + c] = v;
+            const long long i0m = (long long)i0 * m + c0 + c;
+            const bool ok = c < cw;
+            float2* col = tile + c;
+            const bool cj = P.conj_in != 0;
+            switch (code) {
+                case 4 * 8 + 4: super_bfly_first<4, 4, WP>(col, in, ok, cj, g, i0m, stride_a, stride_b, P.tw, tb); break;
+                case 4 * 8 + 2: super_bfly_first<4, 2, WP>(col, in, ok, cj, g, i0m, stride_a, stride_b, P.tw, tb); break;
+                case 4 * 8 + 3: super_bfly_first<4, 3, WP>(col, in, ok, cj, g, i0m, stride_a, stride_b, P.tw, tb); break;
+                case 4 * 8 + 5: super_bfly_first<4, 5, WP>(col, in, ok, cj, g, i0m, stride_a, stride_b, P.tw, tb); break;
+                case 2 * 8 + 3: super_bfly_first<2, 3, WP>(col, in, ok, cj, g, i0m, stride_a, stride_b, P.tw, tb); break;
+                case 2 * 8 + 5: super_bfly_first<2, 5, WP>(col, in, ok, cj, g, i0m, stride_a, stride_b, P.tw, tb); break;
+                case 3 * 8 + 3: super_bfly_first<3, 3, WP>(col, in, ok, cj, g, i0m, stride_a, stride_b, P.tw, tb); break;
+                case 3 * 8 + 5: super_bfly_first<3, 5, WP>(col, in, ok, cj, g, i0m, stride_a, stride_b, P.tw, tb); break;
+                case 5 * 8 + 5: super_bfly_first<5, 5, WP>(col, in, ok, cj, g, i0m, stride_a, stride_b, P.tw, tb); break;
+                case 2 * 8 + 1: super_bfly_first<2, 1, WP>(col, in, ok, cj, g, i0m, stride_a, stride_b, P.tw, tb); break;
+                case 3 * 8 + 1: super_bfly_first<3, 1, WP>(col, in, ok, cj, g, i0m, stride_a, stride_b, P.tw, tb); break;
+                case 4 * 8 + 1: super_bfly_first<4, 1, WP>(col, in, ok, cj, g, i0m, stride_a, stride_b, P.tw, tb); break;
+                default:        super_bfly_first<5, 1, WP>(col, in, ok, cj, g, i0m, stride_a, stride_b, P.tw, tb); break;
+            }
         }
     }
     __syncthreads();
 
     // ---- in-place DIT: one shared-memory sweep per fused stage pair
-    for (int s = 0; s < P.ax.npass; ++s) {
+    for (int s = 1; s < P.ax.npass; ++s) {
         const int ra = P.ax.ra[s], rb = P.ax.rb[s], lp = P.ax.lprev[s];
         const int ta = P.ax.tws_a[s], tb = P.ax.tws_b[s];
         const unsigned magic = P.ax.magic[s];
@@ -332,6 +397,11 @@ static int fill_axis(const ecog_fft_axis& a, AxisDev& d) {
         ++np;
     }
     d.npass = np;
+    {
+        const int used = d.npass ? (d.rb[0] > 1 ? 2 : 1) : 0;
+        d.nrest = a.nstage - used;
+        for (int k = 0; k < d.nrest; ++k) d.rest[k] = a.radix[used + k];
+    }
     if (L != a.n) return fail(ECOG_E_VALUE, "fft axis: radices multiply to %lld, not n=%d", L, a.n);
     if ((long long)a.n * 5 * (long long)sizeof(float2) > 220 * 1024)
         return fail(ECOG_E_UNSUPPORTED, "fft axis: n=%d does not fit shared memory", a.n);
