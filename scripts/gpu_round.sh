@@ -1,6 +1,4 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-for ch in 8 12 16 6; do
-ECOG_PIPELINE_CHUNKS=$ch timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/bench53_$ch.json 2>/dev/null; python -c "
-import json;d=json.load(open('gpurun_out/bench53_$ch.json'));print('chunks=$ch',d['ms_per_step'],d['e2e']['ms_per_step'])"
-done
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/t54.log 2>&1; tail -2 gpurun_out/t54.log
+timeout 60 scripts/micro/fp32_pipes > gpurun_out/fp32_pipes.txt 2>&1; cat gpurun_out/fp32_pipes.txt
