@@ -16,7 +16,7 @@ ECOG_E_VALUE = -1
 ECOG_E_CUDA = -2
 ECOG_E_WORKSPACE = -3
 ECOG_E_UNSUPPORTED = -4
-ABI_VERSION = 4
+ABI_VERSION = 5
 MAX_SECTIONS = 8
 SOS_SCAN = 0
 SOS_WARMUP = 1
@@ -25,7 +25,8 @@ HILBERT_N = 4096
 
 class SosPlan(C.Structure):
     _fields_ = [("nsec", C.c_int32), ("zero_phase", C.c_int32), ("padlen", C.c_int32),
-                ("chunk", C.c_int32), ("tail", C.c_int32), ("mode", C.c_int32), ("threads", C.c_int32)]
+                ("chunk", C.c_int32), ("tail", C.c_int32), ("mode", C.c_int32), ("threads", C.c_int32),
+                ("split", C.c_int32), ("tail_b", C.c_int32)]
 
 
 class FftAxis(C.Structure):
@@ -63,17 +64,18 @@ PROTOTYPES = {
     "ecog_abi_version": (C.c_int, []),
     "ecog_last_error": (C.c_char_p, []),
     "ecog_launch_count": (_I64, []),
-    "ecog_car": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _F64, _P]),
+    "ecog_car": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _F64, _P]),
     "ecog_car_colsum": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P]),
-    "ecog_car_apply": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _F64, _P]),
+    "ecog_car_apply": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _F64, _P]),
     "ecog_row_stats_workspace": (_SZ, [_I64, _I64]),
     "ecog_row_stats": (C.c_int, [_P, _I64, _I64, _I64, _I64, _I64, _P, _P, _P, _SZ, _P]),
-    "ecog_zscore_apply": (C.c_int, [_P, _P, _I64, _I64, _I64, _P, _P, C.c_int, _P]),
+    "ecog_zscore_apply": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _P, C.c_int, _P]),
     "ecog_sos_workspace": (_SZ, [C.POINTER(SosPlan), _I64, _I64]),
     "ecog_sosfilt": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, C.POINTER(SosPlan), _P, _P, _P, _P, _SZ, _P]),
+    "ecog_copy2d": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _P]),
     "ecog_hilbert_twiddle_floats": (_SZ, []),
     "ecog_hilbert_twiddles": (C.c_int, [_P]),
-    "ecog_hilbert_env": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _I32, _I32, _P, _P, _I32, _I32, _P, _P]),
+    "ecog_hilbert_env": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _I32, _I32, _P, _P, _I32, _I32, _P, _P, _F64, _P]),
     "ecog_resample_workspace": (_SZ, [C.POINTER(ResamplePlan), _I64]),
     "ecog_fft_resample": (C.c_int, [_P, _P, _I64, _I64, _I64, C.POINTER(ResamplePlan),
                                     C.POINTER(ResampleTables), _P, _SZ, _P]),

@@ -168,12 +168,101 @@ anova_final_kernel(int64_t CL, int64_t N, int nslab, GroupCounts cnt, int G,
     Pout[idx] = f_survival(dfb, dfw, F);
 }
 
-static int gmax_of(int G) { return G <= 2 ? 2 : (G <= 4 ? 4 : (G <= 8 ? 8 : 16)); }
-static int anova_slabs(int64_t CL, int64_t N) {
+// ---- more than 16 groups (e.g. a syllable target with many classes; scipy's f_oneway has no limit):
+// same algorithm with the group loop at run time -- each group's partials go straight to the
+// workspace instead of a register array.  Group starts ride in the kernel parameters.
+constexpr int kMaxGroups = 256;
+struct GroupStartsBig { int64_t at[kMaxGroups + 1]; };
+
+__global__ void __launch_bounds__(kAnovaThreads)
+anova_partial_rt_kernel(const float* __restrict__ ea, int64_t Na, const float* __restrict__ eb, int64_t Nb,
+                        int64_t CL, const int32_t* __restrict__ order, GroupStartsBig gs, int G, int64_t slab,
+                        double* __restrict__ psum, float* __restrict__ pmin, float* __restrict__ pmax) {
+    __shared__ int32_t ord[kLabelChunk];
+    const int64_t idx = (int64_t)blockIdx.x * kAnovaThreads + threadIdx.x;
+    const bool live = idx < CL;
+    const int64_t N = Na + Nb;
+    const int64_t nBeg = (int64_t)blockIdx.y * slab;
+    const int64_t nEnd = nBeg + slab < N ? nBeg + slab : N;
+    double q = 0.0;
+    const double shift = live ? (double)(Na > 0 ? ea[idx] : eb[idx]) : 0.0;
+    const float* pa = ea + (live ? idx : 0);
+    const float* pb = eb ? eb + (live ? idx : 0) - Na * CL : pa;
+    const int64_t base = (int64_t)blockIdx.y * (G + 1) * CL;
+    const int64_t fb = (int64_t)blockIdx.y * G * CL;
+    for (int k = 0; k < G; ++k) {
+        double sk = 0.0;
+        float lo = INFINITY, hi = -INFINITY;
+        const int64_t g0 = gs.at[k] > nBeg ? gs.at[k] : nBeg;
+        const int64_t g1 = gs.at[k + 1] < nEnd ? gs.at[k + 1] : nEnd;
+        for (int64_t n0 = g0; n0 < g1; n0 += kLabelChunk) {
+            const int chunk = (int)(g1 - n0 < kLabelChunk ? g1 - n0 : kLabelChunk);
+            __syncthreads();
+            for (int i = threadIdx.x; i < chunk; i += kAnovaThreads) ord[i] = order[n0 + i];
+            __syncthreads();
+            if (!live) continue;
+#pragma unroll 8
+            for (int i = 0; i < chunk; ++i) {
+                const int64_t n = ord[i];
+                const float v = __ldg((n < Na ? pa : pb) + n * CL);
+                const double d = (double)v - shift;
+                sk += d;
+                q = fma(d, d, q);
+                lo = fminf(lo, v);
+                hi = fmaxf(hi, v);
+            }
+        }
+        if (live) { psum[base + k * CL + idx] = sk; pmin[fb + k * CL + idx] = lo; pmax[fb + k * CL + idx] = hi; }
+    }
+    if (live) psum[base + (int64_t)G * CL + idx] = q;
+}
+
+__global__ void __launch_bounds__(kAnovaThreads)
+anova_final_rt_kernel(int64_t CL, int64_t N, int nslab, GroupStartsBig gs, int G,
+                      const double* __restrict__ psum, const float* __restrict__ pmin, const float* __restrict__ pmax,
+                      double* __restrict__ Fout, double* __restrict__ Pout) {
+    const int64_t idx = (int64_t)blockIdx.x * kAnovaThreads + threadIdx.x;
+    if (idx >= CL) return;
+    double S = 0.0, ssb = 0.0, q = 0.0;
+    bool all_const = true;
+    float gmn = INFINITY, gmx = -INFINITY;
+    for (int k = 0; k < G; ++k) {
+        double sk = 0.0;
+        float mn = INFINITY, mx = -INFINITY;
+        for (int b = 0; b < nslab; ++b) {           // slab order: deterministic
+            sk += psum[(int64_t)b * (G + 1) * CL + k * CL + idx];
+            mn = fminf(mn, pmin[(int64_t)b * G * CL + k * CL + idx]);
+            mx = fmaxf(mx, pmax[(int64_t)b * G * CL + k * CL + idx]);
+        }
+        S += sk;
+        ssb += sk * sk / (double)(gs.at[k + 1] - gs.at[k]);
+        all_const = all_const && (mn == mx);
+        gmn = fminf(gmn, mn); gmx = fmaxf(gmx, mx);
+    }
+    for (int b = 0; b < nslab; ++b) q += psum[(int64_t)b * (G + 1) * CL + (int64_t)G * CL + idx];
+    const double norm = S * S / (double)N;
+    const double sstot = q - norm;
+    ssb -= norm;
+    const double ssw = sstot - ssb;
+    const double dfb = (double)(G - 1), dfw = (double)(N - G);
+    double F = (ssb / dfb) / (ssw / dfw);
+    if (all_const) F = INFINITY;
+    if (gmn == gmx) F = nan("");
+    Fout[idx] = F;
+    Pout[idx] = f_survival(dfb, dfw, F);
+}
+
+static int gmax_of(int G) { return G <= 2 ? 2 : (G <= 4 ? 4 : (G <= 8 ? 8 : (G <= 16 ? 16 : G))); }
+static int anova_slabs(int64_t CL, int64_t N, int G) {
     // enough (c,t)-threads x slabs to fill the machine with loads in flight; slabs of >= 256 events
     int64_t want = ceil_div((int64_t)kNumSMs * 2048 * 2, CL);
     int64_t cap = N / 256 > 1 ? N / 256 : 1;
     int64_t sl = want < cap ? want : cap;
+    if (G > 16) {   // run-time group path: keep the partials below ~1 GiB
+        const int64_t per = CL * ((int64_t)(G + 1) * 8 + 2 * (int64_t)G * 4);
+        const int64_t fit = ((int64_t)1 << 30) / (per > 0 ? per : 1);
+        if (sl > fit) sl = fit;
+    }
     return (int)(sl < 1 ? 1 : (sl > 64 ? 64 : sl));
 }
 
@@ -204,7 +293,7 @@ using namespace ecog;
 
 extern "C" size_t ecog_anova_workspace(int64_t C, int64_t L, int64_t N, int32_t G) {
     const int64_t CL = C * L;
-    const int gm = gmax_of(G), ns = anova_slabs(CL, N);
+    const int gm = gmax_of(G), ns = anova_slabs(CL, N, G);
     return (size_t)ns * CL * ((gm + 1) * sizeof(double) + 2 * gm * sizeof(float)) + 256;
 }
 
@@ -214,8 +303,37 @@ extern "C" int ecog_anova_f(const float* d_epochs_a, int64_t Na, const float* d_
                             ecog_stream_t stream) {
     if (C <= 0 || L <= 0 || Na < 0 || Nb < 0 || Na + Nb < 2) return fail(ECOG_E_VALUE, "ecog_anova_f: bad shape");
     if (G < 2) return fail(ECOG_E_VALUE, "ecog_anova_f: need at least two groups, got %d", G);
-    if (G > 16) return fail(ECOG_E_UNSUPPORTED, "ecog_anova_f: at most 16 groups supported, got %d", G);
+    if (G > kMaxGroups) return fail(ECOG_E_UNSUPPORTED, "ecog_anova_f: at most %d groups supported, got %d", kMaxGroups, G);
     if (Na + Nb <= G) return fail(ECOG_E_VALUE, "ecog_anova_f: need more events than groups");
+    if (G > 16) {
+        GroupStartsBig gb;
+        int64_t t2 = 0;
+        for (int k = 0; k <= kMaxGroups; ++k) {
+            gb.at[k] = t2;
+            if (k < G) {
+                if (h_group_count[k] <= 0) return fail(ECOG_E_VALUE, "ecog_anova_f: empty group %d", k);
+                t2 += h_group_count[k];
+            }
+        }
+        const int64_t N2 = Na + Nb;
+        if (t2 != N2) return fail(ECOG_E_VALUE, "ecog_anova_f: group counts do not sum to the event count");
+        if (workspace_bytes < ecog_anova_workspace(C, L, N2, G))
+            return fail(ECOG_E_WORKSPACE, "ecog_anova_f: workspace %zu < %zu", workspace_bytes, ecog_anova_workspace(C, L, N2, G));
+        const int64_t CL2 = C * L;
+        const int ns2 = anova_slabs(CL2, N2, G);
+        const int64_t slab2 = ceil_div(N2, ns2);
+        double* ps = (double*)d_workspace;
+        float* pmn = (float*)(ps + (size_t)ns2 * (G + 1) * CL2);
+        float* pmx = pmn + (size_t)ns2 * G * CL2;
+        dim3 g2((unsigned)ceil_div(CL2, kAnovaThreads), (unsigned)ns2);
+        cudaStream_t s2 = (cudaStream_t)stream;
+        anova_partial_rt_kernel<<<g2, kAnovaThreads, 0, s2>>>(d_epochs_a, Na, d_epochs_b, Nb, CL2, d_order, gb, G, slab2,
+                                                             ps, pmn, pmx);
+        ECOG_TRY(check_launch("anova_partial_rt"));
+        anova_final_rt_kernel<<<(unsigned)ceil_div(CL2, kAnovaThreads), kAnovaThreads, 0, s2>>>(CL2, N2, ns2, gb, G, ps, pmn,
+                                                                                              pmx, d_F, d_p);
+        return check_launch("anova_final_rt");
+    }
     GroupCounts cnt;
     GroupStarts gs;
     int64_t tot = 0;
@@ -233,7 +351,7 @@ extern "C" int ecog_anova_f(const float* d_epochs_a, int64_t Na, const float* d_
     if (workspace_bytes < ecog_anova_workspace(C, L, N, G))
         return fail(ECOG_E_WORKSPACE, "ecog_anova_f: workspace %zu < %zu", workspace_bytes, ecog_anova_workspace(C, L, N, G));
     const int64_t CL = C * L;
-    const int gm = gmax_of(G), ns = anova_slabs(CL, N);
+    const int gm = gmax_of(G), ns = anova_slabs(CL, N, G);
     const int64_t slab = ceil_div(N, ns);
     double* psum = (double*)d_workspace;
     float* pmin = (float*)(psum + (size_t)ns * (gm + 1) * CL);

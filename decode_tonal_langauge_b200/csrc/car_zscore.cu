@@ -20,7 +20,7 @@ constexpr int kCarThreads = 256;
 
 template <int TT, bool VEC>
 __global__ void __launch_bounds__(kCarThreads)
-car_fused_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int64_t T, int64_t ld,
+car_fused_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int64_t T, int64_t ld, int64_t ldy,
                  const float* __restrict__ w, float inv_count) {
     extern __shared__ __align__(16) float smem[];
     constexpr int V = TT / 4;                 // float4 column groups
@@ -78,14 +78,14 @@ car_fused_kernel(const float* __restrict__ x, float* __restrict__ y, int C, int6
                 float4 a = *reinterpret_cast<const float4*>(&tile[row * TT + 4 * v]);
                 float4 m = *reinterpret_cast<const float4*>(&mean[4 * v]);
                 a.x -= m.x; a.y -= m.y; a.z -= m.z; a.w -= m.w;
-                stg_stream(reinterpret_cast<float4*>(y + (int64_t)row * ld + t), a);
+                stg_stream(reinterpret_cast<float4*>(y + (int64_t)row * ldy + t), a);
             }
         }
     } else {
         for (int i = tid; i < C * TT; i += kCarThreads) {
             int row = i / TT, v = i - row * TT;
             int64_t t = t0 + v;
-            if (t < T) y[(int64_t)row * ld + t] = tile[row * TT + v] - mean[v];
+            if (t < T) y[(int64_t)row * ldy + t] = tile[row * TT + v] - mean[v];
         }
     }
 }
@@ -116,7 +116,7 @@ car_colsum_kernel(const float* __restrict__ x, int C, int64_t T, int64_t ld,
 }
 
 __global__ void __launch_bounds__(256)
-car_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t ld,
+car_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t ld, int64_t ldy,
                  const float* __restrict__ colsum, float inv_count, bool vec) {
     const int64_t row = blockIdx.y;
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -126,10 +126,10 @@ car_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, 
         float4 v = ldg_stream(reinterpret_cast<const float4*>(x + row * ld + t));
         float4 m = *reinterpret_cast<const float4*>(colsum + t);
         v.x -= m.x * inv_count; v.y -= m.y * inv_count; v.z -= m.z * inv_count; v.w -= m.w * inv_count;
-        stg_stream(reinterpret_cast<float4*>(y + row * ld + t), v);
+        stg_stream(reinterpret_cast<float4*>(y + row * ldy + t), v);
     } else {
         if (i >= T) return;
-        y[row * ld + i] = x[row * ld + i] - colsum[i] * inv_count;
+        y[row * ldy + i] = x[row * ld + i] - colsum[i] * inv_count;
     }
 }
 
@@ -204,7 +204,7 @@ __global__ void row_stats_final_kernel(const float* __restrict__ x, int64_t ld, 
 }
 
 __global__ void __launch_bounds__(256)
-zscore_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t ld,
+zscore_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t ld, int64_t ldy,
                     const double* __restrict__ mean, const double* __restrict__ stdev,
                     int nan_to_zero, bool vec) {
     const int64_t row = blockIdx.y;
@@ -219,27 +219,27 @@ zscore_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t 
             if (isnan(v.x)) v.x = 0.f; if (isnan(v.y)) v.y = 0.f;
             if (isnan(v.z)) v.z = 0.f; if (isnan(v.w)) v.w = 0.f;
         }
-        stg_stream(reinterpret_cast<float4*>(y + row * ld + t), v);
+        stg_stream(reinterpret_cast<float4*>(y + row * ldy + t), v);
     } else {
         if (i >= T) return;
         float v = (x[row * ld + i] - m) / s;
         if (nan_to_zero && isnan(v)) v = 0.f;
-        y[row * ld + i] = v;
+        y[row * ldy + i] = v;
     }
 }
 
-static bool vec_ok(const void* a, const void* b, int64_t T, int64_t ld) {
-    return aligned16(a) && (b == nullptr || aligned16(b)) && (T % 4 == 0) && (ld % 4 == 0);
+static bool vec_ok(const void* a, const void* b, int64_t T, int64_t ld, int64_t ldy = 0) {
+    return aligned16(a) && (b == nullptr || aligned16(b)) && (T % 4 == 0) && (ld % 4 == 0) && (ldy % 4 == 0);
 }
 
 template <int TT, bool VEC>
-static int launch_car_fused(const float* x, float* y, int C, int64_t T, int64_t ld, const float* w,
+static int launch_car_fused(const float* x, float* y, int C, int64_t T, int64_t ld, int64_t ldy, const float* w,
                             float inv, cudaStream_t st) {
     constexpr int RG = kCarThreads / (TT / 4);
     size_t smem = ((size_t)C * TT + (size_t)RG * TT + TT) * sizeof(float);
     auto k = car_fused_kernel<TT, VEC>;
-    ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<(unsigned)ceil_div(T, TT), kCarThreads, smem, st>>>(x, y, C, T, ld, w, inv);
+    ECOG_TRY((smem_attr<car_fused_kernel<TT, VEC>>(smem)));
+    k<<<(unsigned)ceil_div(T, TT), kCarThreads, smem, st>>>(x, y, C, T, ld, ldy, w, inv);
     return check_launch("car_fused");
 }
 
@@ -251,12 +251,12 @@ extern "C" int ecog_abi_version(void) { return ECOG_ABI_VERSION; }
 extern "C" const char* ecog_last_error(void) { return g_err; }
 extern "C" int64_t ecog_launch_count(void) { return g_launches; }
 
-extern "C" int ecog_car(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ld,
+extern "C" int ecog_car(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ld, int64_t ldy,
                         const float* d_w, double inv_count, ecog_stream_t stream) {
-    if (C <= 0 || T <= 0 || ld < T) return fail(ECOG_E_VALUE, "ecog_car: bad shape C=%lld T=%lld ld=%lld",
-                                                 (long long)C, (long long)T, (long long)ld);
+    if (C <= 0 || T <= 0 || ld < T || ldy < T) return fail(ECOG_E_VALUE, "ecog_car: bad shape C=%lld T=%lld ld=%lld ldy=%lld",
+                                                 (long long)C, (long long)T, (long long)ld, (long long)ldy);
     cudaStream_t st = (cudaStream_t)stream;
-    const bool vec = vec_ok(d_x, d_y, T, ld);
+    const bool vec = vec_ok(d_x, d_y, T, ld, ldy);
     const float inv = (float)inv_count;
     // widest strip whose [C x TT] tile leaves room for three CTAs per SM, else one
     const size_t budget3 = 72 * 1024, budget1 = 200 * 1024;
@@ -267,13 +267,13 @@ extern "C" int ecog_car(const float* d_x, float* d_y, int64_t C, int64_t T, int6
     if (!tt) return fail(ECOG_E_UNSUPPORTED, "ecog_car: C=%lld too large for the fused strip; use colsum/apply",
                          (long long)C);
     if (vec) {
-        if (tt == 128) return launch_car_fused<128, true>(d_x, d_y, (int)C, T, ld, d_w, inv, st);
-        if (tt == 64) return launch_car_fused<64, true>(d_x, d_y, (int)C, T, ld, d_w, inv, st);
-        return launch_car_fused<32, true>(d_x, d_y, (int)C, T, ld, d_w, inv, st);
+        if (tt == 128) return launch_car_fused<128, true>(d_x, d_y, (int)C, T, ld, ldy, d_w, inv, st);
+        if (tt == 64) return launch_car_fused<64, true>(d_x, d_y, (int)C, T, ld, ldy, d_w, inv, st);
+        return launch_car_fused<32, true>(d_x, d_y, (int)C, T, ld, ldy, d_w, inv, st);
     }
-    if (tt == 128) return launch_car_fused<128, false>(d_x, d_y, (int)C, T, ld, d_w, inv, st);
-    if (tt == 64) return launch_car_fused<64, false>(d_x, d_y, (int)C, T, ld, d_w, inv, st);
-    return launch_car_fused<32, false>(d_x, d_y, (int)C, T, ld, d_w, inv, st);
+    if (tt == 128) return launch_car_fused<128, false>(d_x, d_y, (int)C, T, ld, ldy, d_w, inv, st);
+    if (tt == 64) return launch_car_fused<64, false>(d_x, d_y, (int)C, T, ld, ldy, d_w, inv, st);
+    return launch_car_fused<32, false>(d_x, d_y, (int)C, T, ld, ldy, d_w, inv, st);
 }
 
 extern "C" int ecog_car_colsum(const float* d_x, int64_t C, int64_t T, int64_t ld, const float* d_w,
@@ -286,13 +286,13 @@ extern "C" int ecog_car_colsum(const float* d_x, int64_t C, int64_t T, int64_t l
     return check_launch("car_colsum");
 }
 
-extern "C" int ecog_car_apply(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ld,
+extern "C" int ecog_car_apply(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ld, int64_t ldy,
                               const float* d_colsum, double inv_count, ecog_stream_t stream) {
-    if (C <= 0 || T <= 0 || ld < T || C > 65535) return fail(ECOG_E_VALUE, "ecog_car_apply: bad shape");
-    const bool vec = vec_ok(d_x, d_y, T, ld) && aligned16(d_colsum);
+    if (C <= 0 || T <= 0 || ld < T || ldy < T || C > 65535) return fail(ECOG_E_VALUE, "ecog_car_apply: bad shape");
+    const bool vec = vec_ok(d_x, d_y, T, ld, ldy) && aligned16(d_colsum);
     int64_t n = vec ? T / 4 : T;
     dim3 grid((unsigned)ceil_div(n, 256), (unsigned)C);
-    car_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_y, T, ld, d_colsum, (float)inv_count, vec);
+    car_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_y, T, ld, ldy, d_colsum, (float)inv_count, vec);
     return check_launch("car_apply");
 }
 
@@ -321,13 +321,22 @@ extern "C" int ecog_row_stats(const float* d_x, int64_t C, int64_t T, int64_t ld
     return check_launch("row_stats_final");
 }
 
-extern "C" int ecog_zscore_apply(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ld,
+extern "C" int ecog_zscore_apply(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ld, int64_t ldy,
                                  const double* d_mean, const double* d_std, int nan_to_zero,
                                  ecog_stream_t stream) {
-    if (C <= 0 || T <= 0 || ld < T || C > 65535) return fail(ECOG_E_VALUE, "ecog_zscore_apply: bad shape");
-    const bool vec = vec_ok(d_x, d_y, T, ld);
+    if (C <= 0 || T <= 0 || ld < T || ldy < T || C > 65535) return fail(ECOG_E_VALUE, "ecog_zscore_apply: bad shape");
+    const bool vec = vec_ok(d_x, d_y, T, ld, ldy);
     int64_t n = vec ? T / 4 : T;
     dim3 grid((unsigned)ceil_div(n, 256), (unsigned)C);
-    zscore_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_y, T, ld, d_mean, d_std, nan_to_zero, vec);
+    zscore_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_x, d_y, T, ld, ldy, d_mean, d_std, nan_to_zero, vec);
     return check_launch("zscore_apply");
+}
+
+extern "C" int ecog_copy2d(const float* d_src, int64_t ld_src, float* d_dst, int64_t ld_dst, int64_t rows,
+                           int64_t cols, ecog_stream_t stream) {
+    if (rows <= 0 || cols <= 0 || ld_src < cols || ld_dst < cols) return fail(ECOG_E_VALUE, "ecog_copy2d: bad shape");
+    ECOG_CUDA(cudaMemcpy2DAsync(d_dst, (size_t)ld_dst * sizeof(float), d_src, (size_t)ld_src * sizeof(float),
+                                (size_t)cols * sizeof(float), (size_t)rows, cudaMemcpyDeviceToDevice,
+                                (cudaStream_t)stream));
+    return ECOG_OK;
 }

@@ -43,6 +43,21 @@ inline int check_launch(const char* what) {
             return ::ecog::fail(ECOG_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e));    \
     } while (0)
 
+// Opt a kernel instance in to `smem` bytes of dynamic shared memory: issued once per kernel, device
+// and size (grow only), not on every launch.
+template <auto K>
+inline int smem_attr(size_t smem) {
+    static size_t cur[64] = {};
+    int dev = 0;
+    ECOG_CUDA(cudaGetDevice(&dev));
+    const bool track = dev >= 0 && dev < 64;
+    if (!track || smem > cur[dev]) {
+        ECOG_CUDA(cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (track) cur[dev] = smem;
+    }
+    return ECOG_OK;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

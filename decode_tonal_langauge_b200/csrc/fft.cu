@@ -420,11 +420,11 @@ static int launch_pass(PassParams& P, int64_t C, cudaStream_t st, const char* wh
     P.tw_shared = tile_bytes + tw_bytes <= one ? 1 : 0;
     const size_t smem = tile_bytes + (P.tw_shared ? tw_bytes : 0);
     if (use8) {
-        ECOG_CUDA(cudaFuncSetAttribute(fft_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ECOG_TRY((smem_attr<fft_tile_kernel<8>>(smem)));
         dim3 grid((unsigned)ceil_div(P.m, 8), (unsigned)C);
         fft_tile_kernel<8><<<grid, kFftThreads, smem, st>>>(P);
     } else {
-        ECOG_CUDA(cudaFuncSetAttribute(fft_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ECOG_TRY((smem_attr<fft_tile_kernel<4>>(smem)));
         dim3 grid((unsigned)ceil_div(P.m, 4), (unsigned)C);
         fft_tile_kernel<4><<<grid, kFftThreads, smem, st>>>(P);
     }

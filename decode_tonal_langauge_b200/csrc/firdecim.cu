@@ -100,11 +100,11 @@ static int launch_fir(const float* x, float* y, int64_t C, int64_t T, int64_t ld
     dim3 grid((unsigned)ceil_div(T1, (int64_t)kFirThreads * R), (unsigned)C);
     if (vec) {
         auto k = fir_decimate_kernel<D, NT4, R, true>;
-        ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ECOG_TRY((smem_attr<fir_decimate_kernel<D, NT4, R, true>>(smem)));
         k<<<grid, kFirThreads, smem, st>>>(x, y, T, T1, ldx, ldy, off, taps);
     } else {
         auto k = fir_decimate_kernel<D, NT4, R, false>;
-        ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ECOG_TRY((smem_attr<fir_decimate_kernel<D, NT4, R, false>>(smem)));
         k<<<grid, kFirThreads, smem, st>>>(x, y, T, T1, ldx, ldy, off, taps);
     }
     return check_launch("fir_decimate");
@@ -226,7 +226,7 @@ extern "C" int ecog_fir_causal(const float* d_x, float* d_y, int64_t C, int64_t 
     const bool vec = aligned16(d_x) && aligned16(d_y) && ldx % 4 == 0 && ldy % 4 == 0;
     const int span4 = (kFirR / 4) * kFirThreads + ntaps4 + 1;
     const size_t smem = (size_t)(span4 + span4 / (kFirR / 4) + 1 + ntaps4) * sizeof(float4);
-    ECOG_CUDA(cudaFuncSetAttribute(fir_causal_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ECOG_TRY((smem_attr<fir_causal_kernel>(smem)));
     dim3 grid((unsigned)ceil_div(T, (int64_t)kFirThreads * kFirR), (unsigned)C);
     fir_causal_kernel<<<grid, kFirThreads, smem, (cudaStream_t)stream>>>(d_x, d_y, T, ldx, ldy, d_taps_rev, ntaps4, vec);
     return check_launch("fir_causal");

@@ -189,7 +189,7 @@ template <int CNT>
 __global__ void __launch_bounds__(kHT, 2)
 hilbert_env_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t ldx, int64_t ldy,
                    const float* __restrict__ gain, int nb, BandShift shift, int halo, int envelope,
-                   const float2* __restrict__ tw, int64_t nBlocks) {
+                   const float2* __restrict__ tw, int64_t nBlocks, const float* __restrict__ colsum, float inv_count) {
     extern __shared__ __align__(16) float2 hsm[];
     float2* bufA = hsm;                       // [4096 + 256]  conj spectra of block 0 | block 1 (2048 each)
     float2* bufB = hsm + (kN + kN / 16);      // [4096 + 256]  exchange buffer
@@ -217,12 +217,25 @@ hilbert_env_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T
                 v[n2].x = xr[s0 + i];
                 v[n2].y = has1 ? xr[s1 + i] : 0.f;
             }
+            if (colsum) {     // common-average reference folded into the load: x - (1/n) sum_c w_c x_c
+#pragma unroll
+                for (int n2 = 0; n2 < 16; ++n2) {
+                    const int i = 256 * n2 + tid;
+                    v[n2].x = fmaf(-inv_count, __ldg(colsum + s0 + i), v[n2].x);
+                    if (has1) v[n2].y = fmaf(-inv_count, __ldg(colsum + s1 + i), v[n2].y);
+                }
+            }
         } else {
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) {
                 const int i = 256 * n2 + tid;
-                v[n2].x = xr[(s0 + i) % T];
-                v[n2].y = has1 ? xr[(s1 + i) % T] : 0.f;
+                const int64_t i0 = (s0 + i) % T, i1 = (s1 + i) % T;
+                v[n2].x = xr[i0];
+                v[n2].y = has1 ? xr[i1] : 0.f;
+                if (colsum) {
+                    v[n2].x = fmaf(-inv_count, __ldg(colsum + i0), v[n2].x);
+                    if (has1) v[n2].y = fmaf(-inv_count, __ldg(colsum + i1), v[n2].y);
+                }
             }
         }
     }
@@ -380,7 +393,7 @@ template <bool ENV, bool EDGE>
 __global__ void __launch_bounds__(kHT, 2)
 hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t ldx, int64_t ldy,
                     const float* __restrict__ gain, int nb, BandShift shift, int halo,
-                    const float2* __restrict__ tw, int64_t nBlocks) {
+                    const float2* __restrict__ tw, int64_t nBlocks, const float* __restrict__ colsum, float inv_count) {
     extern __shared__ __align__(16) float2 hsm[];
     float2* bufA = hsm;                                   // [4608] forward exchange buffer / inverse exchange
     float2* bufB = bufA + kXchg;                          // [4096 + 256] natural-order spectrum / output staging
@@ -411,12 +424,25 @@ hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t 
                 v[n2].x = xr[s0 + i];
                 v[n2].y = has1 ? xr[s1 + i] : 0.f;
             }
+            if (colsum) {     // common-average reference folded into the load: x - (1/n) sum_c w_c x_c
+#pragma unroll
+                for (int n2 = 0; n2 < 16; ++n2) {
+                    const int i = 256 * n2 + tid;
+                    v[n2].x = fmaf(-inv_count, __ldg(colsum + s0 + i), v[n2].x);
+                    if (has1) v[n2].y = fmaf(-inv_count, __ldg(colsum + s1 + i), v[n2].y);
+                }
+            }
         } else {
 #pragma unroll
             for (int n2 = 0; n2 < 16; ++n2) {
                 const int i = 256 * n2 + tid;
-                v[n2].x = xr[(s0 + i) % T];
-                v[n2].y = has1 ? xr[(s1 + i) % T] : 0.f;
+                const int64_t i0 = (s0 + i) % T, i1 = (s1 + i) % T;
+                v[n2].x = xr[i0];
+                v[n2].y = has1 ? xr[i1] : 0.f;
+                if (colsum) {
+                    v[n2].x = fmaf(-inv_count, __ldg(colsum + i0), v[n2].x);
+                    if (has1) v[n2].y = fmaf(-inv_count, __ldg(colsum + i1), v[n2].y);
+                }
             }
         }
     }
@@ -539,7 +565,7 @@ extern "C" int ecog_hilbert_twiddles(float* h_out) {
 extern "C" int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                                 const float* d_gain, int32_t nbands, int32_t rows, const int32_t* h_shift,
                                 const int32_t* h_nz, int32_t halo, int32_t envelope, const float* d_twiddle,
-                                ecog_stream_t stream) {
+                                const float* d_colsum, double inv_count, ecog_stream_t stream) {
     if (C <= 0 || T <= 0 || ldx < T || ldy < T || C > 65535) return fail(ECOG_E_VALUE, "ecog_hilbert_env: bad shape");
     if (nbands < 1 || nbands > 64) return fail(ECOG_E_VALUE, "ecog_hilbert_env: 1..64 bands supported, got %d", nbands);
     if (rows != 1 && rows != 2 && rows != 4 && rows != 8)
@@ -570,10 +596,9 @@ extern "C" int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t
         const size_t smem8 = kFastSmem;
 #define ECOG_HILBERT8(ENVV, EDGEV)                                                                                  \
     do {                                                                                                            \
-        ECOG_CUDA(cudaFuncSetAttribute(hilbert_env8_kernel<ENVV, EDGEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                       (int)smem8));                                                                \
+        ECOG_TRY((smem_attr<hilbert_env8_kernel<ENVV, EDGEV>>(smem8)));                                             \
         hilbert_env8_kernel<ENVV, EDGEV><<<grid, kHT, smem8, st>>>(d_x, d_y, T, ldx, ldy, d_gain, nbands, sh, halo,  \
-                                                                   tw, nBlocks);                                    \
+                                                                   tw, nBlocks, d_colsum, (float)inv_count);        \
     } while (0)
         const bool edge = halo < 256;
         if (envelope && edge) ECOG_HILBERT8(true, true);
@@ -585,10 +610,9 @@ extern "C" int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t
     }
 #define ECOG_HILBERT_LAUNCH(R)                                                                                   \
     do {                                                                                                         \
-        ECOG_CUDA(cudaFuncSetAttribute(hilbert_env_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
-                                       (int)smem));                                                              \
+        ECOG_TRY((smem_attr<hilbert_env_kernel<R>>(smem)));                                                      \
         hilbert_env_kernel<R><<<grid, kHT, smem, st>>>(d_x, d_y, T, ldx, ldy, d_gain, nbands, sh, halo, envelope, \
-                                                       tw, nBlocks);                                             \
+                                                       tw, nBlocks, d_colsum, (float)inv_count);                 \
     } while (0)
     if (rows == 1) ECOG_HILBERT_LAUNCH(1);
     else if (rows == 2) ECOG_HILBERT_LAUNCH(2);

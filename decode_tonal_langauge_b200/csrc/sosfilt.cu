@@ -44,17 +44,29 @@ struct SosMatrix { double m[2 * ECOG_MAX_SECTIONS][2 * ECOG_MAX_SECTIONS]; };
 //   5  unit form with b1 == 0 and b2 == -1, the (1 - z^-2) sections of a Butterworth band-pass
 //                                                         3, and one multiply per sample
 // In the unit forms c[j][1] holds beta1 = b1 / b0; the states are those of the general form.
-template <int NSEC, int NUM = 0>
-__device__ __forceinline__ double sos_step(double u, const double (&c)[NSEC][5], double (&s)[NSEC][2]) {
+template <int J0, int J1, int NUM, int NSEC>
+__device__ __forceinline__ double sos_range(double u, const double (&c)[NSEC][5], double (&s)[NSEC][2]) {
     constexpr bool B1Z = (NUM & 1) != 0;
     constexpr int UNIT = NUM >> 1;              // 0 general, 1: b0 = 1, b2 = +1, 2: b0 = 1, b2 = -1
 #pragma unroll
-    for (int j = 0; j < NSEC; ++j) {
+    for (int j = J0; j < J1; ++j) {
         const double y = UNIT ? u + s[j][0] : fma(c[j][0], u, s[j][0]);
         s[j][0] = B1Z ? fma(-c[j][3], y, s[j][1]) : fma(-c[j][3], y, fma(c[j][1], u, s[j][1]));
         s[j][1] = UNIT == 1 ? fma(-c[j][4], y, u) : UNIT == 2 ? fma(-c[j][4], y, -u) : fma(-c[j][4], y, c[j][2] * u);
         u = y;
     }
+    return u;
+}
+
+// NUMB < 0: one numerator form for the whole cascade.  NUMB >= 0: a PAIR of 4-section cascades run
+// as one (NSEC == 8): sections 0-3 in form NUM, sections 4-7 in form NUMB (both unit forms, the
+// product of the two gains rides on the input); `full` = false runs the first cascade only (early
+// warm-up: the second cascade forgets faster and starts later from a zero state).
+template <int NSEC, int NUM = 0, int NUMB = -1>
+__device__ __forceinline__ double sos_step(double u, const double (&c)[NSEC][5], double (&s)[NSEC][2], bool full = true) {
+    if (NUMB < 0) return sos_range<0, NSEC, NUM, NSEC>(u, c, s);
+    u = sos_range<0, NSEC / 2, NUM, NSEC>(u, c, s);
+    if (full) u = sos_range<NSEC / 2, NSEC, (NUMB < 0 ? 0 : NUMB), NSEC>(u, c, s);
     return u;
 }
 
@@ -338,11 +350,11 @@ sos_scan_kernel(const float* __restrict__ x, int64_t C, int64_t T, int64_t ldx,
 // (few DRAM pages / TLB entries live per CTA).
 // The backward sweep cannot run in place (its warm-up reads the forward result of the
 // neighbouring chunk), so the forward result lives in the workspace.
-template <int NSEC, bool REV, bool VEC, int NT, int NUM>
+template <int NSEC, bool REV, bool VEC, int NT, int NUM, int NUMB = -1>
 __global__ void __launch_bounds__(NT, 512 / NT)
 sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, int64_t T,
                 int64_t ldx, int64_t ldy, int L, int tail, int nChunks, int padlen, int zero_phase,
-                SosCoef coef, double* __restrict__ padbuf, double gain) {
+                SosCoef coef, double* __restrict__ padbuf, double gain, int tail_b) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tiles = reinterpret_cast<float*>(smem_raw);                                   // [kWarmRing][NT][kWPitch]
     int64_t* soff = reinterpret_cast<int64_t*>(tiles + (size_t)kWarmRing * NT * kWPitch); // [NT] x offset of the chunk edge
@@ -386,6 +398,9 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
     // chunks that see the row edge get the exact start-up at the stage where the row starts
     const int64_t before = REV ? T - edge : edge;
     const int s_inject = valid && before <= tail ? -(int)(before / kWSub) : (1 << 30);
+    // cascade pair: the second cascade joins the warm-up tail_b samples before the chunk (or at the
+    // exact start-up of a chunk that sees the row edge)
+    const int s_full = NUMB < 0 ? -(1 << 30) : (s_inject < -(tail_b / kWSub) ? s_inject : -(tail_b / kWSub));
 
     const int nStages = L / kWSub;
     const int first = -(tail / kWSub);
@@ -438,14 +453,14 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
                 for (int j = 0; j < NSEC; ++j) { s[j][0] = coef.zi[j][0] * (double)e0; s[j][1] = coef.zi[j][1] * (double)e0; }
                 for (int i = 0; i < padlen; ++i) {
                     const float e = 2.0f * x0 - xr[padlen - i];
-                    (void)sos_step<NSEC, NUM>(IN((double)e), c, s);
+                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)e), c, s);
                 }
             } else {
                 const double* pb = padbuf + row * padlen;
                 const double y0 = pb[padlen - 1];
 #pragma unroll
                 for (int j = 0; j < NSEC; ++j) { s[j][0] = coef.zi[j][0] * y0; s[j][1] = coef.zi[j][1] * y0; }
-                for (int i = padlen - 1; i >= 0; --i) (void)sos_step<NSEC, NUM>(IN(pb[i]), c, s);
+                for (int i = padlen - 1; i >= 0; --i) (void)sos_step<NSEC, NUM, NUMB>(IN(pb[i]), c, s);
             }
         }
         float* tile = tiles + (size_t)((st - first) % kWarmRing) * NT * kWPitch;
@@ -463,14 +478,24 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
         }
         const bool write = st >= 0;
         const int sbase = st * kWSub;
-        if (sbase >= ulo && sbase + kWSub <= uhi) {          // whole stage inside the row: the common case
+        if (NUMB >= 0 && st < s_full) {                      // early warm-up of a pair: first cascade only, nothing stored
+            if (sbase >= ulo && sbase + kWSub <= uhi) {
+#pragma unroll
+                for (int v = 0; v < kWSub / 4; ++v) {
+                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].x), c, s, false);
+                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].y), c, s, false);
+                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].z), c, s, false);
+                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].w), c, s, false);
+                }
+            }
+        } else if (sbase >= ulo && sbase + kWSub <= uhi) {          // whole stage inside the row: the common case
 #pragma unroll
             for (int v = 0; v < kWSub / 4; ++v) {
                 float4 yv;
-                yv.x = (float)sos_step<NSEC, NUM>(IN((double)xin[v].x), c, s);
-                yv.y = (float)sos_step<NSEC, NUM>(IN((double)xin[v].y), c, s);
-                yv.z = (float)sos_step<NSEC, NUM>(IN((double)xin[v].z), c, s);
-                yv.w = (float)sos_step<NSEC, NUM>(IN((double)xin[v].w), c, s);
+                yv.x = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].x), c, s);
+                yv.y = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].y), c, s);
+                yv.z = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].z), c, s);
+                yv.w = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].w), c, s);
                 if (write) {
                     if (!REV) *reinterpret_cast<float4*>(mine + 4 * (v ^ swz)) = yv;
                     else *reinterpret_cast<float4*>(mine + 4 * ((PP - 1 - v) ^ swz)) = make_float4(yv.w, yv.z, yv.y, yv.x);
@@ -484,7 +509,7 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int u = sbase + 4 * v + e;
-                    if (u >= ulo && u < uhi) yv[e] = (float)sos_step<NSEC, NUM>(IN((double)xv[e]), c, s);
+                    if (u >= ulo && u < uhi) yv[e] = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xv[e]), c, s);
                 }
                 if (write) {
                     if (!REV) *reinterpret_cast<float4*>(mine + 4 * (v ^ swz)) = make_float4(yv[0], yv[1], yv[2], yv[3]);
@@ -527,7 +552,7 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
         double* pb = padbuf + row * padlen;
         for (int i = 0; i < padlen; ++i) {
             const float e = 2.0f * xe - xr[T - 2 - i];
-            pb[i] = sos_step<NSEC, NUM>(IN((double)e), c, s);
+            pb[i] = sos_step<NSEC, NUM, NUMB>(IN((double)e), c, s);
         }
     }
 }
@@ -541,14 +566,66 @@ static int launch_warm(const float* x, float* y, int64_t C, int64_t T, int64_t l
     const unsigned grid = (unsigned)ceil_div(C * nChunks, NT);
     if (vec) {
         auto k = sos_warm_kernel<NSEC, REV, true, NT, NUM>;
-        ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, NT, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, p.zero_phase, coef, padbuf, gain);
+        ECOG_TRY((smem_attr<sos_warm_kernel<NSEC, REV, true, NT, NUM>>(smem)));
+        k<<<grid, NT, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, p.zero_phase, coef, padbuf, gain, 0);
     } else {
         auto k = sos_warm_kernel<NSEC, REV, false, NT, NUM>;
-        ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, NT, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, p.zero_phase, coef, padbuf, gain);
+        ECOG_TRY((smem_attr<sos_warm_kernel<NSEC, REV, false, NT, NUM>>(smem)));
+        k<<<grid, NT, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, p.zero_phase, coef, padbuf, gain, 0);
     }
     return check_launch(REV ? "sos_warm_bwd" : "sos_warm_fwd");
+}
+
+// cascade pair (two 4-section unit-form cascades as one sweep): 512 threads, 128-bit copies only
+template <bool REV, int NUMA, int NUMB>
+static int launch_warm_pair(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                            const ecog_sos_plan& p, int nChunks, const SosCoef& coef, double gain, double* padbuf,
+                            cudaStream_t st) {
+    constexpr int NT = 512;
+    const size_t smem = ((size_t)kWarmRing * NT * kWPitch) * sizeof(float) + (size_t)NT * (2 * sizeof(int64_t) + sizeof(int2));
+    const unsigned grid = (unsigned)ceil_div(C * nChunks, NT);
+    auto k = sos_warm_kernel<8, REV, true, NT, NUMA, NUMB>;
+    ECOG_TRY((smem_attr<sos_warm_kernel<8, REV, true, NT, NUMA, NUMB>>(smem)));
+    k<<<grid, NT, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, p.zero_phase, coef, padbuf, gain,
+                              p.tail_b);
+    return check_launch(REV ? "sos_warm_pair_bwd" : "sos_warm_pair_fwd");
+}
+
+// numerator form of sections [j0, j1): 2 = unit (1 + beta z^-1 + z^-2), 5 = unit (1 - z^-2), 0 = general.
+// `lead` = the section allowed to carry the gain in b0.
+static int unit_form(const SosCoef& coef, int j0, int j1, int lead) {
+    bool b1z = true, unit_p = true, unit_m = true;
+    for (int j = j0; j < j1; ++j) {
+        const double b0 = coef.c[j][0], b2 = coef.c[j][2];
+        b1z = b1z && coef.c[j][1] == 0.0;
+        const bool b0ok = b0 != 0.0 && (j == lead || b0 == 1.0);
+        unit_p = unit_p && b0ok && b2 == b0;
+        unit_m = unit_m && b0ok && b2 == -b0;
+    }
+    return unit_p ? 2 : (unit_m && b1z ? 5 : 0);
+}
+
+static int run_sos_warm_pair(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                             const ecog_sos_plan& p, const SosCoef& coef_in, float* tmp, int64_t ldt, double* padbuf,
+                             cudaStream_t st) {
+    const int nChunks = (int)ceil_div(T, p.chunk);
+    const bool vec = aligned16(x) && aligned16(y) && aligned16(tmp) && T % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldt % 4 == 0;
+    if (!vec) return fail(ECOG_E_UNSUPPORTED, "ecog_sosfilt: the cascade pair needs 16-byte aligned rows (T, ld multiples of 4)");
+    if (!p.zero_phase) return fail(ECOG_E_UNSUPPORTED, "ecog_sosfilt: the cascade pair is a zero-phase path");
+    SosCoef coef = coef_in;
+    const int na = unit_form(coef, 0, 4, 0), nb = unit_form(coef, 4, 8, -1);
+    if (!na || !nb)
+        return fail(ECOG_E_UNSUPPORTED, "ecog_sosfilt: the cascade pair needs unit-form numerators (gain on section 0 only)");
+    const double gain = coef.c[0][0];
+    coef.c[0][1] /= gain;
+#define ECOG_PAIR(REVV, Y_IN, Y_OUT, LD_IN, LD_OUT)                                                                        \
+    (na == 2 && nb == 5 ? launch_warm_pair<REVV, 2, 5>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, st) \
+     : na == 5 && nb == 2 ? launch_warm_pair<REVV, 5, 2>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, st) \
+     : na == 2 ? launch_warm_pair<REVV, 2, 2>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, st)       \
+               : launch_warm_pair<REVV, 5, 5>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, st))
+    ECOG_TRY(ECOG_PAIR(false, x, tmp, ldx, ldt));
+    return ECOG_PAIR(true, tmp, y, ldt, ldy);
+#undef ECOG_PAIR
 }
 
 template <int NSEC>
@@ -562,18 +639,8 @@ static int run_sos_warm(const float* x, float* y, int64_t C, int64_t T, int64_t 
     const bool wide = p.threads >= 512;
     // numerator form: unit sections g (1 + beta1 z^-1 +- z^-2) with the gain on section 0 only
     SosCoef coef = coef_in;
-    bool b1z = true, unit_p = true, unit_m = true;
-    for (int j = 0; j < NSEC; ++j) {
-        const double b0 = coef.c[j][0], b2 = coef.c[j][2];
-        b1z = b1z && coef.c[j][1] == 0.0;
-        const bool b0ok = b0 != 0.0 && (j == 0 || b0 == 1.0);
-        unit_p = unit_p && b0ok && b2 == b0;
-        unit_m = unit_m && b0ok && b2 == -b0;
-    }
-    int num = 0;
+    const int num = unit_form(coef, 0, NSEC, 0);
     double gain = 1.0;
-    if (unit_p) num = 2;
-    else if (unit_m && b1z) num = 5;
     if (num) {
         gain = coef.c[0][0];
         coef.c[0][1] /= gain;
@@ -603,11 +670,11 @@ static int launch_chunk(const float* x, float* y, int64_t C, int64_t T, int64_t 
     const unsigned grid = (unsigned)ceil_div(C * nChunks, kSosThreads);
     if (vec) {
         auto k = sos_chunk_kernel<NSEC, REV, WRITE, true>;
-        ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ECOG_TRY((smem_attr<sos_chunk_kernel<NSEC, REV, WRITE, true>>(smem)));
         k<<<grid, kSosThreads, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, coef, state, gbuf, padbuf);
     } else {
         auto k = sos_chunk_kernel<NSEC, REV, WRITE, false>;
-        ECOG_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ECOG_TRY((smem_attr<sos_chunk_kernel<NSEC, REV, WRITE, false>>(smem)));
         k<<<grid, kSosThreads, smem, st>>>(x, y, C, T, ldx, ldy, p.chunk, p.tail, nChunks, p.padlen, coef, state, gbuf, padbuf);
     }
     return check_launch(WRITE ? "sos_main" : "sos_tail");
@@ -676,6 +743,7 @@ extern "C" int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, 
     }
     const int nChunks = (int)ceil_div(T, p.chunk);
     if (p.mode != ECOG_SOS_SCAN && p.mode != ECOG_SOS_WARMUP) return fail(ECOG_E_VALUE, "ecog_sosfilt: unknown mode %d", p.mode);
+    if (p.split && p.mode != ECOG_SOS_WARMUP) return fail(ECOG_E_VALUE, "ecog_sosfilt: the cascade pair runs in warm-up mode only");
     if (p.mode == ECOG_SOS_WARMUP && !p.zero_phase && d_x == d_y)
         return fail(ECOG_E_VALUE, "ecog_sosfilt: the causal warm-up path cannot run in place");
     if (p.mode == ECOG_SOS_SCAN && nChunks > 1 && !h_M)
@@ -714,6 +782,11 @@ extern "C" int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, 
         const size_t pad = align_up((size_t)C * (p.padlen > 0 ? p.padlen : 1) * sizeof(double), 256);
         float* tmp = (float*)((char*)d_workspace + pad);
         const int64_t ldt = warm_ld(T);
+        if (p.split) {
+            if (p.split != 4 || p.nsec != 8 || p.tail_b < 0 || p.tail_b % kSub || p.tail_b > p.tail)
+                return fail(ECOG_E_VALUE, "ecog_sosfilt: cascade pair needs nsec=8, split=4, 0 <= tail_b <= tail (multiples of %d)", kSub);
+            return run_sos_warm_pair(d_x, d_y, C, T, ldx, ldy, p, coef, tmp, ldt, padbuf, st);
+        }
         switch (ns) {
             case 1: return run_sos_warm<1>(d_x, d_y, C, T, ldx, ldy, p, coef, tmp, ldt, padbuf, st);
             case 2: return run_sos_warm<2>(d_x, d_y, C, T, ldx, ldy, p, coef, tmp, ldt, padbuf, st);

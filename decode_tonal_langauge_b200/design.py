@@ -329,6 +329,40 @@ def butter_design(freqs, fs, order=4, causal=False, filter_type="bandpass") -> S
     return _butter_design(int(order), freqs, float(fs), str(filter_type), bool(causal))
 
 
+def pair_design(A: SosDesign, B: SosDesign):
+    """Two 4-section zero-phase designs as ONE 8-section cascade for the fused sweep pair
+    (csrc/sosfilt.cu, split = 4): sections 0-3 = A with the product of both gains on section 0,
+    sections 4-7 = B with a monic first section.  Returns ``(design, tail_b)`` -- ``tail_b`` is the
+    warm-up length of the second cascade (it forgets faster than the pair and joins the warm-up
+    late) -- or None when either numerator is not of unit form."""
+    return _pair_design(A.sos.tobytes(), B.sos.tobytes(), A.padlen, B.padlen)
+
+
+@functools.lru_cache(maxsize=64)
+def _pair_design(a_bytes: bytes, b_bytes: bytes, pad_a: int, pad_b: int):
+    sa = np.frombuffer(a_bytes, dtype=np.float64).reshape(-1, 6).copy()
+    sb = np.frombuffer(b_bytes, dtype=np.float64).reshape(-1, 6).copy()
+    if sa.shape[0] != 4 or sb.shape[0] != 4:
+        return None
+
+    def unit(sos):
+        g = sos[0, 0]
+        ok = g != 0.0 and np.all(sos[1:, 0] == 1.0) and np.all(np.abs(sos[:, 2]) == np.abs(sos[:, 0]))
+        same = np.all(sos[:, 2] == sos[:, 0]) or (np.all(sos[:, 2] == -sos[:, 0]) and np.all(sos[:, 1] == 0.0))
+        return bool(ok and same and np.all(sos[:, 3] == 1.0))
+
+    if not (unit(sa) and unit(sb)):
+        return None
+    gb = sb[0, 0]
+    sb[0, :3] /= gb
+    sa[0, :3] *= gb
+    sos = np.ascontiguousarray(np.vstack([sa, sb]))
+    zi = sp_signal.sosfilt_zi(sos)          # unit-step steady state in the kernel's DF2T coordinates
+    dsg = SosDesign(sos, np.ascontiguousarray(zi), max(pad_a, pad_b), True)
+    tb = _warm_tail(np.ascontiguousarray(np.frombuffer(b_bytes, dtype=np.float64)).tobytes(), 4, 1 << 30)
+    return dsg, int(2 * tb)
+
+
 @functools.lru_cache(maxsize=256)
 def _chunk_ops(sos_bytes: bytes, nsec: int, chunk: int):
     sos = np.frombuffer(sos_bytes, dtype=np.float64).reshape(nsec, 6)

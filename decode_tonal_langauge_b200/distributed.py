@@ -44,7 +44,7 @@ def _default_backend():
 
 
 def car_sharded(x_local: torch.Tensor, c_lo: int, n_channels: int, exclude_channels: Sequence[int] = (),
-                group=None, backend=None) -> torch.Tensor:
+                group=None, backend=None, reduce=None) -> torch.Tensor:
     """CAR of a channel shard.  ``x_local`` holds global rows [c_lo, c_lo + x_local.shape[0])."""
     backend = backend or _default_backend()
     if not isinstance(exclude_channels, (list, tuple)):
@@ -59,39 +59,59 @@ def car_sharded(x_local: torch.Tensor, c_lo: int, n_channels: int, exclude_chann
         w[local_excl] = 0.0
         weights = torch.from_numpy(w).to(x_local.device)
     partial = backend.car_colsum(x_local, weights)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+    if reduce is not None:
+        reduce(partial)
+    elif dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)     # T floats over NVLink
     n_included = n_channels - len(set(exclude_channels))
     return backend.car_apply(x_local, partial, n_included)
 
 
 def preprocess_signal_sharded(x_local, steps: List[dict], block_params: Namespace, c_lo: int, n_channels: int,
-                              group=None, backend=None):
+                              group=None, backend=None, fuse: Optional[bool] = None, timing: Optional[list] = None):
     """``preprocess_signal`` for a channel shard resident on this rank's device: identical step
-    semantics, except that ``car_rereference`` exchanges the column sums.  Returns
-    ``(local tensor, signal_freq, bands)`` where ``bands`` is the number of concatenated
-    band copies the local rows are organised in (see ``gather_channels``)."""
-    from . import steps as S
-    from .preprocessor import _resolve
+    semantics (same shared parameter Namespace, same fusion groups), except that the CAR column
+    sums are all-reduced between the two kernel enqueues.  Returns ``(local tensor, signal_freq,
+    bands)`` where ``bands`` is the number of concatenated band copies the local rows are organised
+    in (see ``gather_channels``).  ``timing``: optional list; a (start, end) CUDA-event pair is appended
+    around every all-reduce (recorded on the current stream)."""
+    from . import preprocessor as P
     x = x_local
     bands = 1
-    for step in steps:
-        scope = Namespace(**vars(block_params))
-        for k, v in (step.get("params") or {}).items():
-            setattr(scope, k, deepcopy(v))
-        name, fn = _resolve(step["module"])
-        if name == "car_rereference":
-            excl = getattr(scope, "exclude_channels", [])
+    plain = backend is not None            # the CPU test-suite's numpy backend has no fused kernels
+    groups = P.fusion_groups(steps) if (P.fusion_enabled(fuse) and not plain) else [("step", s) for s in steps]
+
+    def reduce(colsum):
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return
+        if timing is not None and colsum.is_cuda:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dist.all_reduce(colsum, op=dist.ReduceOp.SUM, group=group)
+            e1.record()
+            timing.append((e0, e1))
+        else:
+            dist.all_reduce(colsum, op=dist.ReduceOp.SUM, group=group)
+
+    for g in groups:
+        if g[0] == "step" and P._short(g[1]) == "car_rereference":
+            P.apply_step_params(block_params, g[1])
+            excl = getattr(block_params, "exclude_channels", None)
+            if excl is None:
+                excl = block_params.exclude_channels = []
             # after a multi-band frequency_filter the global layout is band-major; CAR then spans
             # bands * n_channels rows and this shard holds `bands` disjoint slices of them
             if bands != 1:
                 raise NotImplementedError("channel-sharded CAR after a multi-band frequency_filter")
-            x = car_sharded(x, c_lo, n_channels, excl, group, backend)
+            x = car_sharded(x, c_lo, n_channels, excl, group, backend, reduce=reduce)
+        elif g[0] == "car_hilbert":
+            if bands != 1:
+                raise NotImplementedError("channel-sharded CAR after a multi-band frequency_filter")
+            x = P._run_group(x, g, block_params, False, shard=(c_lo, n_channels, reduce))
         else:
-            x = fn(x, scope)
-            if name == "frequency_filter":
-                bands *= max(1, len(getattr(scope, "bands", []) or []))
-        block_params.signal_freq = scope.signal_freq
+            x = P._run_group(x, g, block_params, False)
+            if g[0] == "step" and P._short(g[1]) == "frequency_filter":
+                bands *= max(1, len(getattr(block_params, "bands", []) or []))
     return x, block_params.signal_freq, bands
 
 

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+from collections import OrderedDict
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -70,19 +71,46 @@ def workspace(nbytes: int, device, tag: str = "default") -> torch.Tensor:
 
 
 def release_workspaces() -> None:
+    """Drop every scratch buffer and every cached device table (they are rebuilt on demand)."""
     _workspaces.clear()
+    _tables.clear()
+    _pinned_tables.clear()
 
 
-_tables = {}
+# Device-side tables (twiddles, gains, FIR taps, per-length resample / chirp-z tables).  The
+# per-length entries are O(T) each, and real recording lengths differ from block to block, so the
+# cache is an LRU with a byte budget; small length-independent tables are pinned and never evicted.
+TABLE_CACHE_BYTES = int(os.environ.get("ECOG_TABLE_CACHE_BYTES", str(1 << 30)))
+_PINNED_TABLE_BYTES = 1 << 20
+_tables: "OrderedDict" = OrderedDict()
+_pinned_tables = {}
+_table_bytes = 0
 
 
 def _dev_table(key, make, device):
     k = (str(device), key)
+    t = _pinned_tables.get(k)
+    if t is not None:
+        return t
     t = _tables.get(k)
-    if t is None:
-        t = torch.from_numpy(np.ascontiguousarray(make())).to(device)
-        _tables[k] = t
+    if t is not None:
+        _tables.move_to_end(k)
+        return t
+    t = torch.from_numpy(np.ascontiguousarray(make())).to(device)
+    nbytes = t.numel() * t.element_size()
+    if nbytes <= _PINNED_TABLE_BYTES and key[0] in ("hilbert_tw", "hilbert_gain", "fir_taps"):
+        _pinned_tables[k] = t
+        return t
+    _tables[k] = t
+    total = sum(v.numel() * v.element_size() for v in _tables.values())
+    while total > TABLE_CACHE_BYTES and len(_tables) > 1:
+        _, old = _tables.popitem(last=False)         # least recently used; the caller still holds what it needs
+        total -= old.numel() * old.element_size()
     return t
+
+
+def table_cache_bytes() -> int:
+    return sum(v.numel() * v.element_size() for v in _tables.values())
 
 
 # ------------------------------------------------------------------------ K1
@@ -90,9 +118,17 @@ def car(x: torch.Tensor, exclude_channels: Sequence[int] = ()) -> torch.Tensor:
     x = as_signal(x)
     Cn, T = x.shape
     w, n_inc = _car_weights(Cn, exclude_channels, x.device)
-    y = torch.empty_like(x, memory_format=torch.contiguous_format)
-    nat.check(lib.ecog_car(_ptr(x), _ptr(y), Cn, T, _ld(x), _ptr(w), 1.0 / n_inc, _stream()))
+    if Cn > CAR_FUSED_MAX_CHANNELS:
+        # the [C x 32] strip of the fused kernel no longer fits in shared memory (e.g. 256 channels
+        # after an 8-band frequency_filter): column sums, then subtract -- same arithmetic
+        return car_apply(x, car_colsum(x, w), n_inc)
+    y = torch.empty((Cn, T), dtype=torch.float32, device=x.device)
+    nat.check(lib.ecog_car(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), _ptr(w), 1.0 / n_inc, _stream()))
     return y
+
+
+# largest channel count whose [C x 32] float strip (+ partial sums) fits the fused kernel's 200 KB budget
+CAR_FUSED_MAX_CHANNELS = (200 * 1024 // 4 - 32 * 32 - 32) // 32      # 1567 (csrc/car_zscore.cu, ecog_car)
 
 
 def _car_weights(Cn, exclude_channels, device):
@@ -120,8 +156,8 @@ def car_apply(x: torch.Tensor, colsum: torch.Tensor, n_included: int) -> torch.T
     """Phase 2: subtract the (all-reduced) column sum divided by the global included count."""
     x = as_signal(x)
     Cn, T = x.shape
-    y = torch.empty_like(x, memory_format=torch.contiguous_format)
-    nat.check(lib.ecog_car_apply(_ptr(x), _ptr(y), Cn, T, _ld(x), _ptr(colsum), 1.0 / n_included, _stream()))
+    y = torch.empty((Cn, T), dtype=torch.float32, device=x.device)
+    nat.check(lib.ecog_car_apply(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), _ptr(colsum), 1.0 / n_included, _stream()))
     return y
 
 
@@ -142,8 +178,8 @@ def row_stats(x: torch.Tensor, t0: int = 0, t1: Optional[int] = None) -> Tuple[t
 def zscore(x: torch.Tensor, t0: int = 0, t1: Optional[int] = None, nan_to_zero: bool = False) -> torch.Tensor:
     x = as_signal(x)
     mean, std = row_stats(x, t0, t1)
-    y = torch.empty_like(x, memory_format=torch.contiguous_format)
-    nat.check(lib.ecog_zscore_apply(_ptr(x), _ptr(y), x.shape[0], x.shape[1], _ld(x), _ptr(mean), _ptr(std),
+    y = torch.empty(tuple(x.shape), dtype=torch.float32, device=x.device)
+    nat.check(lib.ecog_zscore_apply(_ptr(x), _ptr(y), x.shape[0], x.shape[1], _ld(x), _ld(y), _ptr(mean), _ptr(std),
                                     1 if nan_to_zero else 0, _stream()))
     return y
 
@@ -162,7 +198,7 @@ def sosfilt(x: torch.Tensor, dsg: D.SosDesign, chunk: Optional[int] = None,
     Cn, T = x.shape
     if dsg.zero_phase and T <= dsg.padlen:
         raise ValueError(f"The length of the input vector x must be greater than padlen, which is {dsg.padlen}.")
-    y = out if out is not None else torch.empty_like(x, memory_format=torch.contiguous_format)
+    y = out if out is not None else torch.empty((Cn, T), dtype=torch.float32, device=x.device)
     sos = np.ascontiguousarray(dsg.sos, dtype=np.float64)
     zi = None if dsg.zi is None else np.ascontiguousarray(dsg.zi, dtype=np.float64)
     Mh = None
@@ -196,6 +232,75 @@ def sosfilt(x: torch.Tensor, dsg: D.SosDesign, chunk: Optional[int] = None,
     return y
 
 
+def copy2d(dst: torch.Tensor, src: torch.Tensor) -> None:
+    """dst[:, :] = src[:, :] for float32 row-major views (device-to-device, on the current stream)."""
+    if dst.shape != src.shape or dst.dtype != torch.float32 or src.dtype != torch.float32:
+        raise ValueError("copy2d needs two float32 tensors of the same shape")
+    if dst.stride(1) != 1 or src.stride(1) != 1:
+        raise ValueError("copy2d needs contiguous rows")
+    nat.check(lib.ecog_copy2d(_ptr(src), _ld(src), _ptr(dst), _ld(dst), int(src.shape[0]), int(src.shape[1]), _stream()))
+
+
+def pair_plan(Cn: int, T: int, ld_ok: bool, A: D.SosDesign, B: D.SosDesign):
+    """Plan of the fused cascade pair for a (Cn, T) recording, or None when the pair cannot run
+    (short rows, too few chunks for the 512-thread kernel, non-unit numerators, misaligned rows)."""
+    if not (A.zero_phase and B.zero_phase and A.nsec == 4 and B.nsec == 4 and ld_ok and T % 4 == 0):
+        return None
+    comb = D.pair_design(A, B)
+    if comb is None:
+        return None
+    dsg, tail_b = comb
+    L = D.choose_warm_chunk(Cn, T, _sos_threads_per_sm())
+    n_chunks = -(-T // L)
+    if n_chunks < 2 or Cn * n_chunks < 2 * D.NUM_SMS * 512:
+        return None
+    # forgetting time judged in the two filters' own state scaling (folding both gains onto the input
+    # only rescales the first cascade's states; it does not make the pair remember longer)
+    natural = D.SosDesign(np.ascontiguousarray(np.vstack([A.sos, B.sos])), None, dsg.padlen, True)
+    tail = D.warm_tail(natural, min(int(D.WARM_MAX_OVERHEAD * L), T + D.SUB))
+    if tail < 0 or 4 * tail + 64 > T:
+        return None
+    plan = nat.SosPlan(8, 1, dsg.padlen, L, tail, nat.SOS_WARMUP, 512, 4, min(tail_b, tail))
+    return dsg, plan, tail
+
+
+def sosfilt_pair(x: torch.Tensor, A: D.SosDesign, B: D.SosDesign, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``filtfilt_B(filtfilt_A(x))`` (two consecutive zero-phase Butterworth steps of the reference chain,
+    ref: frequency_filter.py:218-229 twice) in ONE forward and ONE backward sweep.
+
+    Away from the row ends the four sweeps F_A, B_A, F_B, B_B are LTI and commute, so
+    B_B F_B B_A F_A = (B_A B_B)(F_A F_B): an 8-section cascade per direction (ecog_sosfilt, split = 4).
+    Within ``tail`` samples of a row end (``max|A^tail| < 1e-10`` for the pair) the padded start-ups do
+    not commute; those samples are recomputed exactly, by the sequential four-sweep path on the
+    first / last ``2 tail`` samples of every row (their inner halves are discarded), and overwrite the
+    pair's result.  Falls back to the two sequential filtfilts when the pair does not apply."""
+    x = as_signal(x)
+    Cn, T = x.shape
+    y = out if out is not None else torch.empty((Cn, T), dtype=torch.float32, device=x.device)
+    ld_ok = _ld(x) % 4 == 0 and _ld(y) % 4 == 0 and x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0
+    pp = pair_plan(Cn, T, ld_ok, A, B)
+    if pp is None:
+        return sosfilt(sosfilt(x, A), B, out=out)
+    dsg, plan, V = pp
+    if T <= dsg.padlen:
+        raise ValueError(f"The length of the input vector x must be greater than padlen, which is {dsg.padlen}.")
+    # exact edges first (they only read x): rows 0..C-1 = left segments, C..2C-1 = right segments
+    E = 2 * V
+    xe = torch.empty((2 * Cn, E), dtype=torch.float32, device=x.device)
+    copy2d(xe[:Cn], x[:, :E])
+    copy2d(xe[Cn:], x[:, T - E:])
+    ye = sosfilt(sosfilt(xe, A), B)
+    sos = np.ascontiguousarray(dsg.sos, dtype=np.float64)
+    zi = np.ascontiguousarray(dsg.zi, dtype=np.float64)
+    nbytes = lib.ecog_sos_workspace(C.byref(plan), Cn, T)
+    ws = workspace(nbytes, x.device, "sos")
+    nat.check(lib.ecog_sosfilt(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), C.byref(plan), _hptr(sos), _hptr(zi),
+                               _hptr(None), _ptr(ws), ws.numel(), _stream()))
+    copy2d(y[:, :V], ye[:Cn, :V])
+    copy2d(y[:, T - V:], ye[Cn:, E - V:])
+    return y
+
+
 def butter(x: torch.Tensor, freqs, fs, order=4, causal=False, filter_type="bandpass",
            chunk: Optional[int] = None, out: Optional[torch.Tensor] = None, mode: Optional[str] = None) -> torch.Tensor:
     """ref: frequency_filter.py:187-229 (butter_filter keyword names kept)."""
@@ -216,16 +321,25 @@ _hilbert_plans = {}
 
 def hilbert(x: torch.Tensor, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0,
             filterbank_bias=np.log10(0.39), filterbank_slope=0.5, envelope=True,
-            out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """ref: frequency_filter.py:80-184 (hilbert_filter keyword names kept)."""
+            out: Optional[torch.Tensor] = None, car: Optional[Tuple[torch.Tensor, int]] = None) -> torch.Tensor:
+    """ref: frequency_filter.py:80-184 (hilbert_filter keyword names kept).
+
+    ``car = (colsum, n_included)``: filter ``x - colsum / n_included`` instead of ``x`` -- a
+    ``car_rereference`` step directly in front of the bank, folded into the kernel's load
+    (ref: car_rereference.py:34-39; ``colsum`` from ``car_colsum``, all-reduced when channel-sharded)."""
     x = as_signal(x)
     Cn, T = x.shape
+    colsum, inv_count = (None, 0.0) if car is None else (car[0], 1.0 / car[1])
+    if colsum is not None and (colsum.dtype != torch.float32 or colsum.numel() != T or not colsum.is_contiguous()):
+        raise ValueError("car column sums must be a contiguous float32 vector of T elements")
     cfs, sds = D.gaussian_bank(freq_ranges, f0, octspace, filterbank_bias, filterbank_slope)
     if len(cfs) == 0:
         raise ValueError("the frequency ranges contain no filter-bank centre frequency")
     try:
         halo = FP.hilbert_halo(cfs, sds, float(fs), T)
     except NotImplementedError:
+        if colsum is not None:
+            x = car_apply(x, colsum, car[1])
         return _hilbert_global(x, float(fs), cfs, sds, bool(envelope), out)      # low-frequency bands
     key = ("hilbert_gain", tuple(cfs.tolist()), tuple(sds.tolist()), float(fs), bool(envelope))
     plan = _hilbert_plans.get(key)
@@ -237,7 +351,7 @@ def hilbert(x: torch.Tensor, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0,
     y = out if out is not None else torch.empty((Cn, T), dtype=torch.float32, device=x.device)
     nat.check(lib.ecog_hilbert_env(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), _ptr(gain), len(cfs), rows,
                                    _hptr(shift), _hptr(nz), halo, 1 if envelope else 0,
-                                   _ptr(_hilbert_twiddles(x.device)), _stream()))
+                                   _ptr(_hilbert_twiddles(x.device)), _ptr(colsum), float(inv_count), _stream()))
     return y
 
 
@@ -495,11 +609,12 @@ def fft_resample(x: torch.Tensor, num: int, two_stage: Optional[bool] = None) ->
 
 # ------------------------------------------------------------------------ K8
 def epoch_gather(src: torch.Tensor, starts: np.ndarray, length: int) -> torch.Tensor:
-    """out[n, c, :] = src[c, starts[n] : starts[n] + length]; bit copy for 4- and 8-byte dtypes."""
+    """out[n, c, :] = src[c, starts[n] : starts[n] + length]; bit copy for 1-, 2-, 4- and 8-byte dtypes
+    (the reference slices whatever dtype the .npz holds, e.g. int16 audio)."""
     if not src.is_cuda or src.dim() != 2:
         raise TypeError("expected a (channels, time) CUDA tensor")
-    if src.element_size() not in (4, 8):
-        raise TypeError(f"epoch_gather supports 4- and 8-byte element types, got {src.dtype}")
+    if src.element_size() not in (1, 2, 4, 8):
+        raise TypeError(f"epoch_gather supports 1-, 2-, 4- and 8-byte element types, got {src.dtype}")
     if src.stride(1) != 1:
         src = src.contiguous()
     Cn, T = src.shape
@@ -513,11 +628,11 @@ def epoch_gather(src: torch.Tensor, starts: np.ndarray, length: int) -> torch.Te
 
 
 def channel_select(epochs: torch.Tensor, channels) -> torch.Tensor:
-    """out[n, j, :] = epochs[n, channels[j], :] (bit copy, 4- and 8-byte dtypes)."""
+    """out[n, j, :] = epochs[n, channels[j], :] (bit copy, 1-, 2-, 4- and 8-byte dtypes)."""
     if not epochs.is_cuda or epochs.dim() != 3:
         raise TypeError("expected an (events, channels, time) CUDA tensor")
-    if epochs.element_size() not in (4, 8):
-        raise TypeError(f"channel_select supports 4- and 8-byte element types, got {epochs.dtype}")
+    if epochs.element_size() not in (1, 2, 4, 8):
+        raise TypeError(f"channel_select supports 1-, 2-, 4- and 8-byte element types, got {epochs.dtype}")
     epochs = epochs.contiguous()
     N, Cn, L = epochs.shape
     ch = np.ascontiguousarray(channels, dtype=np.int64)

@@ -4,12 +4,26 @@
 list (ref: preprocess/preprocessor.py:39-70) and returns ``(data, signal_freq)``.
 Differences, all supersets:
   * the recording is copied to the device ONCE, stays resident between steps and is
-    copied back ONCE in the dtype the reference would have produced;
-  * every step gets a fresh parameter scope (the reference's shared Namespace forbids
-    repeating a step, B6); ``strict_params=True`` restores the reference's collision error;
+    copied back ONCE in the dtype the reference would have produced (``output_dtype``
+    overrides: float32 halves the return traffic, widening is then the caller's choice);
+  * step parameters are written into ONE shared Namespace exactly like the reference does
+    (ref :46-53), so a key set by an earlier step stays visible to the later ones
+    (``preserve_nans``, ``exclude_channels`` ...); a repeated key is overwritten (last write
+    wins) instead of raising, because the reference's collision error forbids repeating a step
+    (B6); ``strict_params=True`` restores that error;
   * step modules are resolved by their last dotted component, so ``preprocess.<name>``
     (docs, example_config.yaml) and ``preprocess.signal.<name>`` (real location) both work
-    (B1); unknown modules are imported and called like the reference does.
+    (B1); unknown modules are imported and called like the reference does;
+  * the runner owns two re-orderings that leave the result unchanged (``fuse``):
+      - ``butter(zero-phase) -> [car_rereference] -> butter(zero-phase)``: CAR is the same linear
+        combination of rows at every sample and filtfilt (odd padding and ``zi * x[0]`` included)
+        is linear and identical for every row, so CAR commutes with it; the two filtfilts then run
+        as ONE forward and ONE backward sweep of an 8-section cascade (``ops.sosfilt_pair``:
+        4 sweeps -> 2, exact edges recomputed);
+      - ``car_rereference -> frequency_filter[hilbert]``: the column mean is produced by one
+        read-only pass and subtracted in the Hilbert kernel's load (no read + write of the
+        recording for CAR).
+    The step modules keep the reference's one-step contract; ``fuse=False`` runs them one by one.
 """
 from __future__ import annotations
 
@@ -33,6 +47,14 @@ def _resolve(module_name: str):
     return short, module.run
 
 
+def _short(step: dict) -> str:
+    return step["module"].split(".")[-1]
+
+
+def _step_params(step: dict) -> dict:
+    return step.get("params", {}) or {}
+
+
 def _profile_name(name: str, step_params: dict) -> str:
     if name == "frequency_filter":
         kinds = []
@@ -43,56 +65,178 @@ def _profile_name(name: str, step_params: dict) -> str:
     return name
 
 
+def apply_step_params(params: Namespace, step: dict, strict: bool = False) -> None:
+    """Flatten a step's params into the shared Namespace (ref: preprocessor.py:46-53).  The reference
+    raises on a key that is already there; by default the later step wins here (B6)."""
+    for key, value in _step_params(step).items():
+        if strict and hasattr(params, key):
+            raise ValueError(
+                f"Parameter '{key}' already exists in params. "
+                "Please ensure no conflicting parameter names in each preprocessing step.")
+        setattr(params, key, deepcopy(value))
+
+
+# --------------------------------------------------------------------------- fusion planner
+def _single_band(step: dict, method: str) -> Optional[dict]:
+    """The band's params dict if `step` is a frequency_filter with exactly ONE band of `method`."""
+    if _short(step) != "frequency_filter":
+        return None
+    bands = _step_params(step).get("bands")
+    if not isinstance(bands, list) or len(bands) != 1 or not isinstance(bands[0], dict):
+        return None
+    if bands[0].get("method", "hilbert") != method:
+        return None
+    return dict(bands[0].get("params", {}) or {})
+
+
+def _zero_phase_butter(step: dict) -> bool:
+    p = _single_band(step, "butter")
+    return p is not None and "freqs" in p and not p.get("causal", False) and set(p) <= {"freqs", "order", "causal", "filter_type"}
+
+
+def _plain_car(step: dict) -> bool:
+    return _short(step) == "car_rereference"
+
+
+def fusion_groups(steps: List[dict]) -> List[tuple]:
+    """``[("step", step) | ("iir_pair", stepA, stepB) | ("car_hilbert", car_step, hilbert_step)]``.
+
+    First CAR is moved behind a zero-phase Butterworth step that follows it when another one
+    precedes it (A, CAR, B -> A, B, CAR: CAR commutes with per-row linear filters), then adjacent
+    pairs are grouped."""
+    order = list(steps)
+    i = 0
+    while i + 2 < len(order):
+        if _zero_phase_butter(order[i]) and _plain_car(order[i + 1]) and _zero_phase_butter(order[i + 2]):
+            order[i + 1], order[i + 2] = order[i + 2], order[i + 1]
+            i += 2
+        else:
+            i += 1
+    groups, i = [], 0
+    while i < len(order):
+        if i + 1 < len(order) and _zero_phase_butter(order[i]) and _zero_phase_butter(order[i + 1]):
+            groups.append(("iir_pair", order[i], order[i + 1]))
+            i += 2
+        elif i + 1 < len(order) and _plain_car(order[i]) and _single_band(order[i + 1], "hilbert") is not None \
+                and "freq_ranges" in _single_band(order[i + 1], "hilbert"):
+            groups.append(("car_hilbert", order[i], order[i + 1]))
+            i += 2
+        else:
+            groups.append(("step", order[i]))
+            i += 1
+    return groups
+
+
+def fusion_enabled(fuse: Optional[bool]) -> bool:
+    return (os.environ.get("ECOG_FUSE", "1") != "0") if fuse is None else bool(fuse)
+
+
+def _group_steps(group: tuple) -> List[dict]:
+    return list(group[1:])
+
+
+def _group_name(group: tuple) -> str:
+    names = [_profile_name(_short(s), _step_params(s)) for s in _group_steps(group)]
+    return names[0] if group[0] == "step" else "+".join(names)
+
+
+def _run_group(x, group: tuple, params: Namespace, strict: bool, shard=None):
+    """Run one fusion group on a device tensor; ``params`` is the shared Namespace.
+    ``shard`` (channel-sharded recordings, distributed.py): ``(c_lo, n_channels, reduce)`` -- the local
+    rows are global rows [c_lo, c_lo + C_local), ``exclude_channels`` holds global indices and
+    ``reduce(colsum)`` all-reduces the column sums in place."""
+    from . import design as D
+    from . import ops
+    kind = group[0]
+    if kind == "step":
+        step = group[1]
+        apply_step_params(params, step, strict)
+        name, fn = _resolve(step["module"])
+        return fn(x, params)
+    if kind == "iir_pair":
+        designs = []
+        for step in group[1:]:
+            apply_step_params(params, step, strict)
+            (_, p), = S.band_plan(params)
+            designs.append(D.butter_design(p["freqs"], params.signal_freq, p.get("order", 4), False,
+                                           p.get("filter_type", "bandpass")))
+        return ops.sosfilt_pair(ops.as_signal(x), designs[0], designs[1])
+    if kind == "car_hilbert":
+        car_step, hil_step = group[1], group[2]
+        apply_step_params(params, car_step, strict)
+        x = ops.as_signal(x)
+        if shard is None:
+            excl = S.car_exclusions(params, x.shape[0])
+            w, n_inc = ops._car_weights(x.shape[0], excl, x.device)
+            colsum = ops.car_colsum(x, w)
+        else:
+            c_lo, n_channels, reduce = shard
+            excl = S.car_exclusions(params, n_channels)
+            local = [ch - c_lo for ch in excl if c_lo <= ch < c_lo + x.shape[0]]
+            w, _ = ops._car_weights(x.shape[0], local, x.device)
+            colsum = ops.car_colsum(x, w)
+            reduce(colsum)
+            n_inc = n_channels - len(set(excl))
+        apply_step_params(params, hil_step, strict)
+        (_, p), = S.band_plan(params)
+        return ops.hilbert(x, params.signal_freq, car=(colsum, n_inc), **p)
+    raise ValueError(f"unknown fusion group {kind}")
+
+
 # ------------------------------------------------------------------ pipelined host path
 PIPELINE_MIN_CHANNELS = 64       # below this the recording is moved and processed in one piece
 PIPELINE_CHUNKS = int(os.environ.get("ECOG_PIPELINE_CHUNKS", "12"))   # measured at C2: 8 -> 195.4 ms, 12 -> 193.9, 16 -> 193.9
 
 
-def _row_independent(name: str, step_params: dict) -> bool:
-    """Steps whose output row c depends on input row c only and that keep the row count."""
+def _row_independent(group: tuple) -> bool:
+    """Groups whose output row c depends on input row c only and that keep the row count."""
+    if group[0] == "iir_pair":
+        return True
+    if group[0] != "step":
+        return False
+    name, p = _short(group[1]), _step_params(group[1])
     if name == "frequency_filter":
-        return len(step_params.get("bands") or []) == 1
+        return len(p.get("bands") or []) == 1
     return name in ("channel_zscore", "zscore_rereference", "rolling_zscore", "downsample")
 
 
-def _scoped(step: dict, block_params: Namespace) -> Namespace:
-    scope = Namespace(**vars(block_params))
-    for key, value in (step.get("params", {}) or {}).items():
-        setattr(scope, key, deepcopy(value))
-    return scope
+def _needs_all_rows(group: tuple) -> bool:
+    return group[0] == "car_hilbert" or (group[0] == "step" and _short(group[1]) == "car_rereference")
 
 
-def _run_segment(x, segment, block_params: Namespace):
-    """Run consecutive steps on a device tensor with a private copy of the parameters; returns
+def _run_segment(x, segment: List[tuple], block_params: Namespace):
+    """Run consecutive groups on a device tensor with a private copy of the parameters; returns
     (tensor, params after the segment)."""
     params = Namespace(**vars(block_params))
-    for step in segment:
-        scope = _scoped(step, params)
-        _, fn = _resolve(step["module"])
-        x = fn(x, scope)
-        params.signal_freq = scope.signal_freq
+    for group in segment:
+        x = _run_group(x, group, params, False)
     return x, params
 
 
-def _pipelined_host_run(data: np.ndarray, steps: List[dict], block_params: Namespace, out_dtype):
+def _pipelined_host_run(data: np.ndarray, groups: List[tuple], block_params: Namespace, out_dtype):
     """Host array in, host array out, with the PCIe copies hidden behind the kernels.
 
     Every step but ``car_rereference`` is row independent (ref: each preprocess/signal/*.py works
     along axis 1), so the recording is cut into channel chunks: chunk i+1 is copied to the device
-    while the steps BEFORE the first CAR run on chunk i, and the steps AFTER the last CAR run on
+    while the groups BEFORE the first CAR run on chunk i, and the groups AFTER the last CAR run on
     chunk i while chunk i-1 travels back.  CAR itself (and anything between two CARs) sees the
-    whole array.  Returns None when the step list does not have that shape."""
+    whole array; a CAR folded into the Hilbert load contributes its column-sum pass to the middle
+    and its Hilbert kernel to the per-chunk tail.  Returns None when the list does not have that shape."""
     import torch
-    names = [s["module"].split(".")[-1] for s in steps]
-    if data.ndim != 2 or data.shape[0] < PIPELINE_MIN_CHANNELS or not all(n in S.STEPS for n in names):
+    from . import ops
+    if data.ndim != 2 or data.shape[0] < PIPELINE_MIN_CHANNELS:
         return None
-    ok = [n == "car_rereference" or _row_independent(n, s.get("params", {}) or {}) for n, s in zip(names, steps)]
-    if not all(ok):
-        return None
-    cars = [i for i, n in enumerate(names) if n == "car_rereference"]
-    head = steps[:cars[0]] if cars else []
-    middle = steps[cars[0]:cars[-1] + 1] if cars else []
-    tail = steps[cars[-1] + 1:] if cars else steps
+    for g in groups:
+        if not all(_short(s) in S.STEPS for s in _group_steps(g)):
+            return None
+        if not (_row_independent(g) or _needs_all_rows(g)):
+            return None
+    cars = [i for i, g in enumerate(groups) if _needs_all_rows(g)]
+    head = groups[:cars[0]] if cars else []
+    middle = groups[cars[0]:cars[-1] + 1] if cars else []
+    tail = groups[cars[-1] + 1:] if cars else groups
+    # a trailing car_hilbert group: column sums over the whole array (middle), Hilbert per chunk (tail)
+    split_last = bool(middle) and middle[-1][0] == "car_hilbert"
     Cn, T = data.shape
     bounds = np.linspace(0, Cn, PIPELINE_CHUNKS + 1).astype(int)
     chunks = [(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
@@ -124,6 +268,7 @@ def _pipelined_host_run(data: np.ndarray, steps: List[dict], block_params: Names
         xc = x0[a:b]
         return xc if xc.dtype == torch.float32 else xc.to(torch.float32)
 
+    car_fold = None
     if cars:
         x1 = None
         for i, (a, b) in enumerate(chunks):
@@ -135,7 +280,19 @@ def _pipelined_host_run(data: np.ndarray, steps: List[dict], block_params: Names
                     torch.empty((Cn, yc.shape[1]), dtype=torch.float32, device=dev)
             if x1 is not x0:
                 x1[a:b].copy_(yc)
-        x1, params = _run_segment(x1, middle, params)
+        if split_last:
+            x1, params = _run_segment(x1, middle[:-1], params)
+            params = Namespace(**vars(params))
+            car_step, hil_step = middle[-1][1], middle[-1][2]
+            apply_step_params(params, car_step)
+            excl = S.car_exclusions(params, x1.shape[0])
+            w, n_inc = ops._car_weights(x1.shape[0], excl, x1.device)
+            colsum = ops.car_colsum(x1, w)
+            apply_step_params(params, hil_step)
+            (_, hp), = S.band_plan(params)
+            car_fold = (colsum, n_inc, hp)
+        else:
+            x1, params = _run_segment(x1, middle, params)
         chunk_mid = lambda i: x1[chunks[i][0]:chunks[i][1]]
     else:
         chunk_mid = chunk_in              # no CAR: the whole list runs per chunk, both copies overlap it
@@ -146,6 +303,8 @@ def _pipelined_host_run(data: np.ndarray, steps: List[dict], block_params: Names
     final = params
     for i, (a, b) in enumerate(chunks):
         yc = chunk_mid(i)
+        if car_fold is not None:
+            yc = ops.hilbert(yc, params.signal_freq, car=(car_fold[0], car_fold[1]), **car_fold[2])
         if tail:
             yc, final = _run_segment(yc, tail, params)
         yc = yc.to(td) if yc.dtype != td else yc
@@ -160,7 +319,8 @@ def _pipelined_host_run(data: np.ndarray, steps: List[dict], block_params: Names
     down.synchronize()
     main.synchronize()
     rt.d2h_bytes += out.numel() * out.element_size()
-    block_params.signal_freq = final.signal_freq
+    for k, v in vars(final).items():          # the shared Namespace the caller handed in sees every step's keys
+        setattr(block_params, k, v)
     return out.numpy()
 
 
@@ -177,51 +337,45 @@ def _copy_streams(dev):
 
 def preprocess_signal(data, steps: List[dict], block_params: Namespace, figure_dir: Optional[str] = None,
                       num_channels: int = 5, duration: float = 1.0, strict_params: bool = False,
-                      profile: Optional[list] = None):
-    """``profile``: optional list; one (step name, start event, end event) CUDA-event triple
-    per step is appended (events recorded on the current stream, no synchronisation)."""
+                      profile: Optional[list] = None, fuse: Optional[bool] = None, output_dtype=None):
+    """``profile``: optional list; one (group name, start event, end event) CUDA-event triple
+    per executed group is appended (events recorded on the current stream, no synchronisation).
+    ``fuse``: None = on unless ECOG_FUSE=0.  ``output_dtype``: dtype of the array handed back to a
+    numpy caller (None = the reference's own convention)."""
     was_host = not rt.is_device(data)
     ref_dtype = np.asarray(data).dtype if was_host else np.dtype(np.float32)
-    if was_host and len(steps) and not strict_params and profile is None and os.environ.get("ECOG_PIPELINE", "1") != "0":
-        dt = ref_dtype
+    known = all(_short(s) in S.STEPS for s in steps)
+    groups = fusion_groups(steps) if (fusion_enabled(fuse) and known and not strict_params) else [("step", s) for s in steps]
+
+    def final_dtype(dt):
         for step in steps:
-            dt = S.reference_dtype_after(step["module"].split(".")[-1], step.get("params", {}) or {}, dt)
+            dt = S.reference_dtype_after(_short(step), _step_params(step), dt)
+        return np.dtype(output_dtype) if output_dtype is not None else rt.output_dtype(dt)
+
+    if was_host and len(steps) and not strict_params and profile is None and os.environ.get("ECOG_PIPELINE", "1") != "0":
         arr = np.asarray(data)
         if np.issubdtype(arr.dtype, np.floating) and arr.flags.c_contiguous:
             if not arr.flags.writeable:
                 arr = arr.copy()
-            y = _pipelined_host_run(arr, steps, block_params, rt.output_dtype(dt))
+            y = _pipelined_host_run(arr, groups, block_params, final_dtype(ref_dtype))
             if y is not None:
                 return y, block_params.signal_freq
-    if was_host and len(steps) and all(s["module"].split(".")[-1] in S.STEPS for s in steps):
+    if was_host and len(steps) and known:
         x = rt.to_device(np.asarray(data))
     else:
         x = data
-    for step in steps:
-        step_params = step.get("params", {}) or {}
-        if strict_params:
-            for key in step_params:
-                if hasattr(block_params, key):
-                    raise ValueError(
-                        f"Parameter '{key}' already exists in params. "
-                        "Please ensure no conflicting parameter names in each preprocessing step.")
-        scope = block_params if strict_params else Namespace(**vars(block_params))
-        for key, value in step_params.items():
-            setattr(scope, key, deepcopy(value))
-        name, fn = _resolve(step["module"])
+    for group in groups:
         if profile is not None and rt.is_device(x):
             import torch
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             ev0.record()
-            x = fn(x, scope)
+            x = _run_group(x, group, block_params, strict_params)
             ev1.record()
-            profile.append((_profile_name(name, step_params), ev0, ev1))
+            profile.append((_group_name(group), ev0, ev1))
         else:
-            x = fn(x, scope)
-        block_params.signal_freq = scope.signal_freq
-        ref_dtype = S.reference_dtype_after(name, step_params, ref_dtype)
+            x = _run_group(x, group, block_params, strict_params)
     if was_host and rt.is_device(x):
-        x = rt.to_host(x, rt.output_dtype(ref_dtype))
+        x = rt.to_host(x, final_dtype(ref_dtype))
     return x, block_params.signal_freq
 
 

@@ -39,14 +39,12 @@ _f64 = lambda dt: np.float64
 
 
 # ------------------------------------------------------------ frequency_filter
-def frequency_filter(data, params: Namespace):
-    """ref: preprocess/signal/frequency_filter.py:9-77.  ``params.bands`` is a list of
-    {method: hilbert|butter|fir, params: {...}}; every band filters the SAME input and the
-    results are concatenated along the channel axis."""
+def band_plan(params: Namespace):
+    """Validated ``[(method, params dict), ...]`` of a frequency_filter step (ref: frequency_filter.py:33-74:
+    same checks, same messages; unknown methods are silently ignored like the reference does)."""
     bands = getattr(params, "bands", None)
     if bands is None:
         raise ValueError("bands must be specified in params.")
-    fs = params.signal_freq
     plan = []
     for cfg in bands:
         method = cfg.get("method", "hilbert")
@@ -65,6 +63,15 @@ def frequency_filter(data, params: Namespace):
         plan.append((method, p))
     if not plan:
         raise ValueError("need at least one array to concatenate")
+    return plan
+
+
+def frequency_filter(data, params: Namespace):
+    """ref: preprocess/signal/frequency_filter.py:9-77.  ``params.bands`` is a list of
+    {method: hilbert|butter|fir, params: {...}}; every band filters the SAME input and the
+    results are concatenated along the channel axis."""
+    plan = band_plan(params)
+    fs = params.signal_freq
 
     def run_band(x, method, p, out=None):
         if method == "hilbert":
@@ -90,15 +97,20 @@ def frequency_filter(data, params: Namespace):
 # ---------------------------------------------------------------- car_rereference
 def car_rereference(data, params: Namespace):
     """ref: preprocess/signal/car_rereference.py:5-41 (sets params.exclude_channels=[] when absent)."""
+    excl = car_exclusions(params, data.shape[0])
+    return _wrap(lambda x: ops.car(x, excl), data, params, _same)
+
+
+def car_exclusions(params: Namespace, n_ch: int) -> list:
+    """Validated ``exclude_channels`` (ref: car_rereference.py:23-32, including the side effect on params)."""
     if not hasattr(params, "exclude_channels"):
         params.exclude_channels = []
     excl = params.exclude_channels
     if not isinstance(excl, list):
         raise ValueError("exclude_channels must be a list of integers.")
-    n_ch = data.shape[0]
     if any(ch < 0 or ch >= n_ch for ch in excl):
         raise ValueError("exclude_channels contains invalid channel indices.")
-    return _wrap(lambda x: ops.car(x, excl), data, params, _same)
+    return excl
 
 
 # ----------------------------------------------------------------- channel_zscore

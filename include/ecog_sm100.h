@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ECOG_ABI_VERSION 4
+#define ECOG_ABI_VERSION 5
 
 #define ECOG_OK 0
 #define ECOG_E_VALUE (-1)     /* bad argument (reference raises ValueError)          */
@@ -50,12 +50,13 @@ int64_t ecog_launch_count(void);
  *   y[c,t] = x[c,t] - (1/n_inc) * sum_c w[c] x[c,t];  d_w (C floats, 0/1) may be NULL.
  * ecog_car is the single-GPU fused pass.  ecog_car_colsum / ecog_car_apply are the
  * two-phase form for channel-sharded recordings: the caller all-reduces d_colsum
- * (T floats) between the two enqueues.                                             */
-int ecog_car(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ld,
+ * (T floats) between the two enqueues.  Input and output rows have their own strides
+ * (ldx, ldy >= T), like every other kernel family.                                  */
+int ecog_car(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
              const float* d_w, double inv_count, ecog_stream_t stream);
 int ecog_car_colsum(const float* d_x, int64_t C, int64_t T, int64_t ld, const float* d_w,
                     float* d_colsum, ecog_stream_t stream);
-int ecog_car_apply(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ld,
+int ecog_car_apply(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                    const float* d_colsum, double inv_count, ecog_stream_t stream);
 
 /* -------------------------------------------------------- K2: row statistics
@@ -67,7 +68,7 @@ size_t ecog_row_stats_workspace(int64_t C, int64_t T);
 int ecog_row_stats(const float* d_x, int64_t C, int64_t T, int64_t ld, int64_t t0, int64_t t1,
                    double* d_mean, double* d_std, void* d_workspace, size_t workspace_bytes,
                    ecog_stream_t stream);
-int ecog_zscore_apply(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ld,
+int ecog_zscore_apply(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                       const double* d_mean, const double* d_std, int nan_to_zero,
                       ecog_stream_t stream);
 
@@ -90,7 +91,18 @@ typedef struct {
     int32_t tail;        /* multiple of 16; <= chunk in scan mode                     */
     int32_t mode;        /* ECOG_SOS_SCAN (exact carry scan) or ECOG_SOS_WARMUP        */
     int32_t threads;     /* warm-up mode: threads per CTA, 256 or 512                 */
+    int32_t split;       /* 0, or 4: h_sos holds TWO 4-section unit-form cascades      */
+    int32_t tail_b;      /* split: warm-up samples of the second cascade (<= tail)     */
 } ecog_sos_plan;
+/* Cascade pair (split = 4, warm-up mode, zero phase, nsec = 8): two consecutive filtfilt steps
+ * of the reference chain (e.g. the 58-62 Hz band-stop and the 70-150 Hz band-pass,
+ * frequency_filter.py:218-229 twice) run as ONE forward and ONE backward sweep.  Away from the
+ * row ends forward and backward sweeps of different LTI filters commute, so the result equals
+ * the two sequential filtfilts there (to the warm-up bound); within `tail` samples of a row end
+ * it does not, and the caller overwrites those samples with the sequential result computed on
+ * short edge segments (decode_tonal_langauge_b200/ops.py::sosfilt_pair).  Sections 0-3 and 4-7
+ * must each be of unit form (b2 = +-b0, all b0 = 1 except section 0, which carries the product
+ * of both gains).                                                                           */
 /* ECOG_SOS_WARMUP: one kernel per sweep; every chunk re-creates its start state by filtering
  * the `tail` samples before it from a zero state (valid when the host has checked that the
  * cascade's zero-input response is < 1e-10 after `tail` samples); chunks within `tail` of the
@@ -105,6 +117,11 @@ int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx
                  const double* h_M, void* d_workspace, size_t workspace_bytes,
                  ecog_stream_t stream);
 
+/* strided device-to-device copy of a float32 (rows, cols) view (cudaMemcpy2DAsync on `stream`):
+ * gathers / scatters the row-edge segments of the cascade pair without a host round trip.   */
+int ecog_copy2d(const float* d_src, int64_t ld_src, float* d_dst, int64_t ld_dst, int64_t rows,
+                int64_t cols, ecog_stream_t stream);
+
 /* ------------------------------------ K4: Gaussian-Hilbert envelope (block-wise)
  * replaces preprocess/signal/frequency_filter.py:154-184.
  * Overlap-save with 4096-point shared-memory FFTs and a circular halo of `halo` samples.
@@ -113,14 +130,18 @@ int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx
  * those bins (host, float64 -> float32).  rows in {1,2,4,8}.  With envelope=0 (real part)
  * every h_shift must be 0.  h_nz (optional, NULL = 16 per band; used when rows == 1): the
  * caller's promise that d_gain[b][k] == 0 for k >= 16 * h_nz[b] -- the inverse transforms then
- * skip the zero bins.  d_twiddle: table from ecog_hilbert_twiddles.                    */
+ * skip the zero bins.  d_twiddle: table from ecog_hilbert_twiddles.
+ * d_colsum (optional, NULL = none): T column sums from ecog_car_colsum; the kernel then filters
+ * x[c,t] - inv_count * d_colsum[t], i.e. car_rereference.py:34-39 folded into the load (the
+ * common-average step directly in front of the bank costs one read-only pass instead of a
+ * read + write of the recording).                                                        */
 #define ECOG_HILBERT_N 4096
 size_t ecog_hilbert_twiddle_floats(void);
 int ecog_hilbert_twiddles(float* h_out);   /* host helper: fills the per-thread twiddle table */
 int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                      const float* d_gain, int32_t nbands, int32_t rows, const int32_t* h_shift,
                      const int32_t* h_nz, int32_t halo, int32_t envelope, const float* d_twiddle,
-                     ecog_stream_t stream);
+                     const float* d_colsum, double inv_count, ecog_stream_t stream);
 
 /* ------------------------------------------------- K5: whole-row FFT resample
  * replaces preprocess/signal/downsample.py:21-27 (scipy.signal.resample, real input).
@@ -223,7 +244,7 @@ int ecog_rolling_zscore(const float* d_x, float* d_y, int64_t C, int64_t T, int6
 
 /* ------------------------------------------------------- K8: epoch gather
  * replaces data_loading/text_align.py:290-304,331-340,380-394.
- *   out[n, c, 0:L] = src[c, start[n] : start[n]+L]    (bit copy; elem_bytes 4 or 8)
+ *   out[n, c, 0:L] = src[c, start[n] : start[n]+L]    (bit copy; elem_bytes 1, 2, 4 or 8)
  * d_start: int64 onset indices computed on the host in float64 (Appendix A6).
  * Returns ECOG_E_VALUE if any window leaves [0, T) -- checked on the host copy h_start. */
 int ecog_epoch_gather(const void* d_src, void* d_out, int64_t C, int64_t T, int64_t ld,

@@ -30,7 +30,7 @@ def test_header_symbols_exported_and_bound():
 def test_error_mapping_without_gpu():
     """Argument validation happens before any CUDA call, so it is testable on CPU."""
     from decode_tonal_langauge_b200 import _native as nat
-    rc = nat.lib.ecog_car(None, None, 0, 10, 10, None, 1.0, None)
+    rc = nat.lib.ecog_car(None, None, 0, 10, 10, 10, None, 1.0, None)
     assert rc == nat.ECOG_E_VALUE
     with pytest.raises(ValueError):
         nat.check(rc)

@@ -155,7 +155,14 @@ def test_step_runner_param_scope_and_rate_threading():
     p = Namespace(signal_freq=100)
     y, f = preprocess_signal(x, steps, p)              # repeated step + repeated key: allowed (B6)
     assert f == 50 and y.shape == (2, 4) and np.all(y == 6.0) and p.signal_freq == 50
-    assert not hasattr(p, "gain")                      # step parameters do not leak into the caller's scope
+    # the reference flattens every step's params into ONE shared Namespace (preprocessor.py:46-53):
+    # keys of earlier steps stay visible to later ones and to the caller; a repeated key is overwritten
+    assert p.gain == 3.0 and p.halve_rate is True
+    # ... so a key set by step 1 only governs step 2 as well (the reference's behaviour)
+    steps2 = [{"module": "helpers.fake_step", "params": {"gain": 2.0, "halve_rate": True}},
+              {"module": "helpers.fake_step", "params": {"gain": 3.0}}]
+    y2, f2 = preprocess_signal(x, steps2, Namespace(signal_freq=100))
+    assert f2 == 25 and y2.shape == (2, 2)
     with pytest.raises(ValueError, match="already exists"):
         preprocess_signal(x, steps, Namespace(signal_freq=100), strict_params=True)
 
