@@ -39,26 +39,43 @@ SHARDED = {"C4", "C4small"}
 # algorithmic bytes per RAW channel-sample, unfused contract of SURVEY.md section 8(d)
 FULL6_BYTES_PER_SAMPLE = 39.2
 HILBERT_BYTES_PER_SAMPLE = 8.0
-# per step, same contract (bytes per RAW channel-sample at 2 kHz -> 400 Hz)
+# per executed group, same contract (bytes per RAW channel-sample at 2 kHz -> 400 Hz): external inputs
+# read once + outputs written once; a fused group counts once; a statistics pre-pass that cannot be
+# fused counts one extra read (the CAR column-sum pass in front of the Hilbert kernel).
 STEP_BYTES_PER_SAMPLE = {
     "frequency_filter[butter_bandstop]": 8.0, "car_rereference": 8.0, "frequency_filter[butter_bandpass]": 8.0,
     "frequency_filter[hilbert]": 8.0, "downsample": 4.8, "channel_zscore": 2.4,
+    "frequency_filter[butter_bandstop]+frequency_filter[butter_bandpass]": 8.0,
+    "car_rereference+frequency_filter[hilbert]": 12.0,
 }
+HILBERT_KEYS = ("car_rereference+frequency_filter[hilbert]", "frequency_filter[hilbert]")
+KERNEL_SOURCES = {"hilbert_env8_kernel": "decode_tonal_langauge_b200/csrc/hilbert.cu",
+                  "sos_warm_kernel": "decode_tonal_langauge_b200/csrc/sosfilt.cu"}
 
 
-def ncu_traffic(kernel: str, channels: int, samples: int):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture
-    (profiles/r01_traffic.json: bytes per channel-sample measured by ncu, scaled to this launch)."""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if not os.path.exists(path):
-        return None
-    with open(path) as f:
-        t = json.load(f)
-    e = t.get(kernel)
-    if not e:
-        return None
-    return {"gb_per_launch": e["dram_bytes_per_channel_sample"] * channels * samples / 1e9,
-            "source": e["source"]}
+def source_sha(rel: str) -> str:
+    import hashlib
+    with open(os.path.join(ROOT, rel), "rb") as f:
+        return hashlib.sha256(f.read()).hexdigest()[:16]
+
+
+def ncu_record(kernel: str):
+    """Per-kernel ncu facts (DRAM bytes and warp instructions per channel-sample) from the newest
+    committed capture -- profiles/r02_traffic.json, written by scripts/ncu_traffic.py from an
+    `ncu --set full` report together with the sha256 of the kernel's source file.  A capture taken
+    from an older version of the source is STALE and is not reported (None)."""
+    for name in ("r02_traffic.json",):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        with open(path) as f:
+            e = json.load(f).get(kernel)
+        if not e:
+            continue
+        if e.get("source_sha") != source_sha(KERNEL_SOURCES[kernel]):
+            return {"stale": True, "source": e.get("source")}
+        return e
+    return None
 
 
 def measured_peaks():
@@ -124,25 +141,68 @@ def _oracle_full6(x, fs):
     return ochains.run_chain(x, fs, FULL6_STEPS)
 
 
+_WORKER_DATA = {}
+
+
 def _cpu_worker(args):
-    seed, ch, T, fs = args
+    """One process of the reference arm: FULL6 (oracle port) on a block of synthetic channels
+    (decode_tonal_langauge_b200.synth, the generator of SURVEY.md section 8d), CAR over the block.
+    The block is generated once per process, outside the timed call."""
+    block, ch, T, fs, prepare = args
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    rng = np.random.default_rng(seed)
-    x = (rng.standard_normal((ch, T)) * 30).astype(np.float32)
+    key = (block, ch, T, fs)
+    if key not in _WORKER_DATA:
+        from decode_tonal_langauge_b200 import synth
+        _WORKER_DATA.clear()
+        _WORKER_DATA[key] = synth.session_channels(0, range(block * ch, (block + 1) * ch), T, fs, 256)
+    if prepare:
+        return 0.0, 0.0
     t0 = time.perf_counter()
-    y, _ = _oracle_full6(x, fs)
+    y, _ = _oracle_full6(_WORKER_DATA[key], fs)
     return time.perf_counter() - t0, float(np.nanmax(np.abs(y)))
 
 
-def cpu_baseline_single(T, fs, channels=3):
-    """The reference's own execution model: one thread."""
-    dt, _ = _cpu_worker((1234, channels, T, fs))
-    return {"value": channels * T / dt, "unit": "channel-samples/s", "cores": 1, "kind": "port",
-            "sample": f"oracle FULL6 on {channels} ch x {T} samples (full session length), 1 thread, {dt:.1f} s"}
+def oracle_rows_of_session(x_dev, rows, fs, col_mean):
+    """FULL6 of the oracle for `rows` of the device-resident session the GPU arm timed.  The chain's
+    CAR is linear, the same combination of rows at every sample, and every step in front of it is a
+    per-row linear filter, so chain(x)[c] = chain_without_car(x[c] - mean_k x[k]) (`col_mean`, float64,
+    over ALL channels of the recording).  Returns (float64 oracle, long-double-notch truth, seconds of
+    the float64 oracle run)."""
+    import torch
+    from oracle import chains as ochains
+    from oracle import steps as osteps
+    from decode_tonal_langauge_b200 import design as D
+    from decode_tonal_langauge_b200.chains import FULL6_STEPS
+    xin = x_dev[rows].to(torch.float64).cpu().numpy() - col_mean[None]
+    no_car = [FULL6_STEPS[0]] + FULL6_STEPS[2:]
+    t0 = time.perf_counter()
+    ref, _ = ochains.run_chain(xin, fs, no_car)
+    dt = time.perf_counter() - t0
+    d = D.butter_design([58, 62], fs, 4, False, "bandstop")
+    notch_ld = np.asarray(osteps.filtfilt_pad(d.b, d.a, xin, dtype=np.longdouble, reference_edges=True), dtype=np.float64)
+    truth, _ = ochains.run_chain(notch_ld, fs, no_car[1:])
+    return ref, truth, dt
+
+
+def max_rel(y, ref):
+    y, ref = np.asarray(y, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    return float(np.max(np.max(np.abs(y - ref), axis=1) / np.max(np.abs(ref), axis=1)))
+
+
+def parity_record(got, ref, truth, rows, what):
+    """SURVEY.md section 8c rule: float outputs within 1e-5 (max_t|y - ref| / max_t|ref| per channel) of
+    the reference; designs with pole radius > 0.99 (the 58-62 Hz notch) are judged against the
+    long-double evaluation of the reference's own algorithm: err(gpu, truth) <= max(1e-5, err(ref, truth))."""
+    e_gpu, e_ref, e_direct = max_rel(got, truth), max_rel(ref, truth), max_rel(got, ref)
+    return {"max_rel": e_gpu, "tol": 1e-5, "pass": bool(e_gpu <= max(1e-5, e_ref)),
+            "rule": "err(gpu, long-double truth) <= max(tol, err(float64 reference, truth)); "
+                    "max_t|y-ref|/max_t|ref| per channel, worst channel",
+            "reference_vs_truth": e_ref, "gpu_vs_float64_reference": e_direct, "rows": list(rows), "what": what}
 
 
 def run_reference_arm(args):
-    """--impl reference: the oracle port of the reference's CPU path on all usable host cores."""
+    """--impl reference: the oracle port of the reference's CPU path on all usable host cores
+    (the reference tree is pure Python and does not travel to the GPU box; `kind: port`)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -159,17 +219,21 @@ def run_reference_arm(args):
     ctx = mp.get_context("fork")
     times = []
     with ctx.Pool(workers) as pool:
+        pool.map(_cpu_worker, [(w, ch_per_worker, T, fs, True) for w in range(workers)], chunksize=1)
         for step in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            pool.map(_cpu_worker, [(step * 1000 + w, ch_per_worker, T, fs) for w in range(workers)])
+            pool.map(_cpu_worker, [(w, ch_per_worker, T, fs, False) for w in range(workers)], chunksize=1)
             dt = time.perf_counter() - t0
             if step >= args.warmup:
                 times.append(dt)
     total = sum(times)
     units = workers * ch_per_worker * T * len(times)
     value = units / total
-    sample = (f"{workers} processes x {ch_per_worker} ch x {T} samples per step (bounded sample of {C} ch); "
-              f"oracle port of the reference (numpy/scipy), CAR over each block")
+    sample = (f"{workers} processes x {ch_per_worker} ch x {T} samples per step = {workers * ch_per_worker} of the {C} "
+              f"channels of the workload (bounded sample, full session length); synthetic session of "
+              f"decode_tonal_langauge_b200.synth (pink noise + common mode + line noise); oracle port of the reference "
+              f"(numpy/scipy, float64), CAR over each {ch_per_worker}-channel block; NOT like for like with the GPU arm: "
+              f"fewer channels, CAR over blocks, kind=port")
     line = {"impl": "reference", "metric": "channel_samples_per_sec", "value": value, "unit": "channel-samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
@@ -183,6 +247,127 @@ def run_reference_arm(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def _timed_steps(step, steps, barrier, torch):
+    """K timed steps bracketed by barrier + synchronize; returns (elapsed ms of this rank, per-step profiles)."""
+    profiles = []
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        prof = []
+        step(prof)
+        profiles.append(prof)
+    ev1.record()
+    barrier()
+    return ev0.elapsed_time(ev1), profiles
+
+
+def _mean_ms(profiles):
+    acc = {}
+    for prof in profiles:
+        for name, a, b in prof:
+            acc.setdefault(name, []).append(a.elapsed_time(b))
+    return {k: float(np.mean(v)) for k, v in acc.items()}
+
+
+def host_copy_ceiling(torch, n_in_bytes, out_shape, out_dtype, chunks, steps=3):
+    """Pinned H2D of the input and D2H of the result with NO kernels in between, on two copy streams
+    (the D2H of chunk i overlaps the H2D of chunk i+1, as far as the host allows): the floor the host
+    memory system / PCIe puts under the end-to-end number."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    hin = torch.empty(n_in_bytes // 4, dtype=torch.float32, pin_memory=True)
+    din = torch.empty(n_in_bytes // 4, dtype=torch.float32, device=dev)
+    dout = torch.zeros(out_shape, dtype=out_dtype, device=dev)
+    hout = torch.empty(out_shape, dtype=out_dtype, pin_memory=True)
+    up, down = torch.cuda.Stream(), torch.cuda.Stream()
+    n = hin.numel()
+    cut = [n * i // chunks for i in range(chunks + 1)]
+    rows = [out_shape[0] * i // chunks for i in range(chunks + 1)]
+    times = []
+    for it in range(steps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(up):
+            for i in range(chunks):
+                din[cut[i]:cut[i + 1]].copy_(hin[cut[i]:cut[i + 1]], non_blocking=True)
+        up.synchronize()                       # CAR sees every channel before the first result exists
+        with torch.cuda.stream(down):
+            for i in range(chunks):
+                hout[rows[i]:rows[i + 1]].copy_(dout[rows[i]:rows[i + 1]], non_blocking=True)
+        down.synchronize()
+        if it:
+            times.append(time.perf_counter() - t0)
+    del hin, din, dout, hout
+    return float(np.mean(times))
+
+
+def run_sharded_record(args, torch, dist, world, rank, local, workload="C4"):
+    """One recording channel-sharded over the ranks (BASELINE configs[3]): FULL6 with the CAR column
+    sums all-reduced over NCCL.  Returns the sub-record on rank 0 (None elsewhere)."""
+    from decode_tonal_langauge_b200 import distributed as D
+    from decode_tonal_langauge_b200 import ops, synth
+    from decode_tonal_langauge_b200 import _native as nat
+    from decode_tonal_langauge_b200.chains import FULL6_STEPS
+    C, T, fs, desc = WORKLOADS[workload]
+    c_lo, c_hi = D.shard_bounds(C, rank, world)
+    x = synth.device_session(c_hi - c_lo, T, fs, seed=0, channel_seed=rank)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    y = None
+    steps = max(3, min(args.steps, 10))
+    for _ in range(max(3, args.warmup)):
+        y, _, _ = D.preprocess_signal_sharded(x, FULL6_STEPS, Namespace(signal_freq=fs), c_lo, C)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ar_events, group_events = [], []
+    l0 = nat.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        y, _, _ = D.preprocess_signal_sharded(x, FULL6_STEPS, Namespace(signal_freq=fs), c_lo, C, timing=ar_events,
+                                              profile=group_events)
+    ev1.record()
+    barrier()
+    launches = nat.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = torch.tensor([ev0.elapsed_time(ev1) / steps], dtype=torch.float64, device="cuda")
+    ar = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in ar_events]))], dtype=torch.float64, device="cuda")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    dist.all_reduce(ar, op=dist.ReduceOp.MAX)
+    step_ms = _mean_ms([group_events])
+    # parity: three local rows of rank 0 against the oracle, with the GLOBAL column mean (float64, all-reduced)
+    col = x.sum(dim=0, dtype=torch.float64)
+    dist.all_reduce(col, op=dist.ReduceOp.SUM)
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        rows = [0, (c_hi - c_lo) // 2, c_hi - c_lo - 1]
+        ref, truth, _ = oracle_rows_of_session(x, rows, fs, (col / C).cpu().numpy())
+        parity = parity_record(y[rows].cpu().numpy(), ref, truth, rows,
+                               f"rank 0 rows of the channel-sharded FULL6 output vs the oracle with the global "
+                               f"column mean ({C} channels over {world} ranks)")
+    barrier()
+    del x, y
+    ops.release_workspaces()
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"workload": desc, "channels": C, "samples": T, "fs": fs, "scaling": "strong", "n_gpus": world,
+            "channels_per_rank": c_hi - c_lo, "steps": steps, "ms_per_step": float(ms.item()),
+            "value": C * T / (float(ms.item()) * 1e-3), "unit": "channel-samples/s",
+            "allreduce": {"ms": float(ar.item()), "bytes": 4 * T, "share_of_step": float(ar.item()) / float(ms.item()),
+                          "what": "dist.all_reduce(SUM) of the T float32 CAR column sums, CUDA events around the "
+                                  "call on the compute stream (max over ranks); between ecog_car_colsum and the "
+                                  "Hilbert kernel that subtracts the mean in its load"},
+            "step_ms": step_ms, "gpu_launches": int(launches), "clocks": clocks, "parity": parity}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -213,28 +398,31 @@ def run_ours(args):
             os.close(saved)
 
     from decode_tonal_langauge_b200 import _native as nat
+    from decode_tonal_langauge_b200 import ops
     from decode_tonal_langauge_b200 import runtime as rt
     from decode_tonal_langauge_b200 import synth
     from decode_tonal_langauge_b200.chains import FULL6_STEPS
     from decode_tonal_langauge_b200.preprocessor import preprocess_signal
 
+    if args.workload in SHARDED:
+        if world < 2:
+            raise SystemExit(f"--workload {args.workload} is channel-sharded: run it under torchrun with >= 2 ranks")
+        rec = run_sharded_record(args, torch, dist, world, rank, local, args.workload)
+        if rank == 0:
+            line = {"metric": "channel_samples_per_sec", "value": rec["value"], "unit": rec["unit"], "n_gpus": world,
+                    "steps": rec["steps"], "warmup": max(3, args.warmup), "ms_per_step": rec["ms_per_step"],
+                    "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": rec["workload"], "chain": "FULL6"}, "clocks": rec["clocks"],
+                    "gpu_launches": rec["gpu_launches"], "sharded": rec}
+            print(json.dumps(line), flush=True)
+        dist.destroy_process_group()
+        return
+
     C, T, fs, desc = WORKLOADS[args.workload]
-    sharded = args.workload in SHARDED
-    if sharded:
-        from decode_tonal_langauge_b200 import distributed as D
-        c_lo, c_hi = D.shard_bounds(C, rank, world)
-        # every rank draws the same common-mode / line terms (same seed) and its own channel noise
-        x = synth.device_session(c_hi - c_lo, T, fs, seed=0, channel_seed=rank)
-        C_local = c_hi - c_lo
-    else:
-        x = synth.device_session(C, T, fs, seed=rank)              # one session per rank, resident in HBM
-        C_local = C
+    x = synth.device_session(C, T, fs, seed=rank)              # one session per rank, resident in HBM
     torch.cuda.synchronize()
 
     def step(profile=None):
-        if sharded:
-            y, f, _ = D.preprocess_signal_sharded(x, FULL6_STEPS, Namespace(signal_freq=fs), c_lo, C)
-            return y
         y, f = preprocess_signal(x, FULL6_STEPS, Namespace(signal_freq=fs), profile=profile)
         return y
 
@@ -251,107 +439,157 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     launches0 = nat.launch_count()
-    profiles = []
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        prof = []
-        y = step(prof)
-        profiles.append(prof)
-    ev1.record()
-    barrier()
+    keep = {}
+
+    def timed(prof):
+        keep["y"] = step(prof)
+
+    my_ms, profiles = _timed_steps(timed, args.steps, barrier, torch)
     launches = nat.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
+    y = keep.pop("y")
+    ms = torch.tensor([my_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     total_ms = float(ms.item())
     out_shape = tuple(y.shape)
 
-    # per-step device times (rank 0), dominant kernel = the single-launch Hilbert step
-    step_ms = {}
-    for prof in profiles:
-        for name, a, b in prof:
-            step_ms.setdefault(name, []).append(a.elapsed_time(b))
-    step_ms = {k: float(np.mean(v)) for k, v in step_ms.items()}
-    hil_key = "frequency_filter[hilbert]"
+    # per-group device times (rank 0), dominant kernel = the single-launch Hilbert group
+    step_ms = _mean_ms(profiles)
     peak, peak_src = measured_peaks()
+    hil_key = next((k for k in HILBERT_KEYS if k in step_ms), None)
     hil_ms = step_ms.get(hil_key)
-    hil_gbs = HILBERT_BYTES_PER_SAMPLE * C_local * T / (hil_ms * 1e-3) / 1e9 if hil_ms else None
-    chain_gbs = FULL6_BYTES_PER_SAMPLE * C_local * T / (total_ms / args.steps * 1e-3) / 1e9
-    step_roofline = {k: {"ms": v, "alg_gb": STEP_BYTES_PER_SAMPLE[k] * C_local * T / 1e9,
-                         "achieved_gbs": STEP_BYTES_PER_SAMPLE[k] * C_local * T / (v * 1e-3) / 1e9,
-                         "frac": STEP_BYTES_PER_SAMPLE[k] * C_local * T / (v * 1e-3) / 1e9 / peak}
+    chain_gbs = FULL6_BYTES_PER_SAMPLE * C * T / (total_ms / args.steps * 1e-3) / 1e9
+    step_roofline = {k: {"ms": v, "alg_gb": STEP_BYTES_PER_SAMPLE[k] * C * T / 1e9,
+                         "achieved_gbs": STEP_BYTES_PER_SAMPLE[k] * C * T / (v * 1e-3) / 1e9,
+                         "frac": STEP_BYTES_PER_SAMPLE[k] * C * T / (v * 1e-3) / 1e9 / peak}
                      for k, v in step_ms.items() if k in STEP_BYTES_PER_SAMPLE}
-    traffic = ncu_traffic("hilbert_env8_kernel", C_local, T)
 
-    # ---- end to end through the plug-in call with HOST buffers (pinned), H2D + D2H inside
+    # ---- in-run parity: rows of THIS run's output against the oracle on the same session (rank 0, N = 1)
+    cpu, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        rows = [0, C // 2 + 1, C - 1]
+        col_mean = x.mean(dim=0, dtype=torch.float64).cpu().numpy()
+        ref, truth, dt_cpu = oracle_rows_of_session(x, rows, fs, col_mean)
+        parity = parity_record(y[rows].cpu().numpy(), ref, truth, rows,
+                               "rows of the timed run's own output (default plans, fused groups) vs the oracle on the "
+                               "same synthetic session")
+        cpu = {"value": len(rows) * T / dt_cpu, "unit": "channel-samples/s", "cores": 1, "kind": "port",
+               "sample": f"oracle FULL6 on {len(rows)} rows x {T} samples of the session the GPU arm timed (full session "
+                         f"length; CAR by linearity: the {C}-channel column mean is subtracted up front), 1 thread "
+                         f"(the reference's own execution model), {dt_cpu:.1f} s"}
+        del ref, truth
+
+    # ---- end to end through the plug-in call with HOST buffers, H2D + D2H inside the timed region
     del y
     e2e = None
-    if not args.no_e2e and not sharded:
+    if not args.no_e2e:
+        def e2e_run(xin, n, **kw):
+            yh, _ = preprocess_signal(xin, FULL6_STEPS, Namespace(signal_freq=fs), **kw)        # warm the pinned pools
+            del yh
+            rt.reset_counters()
+            barrier()
+            t0 = time.perf_counter()
+            dtype = None
+            for _ in range(n):
+                yh, _ = preprocess_signal(xin, FULL6_STEPS, Namespace(signal_freq=fs), **kw)
+                _ = float(yh[0, :8].sum())
+                dtype = str(yh.dtype)
+                del yh                      # hand the pinned result buffer back before the next step
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            return float(dt.item()) / n, dtype, rt.h2d_bytes // n, rt.d2h_bytes // n
+
         host_in = torch.empty((C, T), dtype=torch.float32, pin_memory=True)
         host_in.copy_(x)
         torch.cuda.synchronize()
         xin = host_in.numpy()
         e2e_steps = max(2, min(args.steps, 5))
-        rt.reset_counters()
-        yh, _ = preprocess_signal(xin, FULL6_STEPS, Namespace(signal_freq=fs))        # warm the pinned pools
-        del yh
-        rt.reset_counters()
-        barrier()
-        t0 = time.perf_counter()
-        out_dtype = None
-        for _ in range(e2e_steps):
-            yh, _ = preprocess_signal(xin, FULL6_STEPS, Namespace(signal_freq=fs))
-            checksum = float(yh[0, :8].sum())
-            out_dtype = str(yh.dtype)
-            del yh                      # hand the pinned result buffer back before the next step
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        sec, out_dtype, h2d, d2h = e2e_run(xin, e2e_steps)
+        e2e = {"value": world * C * T / sec, "unit": "channel-samples/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": 1e3 * sec,
+               "api": "preprocess_signal(numpy (C,T) float32, pinned) -> numpy float64 (the reference's dtype after its "
+                      "first filtfilt); channel-chunked copies overlapped with the kernels",
+               "out_dtype": out_dtype, "host_cpus": len(host_cpus) if host_cpus else None}
+        # the same call with the device's storage dtype handed back (half the return traffic; explicit option)
+        sec32, dt32, _, d2h32 = e2e_run(xin, 2, output_dtype=np.float32)
+        ceiling = host_copy_ceiling(torch, C * T * 4, out_shape, torch.float64, 12)
+        ceil_t = torch.tensor([ceiling], dtype=torch.float64, device="cuda")
         if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * C * T * e2e_steps / float(dt.item()), "unit": "channel-samples/s",
-               "h2d_bytes_per_step": rt.h2d_bytes // e2e_steps, "d2h_bytes_per_step": rt.d2h_bytes // e2e_steps,
-               "steps": e2e_steps, "ms_per_step": 1e3 * float(dt.item()) / e2e_steps,
-               "api": "preprocess_signal(numpy (C,T) float32 pinned) -> numpy float64 (reference dtype); "
-                      "channel-chunked copies overlapped with the kernels",
-               "out_dtype": out_dtype,
-               "host_cpus": len(host_cpus) if host_cpus else None}     # cores this rank is pinned to (GPU-local NUMA node)
-        del host_in
+            dist.all_reduce(ceil_t, op=dist.ReduceOp.MAX)
+        e2e["variants"] = {
+            "float32_out": {"ms_per_step": 1e3 * sec32, "value": world * C * T / sec32, "out_dtype": dt32,
+                            "d2h_bytes_per_step": d2h32, "api": "preprocess_signal(..., output_dtype=np.float32)"},
+            "host_copy_ceiling": {"ms_per_step": 1e3 * float(ceil_t.item()), "value": world * C * T / float(ceil_t.item()),
+                                  "frac_of_ceiling": float(ceil_t.item()) / sec,
+                                  "what": "pinned H2D of the input, then D2H of a float64 result of the same shape, no "
+                                          "kernels, all ranks at once (max over ranks): what the host memory system and "
+                                          "PCIe allow this contract"}}
+        if world == 1:
+            pageable = np.empty((C, T), dtype=np.float32)          # what np.load hands a caller
+            pageable[:] = xin
+            secp, _, _, _ = e2e_run(pageable, 2)
+            e2e["variants"]["pageable_in"] = {"ms_per_step": 1e3 * secp, "value": C * T / secp,
+                                              "api": "same call, input in pageable host memory (np.load output)"}
+            del pageable
+        del host_in, xin
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline_single(T, fs)
+    # ---- N > 1: the channel-sharded recording (BASELINE configs[3]) with the NCCL CAR all-reduce
+    del x
+    ops.release_workspaces()
+    torch.cuda.empty_cache()
+    sharded = None
+    if world > 1 and not args.no_sharded:
+        sharded = run_sharded_record(args, torch, dist, world, rank, local, "C4")
 
     if rank == 0:
-        units = C * T if sharded else world * C * T
-        value = units * args.steps / (total_ms * 1e-3)
+        value = world * C * T * args.steps / (total_ms * 1e-3)
+        hil_gbs = HILBERT_BYTES_PER_SAMPLE * C * T / (hil_ms * 1e-3) / 1e9 if hil_ms else None
+        rec = ncu_record("hilbert_env8_kernel")
+        fresh = bool(rec) and not rec.get("stale")
+        traffic = rec["dram_bytes_per_channel_sample"] * C * T / 1e9 if fresh else None
+        compute = None
+        if fresh and hil_ms and clocks and clocks.get("sm_mhz"):
+            # warp instructions issued per clock and SM over the live launch time, against the issue
+            # ceiling of this kernel's own instruction mix (scripts/micro/fp32_pipes.cu) and the 4.0 the
+            # four schedulers of an SM can issue
+            ipc = rec["warp_inst_per_channel_sample"] * C * T / (hil_ms * 1e-3) / (148 * clocks["sm_mhz"] * 1e6)
+            compute = {"bound": "issue", "achieved": ipc, "unit": "warp-instructions / clock / SM",
+                       "peak": rec.get("mix_ceiling_ipc", 4.0), "frac": ipc / rec.get("mix_ceiling_ipc", 4.0),
+                       "frac_of_4_ipc": ipc / 4.0, "thread_inst_per_sample": 32 * rec["warp_inst_per_channel_sample"],
+                       "floor_ms_at_4_ipc": rec["warp_inst_per_channel_sample"] * C * T / (4.0 * 148 * clocks["sm_mhz"] * 1e6) * 1e3,
+                       "peak_source": rec.get("mix_ceiling_source", "4 schedulers x 1 warp instruction per clock"),
+                       "source": rec["source"]}
         line = {
             "metric": "channel_samples_per_sec", "value": value, "unit": "channel-samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
-            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": desc, "chain": "FULL6", "channels": C, "samples": T, "fs": fs,
-                       "sharding": ("channels of one recording split over the ranks; CAR column sums "
-                                    "all-reduced over NCCL (T floats per step)") if sharded else
-                                   "one session per rank, no data-path collective",
+                       "sharding": "one session per rank, no data-path collective"
+                                   + ("; plus `sharded`: BASELINE configs[3] channel-sharded with the NCCL CAR all-reduce"
+                                      if sharded else ""),
                        "l2": "inputs larger than L2 (7.4 GB per session); no flush needed",
-                       "output": list(out_shape), "state_dtype": "f64 IIR state / statistics, f32 storage"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "hilbert_env8_kernel (dominant: %.0f%% of the step)" %
-                         (100 * hil_ms / (total_ms / args.steps)) if hil_ms else None,
+                       "output": list(out_shape), "state_dtype": "f64 IIR state / statistics, f32 storage",
+                       "groups": list(step_ms)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "parity": parity,
+            "roofline": {"bound": "issue", "kernel": ("hilbert_env8_kernel (dominant: %.0f%% of the step)" %
+                                                      (100 * hil_ms / (total_ms / args.steps))) if hil_ms else None,
                          "achieved": hil_gbs, "peak": peak, "unit": "GB/s",
                          "frac": hil_gbs / peak if hil_gbs else None,
-                         "traffic": traffic["gb_per_launch"] if traffic else None, "traffic_unit": "GB per launch",
-                         "traffic_source": traffic["source"] if traffic else None,
-                         "algorithmic_gb_per_launch": HILBERT_BYTES_PER_SAMPLE * C_local * T / 1e9,
-                         "peak_source": peak_src,
-                         "note": "issue / shared-memory-pipe / FP32 bound kernel (8.5 FFTs of 4096 points per 3422 samples; ncu: "
-                                 "issue 68 %, LSU data pipe 63 %, FMA pipe 53 %, DRAM 7.5 %), not HBM bound; "
-                                 "see DESIGN.md section 3",
+                         "traffic": traffic, "traffic_unit": "GB per launch",
+                         "traffic_source": (rec["source"] if fresh else
+                                            ("stale: the committed ncu capture predates the kernel source" if rec else None)),
+                         "algorithmic_gb_per_launch": HILBERT_BYTES_PER_SAMPLE * C * T / 1e9,
+                         "peak_source": peak_src, "compute": compute,
+                         "note": "achieved/peak/frac are the HBM roofline of the contract (algorithmic 8 B per sample over the "
+                                 "live launch time); the kernel is instruction-issue / shared-memory-pipe / FP32 bound "
+                                 "(8.5 FFTs of 4096 points per 3422 samples), see `compute` and DESIGN.md section 3",
                          "chain_achieved": chain_gbs, "chain_frac": chain_gbs / peak,
                          "chain_bytes_per_sample": FULL6_BYTES_PER_SAMPLE, "steps": step_roofline},
-            "cpu_baseline": cpu, "step_ms": step_ms,
+            "cpu_baseline": cpu, "step_ms": step_ms, "sharded": sharded,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -444,6 +682,7 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS) + ["C3"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the channel-sharded configs[3] sub-record")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print("note: fewer than 3 warm-up steps; numbers are not reportable", file=sys.stderr)

@@ -1,0 +1,302 @@
+// Shared pieces of the IIR biquad-cascade kernels (K3): constants, the cascade step and the
+// warm-up sweep kernel, used by sosfilt.cu (single cascades, scan path, entry points) and
+// sosfilt_pair.cu (two cascades fused into one sweep pair).
+#pragma once
+#include "common.cuh"
+
+namespace ecog {
+
+constexpr int kSosThreads = 512;
+constexpr int kSub = 16;              // samples per stage per chunk
+constexpr int kPitch = kSub + 4;      // shared row pitch in floats (conflict-free LDS.128)
+constexpr int kRing = 2;
+constexpr int kWarmRing = 5;      // warm-up kernel: tile slots (prefetch distance kWarmRing - 1), one barrier per stage
+constexpr int kWSub = 16;         // warm-up kernel: samples per stage per chunk (64 B per chunk and stage; 128 B measured no faster)
+constexpr int kWPitch = kWSub;   // no padding: the 16-byte pieces of a row are XOR-swizzled (conflict-free LDS.128)
+
+struct SosCoef {
+    double c[ECOG_MAX_SECTIONS][5];   // b0 b1 b2 a1 a2
+    double zi[ECOG_MAX_SECTIONS][2];
+};
+struct SosMatrix { double m[2 * ECOG_MAX_SECTIONS][2 * ECOG_MAX_SECTIONS]; };
+
+// Numerator forms (NUM):
+//   0  general b0 b1 b2                                   5 FP64 ops per section and sample
+//   1  b1 == 0                                            4
+//   2  unit form  g * (1 + beta1 z^-1 + z^-2) per section: the gain g of the cascade is applied
+//      once to the input, sections are monic with b2 == +1 (Butterworth band-stop / low-pass /
+//      high-pass: zeros on the unit circle)               4, and one multiply per sample
+//   5  unit form with b1 == 0 and b2 == -1, the (1 - z^-2) sections of a Butterworth band-pass
+//                                                         3, and one multiply per sample
+// In the unit forms c[j][1] holds beta1 = b1 / b0; the states are those of the general form.
+template <int J0, int J1, int NUM, int NSEC>
+__device__ __forceinline__ double sos_range(double u, const double (&c)[NSEC][5], double (&s)[NSEC][2]) {
+    constexpr bool B1Z = (NUM & 1) != 0;
+    constexpr int UNIT = NUM >> 1;              // 0 general, 1: b0 = 1, b2 = +1, 2: b0 = 1, b2 = -1
+#pragma unroll
+    for (int j = J0; j < J1; ++j) {
+        const double y = UNIT ? u + s[j][0] : fma(c[j][0], u, s[j][0]);
+        s[j][0] = B1Z ? fma(-c[j][3], y, s[j][1]) : fma(-c[j][3], y, fma(c[j][1], u, s[j][1]));
+        s[j][1] = UNIT == 1 ? fma(-c[j][4], y, u) : UNIT == 2 ? fma(-c[j][4], y, -u) : fma(-c[j][4], y, c[j][2] * u);
+        u = y;
+    }
+    return u;
+}
+
+// NUMB < 0: one numerator form for the whole cascade.  NUMB >= 0: a PAIR of 4-section cascades run
+// as one (NSEC == 8): sections 0-3 in form NUM, sections 4-7 in form NUMB (both unit forms, the
+// product of the two gains rides on the input); `full` = false runs the first cascade only (early
+// warm-up: the second cascade forgets faster and starts later from a zero state).
+template <int NSEC, int NUM = 0, int NUMB = -1>
+__device__ __forceinline__ double sos_step(double u, const double (&c)[NSEC][5], double (&s)[NSEC][2], bool full = true) {
+    if (NUMB < 0) return sos_range<0, NSEC, NUM, NSEC>(u, c, s);
+    u = sos_range<0, NSEC / 2, NUM, NSEC>(u, c, s);
+    if (full) u = sos_range<NSEC / 2, NSEC, (NUMB < 0 ? 0 : NUMB), NSEC>(u, c, s);
+    return u;
+}
+
+// WRITE=false: tail pass (zero state, last `tail` samples, end state -> slot k+1)
+// WRITE=true : main pass (state from slot k, float32 output)
+// ------------------------------------------------------------------ warm-up path
+// Single kernel per sweep, no scan: when the cascade forgets a zero-state start within
+// `tail` samples (max |A^tail| < 1e-10, decided by the host) a chunk's true start state is
+// reproduced by running the recurrence from a ZERO state over the `tail` samples that precede
+// the chunk.  One thread = one chunk: stages -tail/16 .. -1 are the warm-up (loads only),
+// stages 0 .. L/16-1 filter the chunk and are written.  Chunks whose warm-up would cross the
+// row edge are exact instead: the filtfilt start-up state (zi * ext[0] pushed through the odd
+// extension pad) is injected at the stage where the row starts.  Redundant work is tail/L,
+// against a full extra pass for the scan path, and the chunk length is chosen for a few
+// warps per scheduler only (the FP64 pipe saturates early), which makes L long.
+// Thread q -> (row q / nChunks, chunk q % nChunks): a CTA walks neighbouring chunks of one row
+// (few DRAM pages / TLB entries live per CTA).
+// The backward sweep cannot run in place (its warm-up reads the forward result of the
+// neighbouring chunk), so the forward result lives in the workspace.
+template <int NSEC, bool REV, bool VEC, int NT, int NUM, int NUMB = -1>
+__global__ void __launch_bounds__(NT, 512 / NT)
+sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, int64_t T,
+                int64_t ldx, int64_t ldy, int L, int tail, int nChunks, int padlen, int zero_phase,
+                SosCoef coef, double* __restrict__ padbuf, double gain, int tail_b) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* tiles = reinterpret_cast<float*>(smem_raw);                                   // [kWarmRing][NT][kWPitch]
+    int64_t* soff = reinterpret_cast<int64_t*>(tiles + (size_t)kWarmRing * NT * kWPitch); // [NT] x offset of the chunk edge
+    int64_t* doff = soff + NT;                                                           // [NT] y offset of the chunk edge
+    int2* lohi = reinterpret_cast<int2*>(doff + NT);                                     // [NT] valid logical offsets
+    constexpr int PE = 4;                       // samples per piece (one 16 B copy when VEC)
+    constexpr int PP = kWSub / PE;              // pieces per tile row
+    constexpr int RPB = 32 / kWSub;             // tile rows per 128 bytes of shared memory (swizzle period)
+    constexpr int NJ = PP;                      // pieces each thread moves per stage
+
+    const int tid = threadIdx.x;
+    const int64_t q = (int64_t)blockIdx.x * NT + tid;
+    const bool valid = q < C * nChunks;
+    const int64_t row = valid ? q / nChunks : 0;
+    const int k = valid ? (int)(q - row * nChunks) : 0;
+    int64_t edge; int ulo, uhi;
+    {
+        int64_t a, b;
+        if (!REV) { a = (int64_t)k * L; b = a + L < T ? a + L : T; }
+        else      { b = T - (int64_t)k * L; a = b - L > 0 ? b - L : 0; }
+        const int64_t bef = REV ? T - b : a;            // samples between the row edge and the chunk, sweep order
+        edge = REV ? b : a;
+        ulo = valid ? (bef < tail ? -(int)bef : -tail) : 0;
+        uhi = valid ? (int)(b - a) : 0;
+    }
+    soff[tid] = row * ldx + edge;
+    doff[tid] = row * ldy + edge;
+    lohi[tid] = make_int2(ulo, uhi);
+    __syncthreads();
+    const int pc = tid % PP;                    // this thread moves piece pc of tile rows tid / PP + j * (NT / PP)
+
+    double c[NSEC][5], s[NSEC][2];
+    // unit forms take the cascade gain on the input
+#define IN(v) ((NUM >> 1) ? gain * (v) : (v))
+#pragma unroll
+    for (int j = 0; j < NSEC; ++j) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) c[j][i] = coef.c[j][i];
+        s[j][0] = 0.0; s[j][1] = 0.0;
+    }
+    // chunks that see the row edge get the exact start-up at the stage where the row starts
+    const int64_t before = REV ? T - edge : edge;
+    const int s_inject = valid && before <= tail ? -(int)(before / kWSub) : (1 << 30);
+    // cascade pair: the second cascade joins the warm-up tail_b samples before the chunk (or at the
+    // exact start-up of a chunk that sees the row edge)
+    const int s_full = NUMB < 0 ? -(1 << 30) : (s_inject < -(tail_b / kWSub) ? s_inject : -(tail_b / kWSub));
+
+    const int nStages = L / kWSub;
+    const int first = -(tail / kWSub);
+
+    // logical offset of the first element of piece pc in stage st, and its distance from the chunk edge
+    auto issue = [&](int stage) {
+        if (stage < nStages) {
+            float* tile = tiles + (size_t)((stage - first) % kWarmRing) * NT * kWPitch;
+            const int u0 = !REV ? stage * kWSub + PE * pc : stage * kWSub + (kWSub - PE) - PE * pc;
+            const int off = !REV ? u0 : -u0 - PE;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int r = tid / PP + j * (NT / PP);
+                const int2 lh = lohi[r];
+                const float* g = x + soff[r];
+                float* d = tile + r * kWPitch + PE * (pc ^ ((r / RPB) & (PP - 1)));
+                if (VEC) {
+                    const bool ok = u0 >= lh.x && u0 + PE <= lh.y;
+                    cp_async16_zfill(d, ok ? g + off : g, ok);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < PE; ++e) {
+                        const int u = !REV ? u0 + e : u0 + PE - 1 - e;      // element e in ascending address order
+                        const bool ok = u >= lh.x && u < lh.y;
+                        cp_async4_zfill(d + e, ok ? g + off + e : g, ok);
+                    }
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    // kWarmRing tile slots, ONE barrier per stage: the barrier that publishes the results of stage st
+    // also publishes the tiles of stage st + 1 (every thread has waited for its own copies); the
+    // slot refilled after it (stage st + kWarmRing - 1) was last read by the store of stage st - 1.
+    // Four stages of loads stay in flight per CTA, so neither the copy wait nor the barrier sees
+    // DRAM latency.
+#pragma unroll
+    for (int i = 0; i < kWarmRing - 1; ++i) issue(first + i);
+    cp_async_wait<kWarmRing - 2>();
+    __syncthreads();
+    for (int st = first; st < nStages; ++st) {
+        if (st == s_inject && zero_phase) {
+            // filtfilt start-up: zi * ext[0], then the odd-extension pad (zero state for the causal filter)
+            if (!REV) {
+                const float* xr = x + row * ldx;
+                const float x0 = xr[0];
+                const float e0 = 2.0f * x0 - xr[padlen];
+#pragma unroll
+                for (int j = 0; j < NSEC; ++j) { s[j][0] = coef.zi[j][0] * (double)e0; s[j][1] = coef.zi[j][1] * (double)e0; }
+                for (int i = 0; i < padlen; ++i) {
+                    const float e = 2.0f * x0 - xr[padlen - i];
+                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)e), c, s);
+                }
+            } else {
+                const double* pb = padbuf + row * padlen;
+                const double y0 = pb[padlen - 1];
+#pragma unroll
+                for (int j = 0; j < NSEC; ++j) { s[j][0] = coef.zi[j][0] * y0; s[j][1] = coef.zi[j][1] * y0; }
+                for (int i = padlen - 1; i >= 0; --i) (void)sos_step<NSEC, NUM, NUMB>(IN(pb[i]), c, s);
+            }
+        }
+        float* tile = tiles + (size_t)((st - first) % kWarmRing) * NT * kWPitch;
+        float* mine = tile + tid * kWPitch;
+        const int swz = (tid / RPB) & (PP - 1);
+        float4 xin[kWSub / 4];
+#pragma unroll
+        for (int v = 0; v < kWSub / 4; ++v) {
+            if (!REV) {
+                xin[v] = *reinterpret_cast<const float4*>(mine + 4 * (v ^ swz));
+            } else {
+                float4 t4 = *reinterpret_cast<const float4*>(mine + 4 * ((PP - 1 - v) ^ swz));
+                xin[v] = make_float4(t4.w, t4.z, t4.y, t4.x);
+            }
+        }
+        const bool write = st >= 0;
+        const int sbase = st * kWSub;
+        if (NUMB >= 0 && st < s_full) {                      // early warm-up of a pair: first cascade only, nothing stored
+            if (sbase >= ulo && sbase + kWSub <= uhi) {
+#pragma unroll
+                for (int v = 0; v < kWSub / 4; ++v) {
+                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].x), c, s, false);
+                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].y), c, s, false);
+                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].z), c, s, false);
+                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].w), c, s, false);
+                }
+            }
+        } else if (sbase >= ulo && sbase + kWSub <= uhi) {          // whole stage inside the row: the common case
+#pragma unroll
+            for (int v = 0; v < kWSub / 4; ++v) {
+                float4 yv;
+                yv.x = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].x), c, s);
+                yv.y = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].y), c, s);
+                yv.z = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].z), c, s);
+                yv.w = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].w), c, s);
+                if (write) {
+                    if (!REV) *reinterpret_cast<float4*>(mine + 4 * (v ^ swz)) = yv;
+                    else *reinterpret_cast<float4*>(mine + 4 * ((PP - 1 - v) ^ swz)) = make_float4(yv.w, yv.z, yv.y, yv.x);
+                }
+            }
+        } else {                                            // outside the row / ragged chunk end: state frozen
+#pragma unroll
+            for (int v = 0; v < kWSub / 4; ++v) {
+                const float xv[4] = {xin[v].x, xin[v].y, xin[v].z, xin[v].w};
+                float yv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int u = sbase + 4 * v + e;
+                    if (u >= ulo && u < uhi) yv[e] = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xv[e]), c, s);
+                }
+                if (write) {
+                    if (!REV) *reinterpret_cast<float4*>(mine + 4 * (v ^ swz)) = make_float4(yv[0], yv[1], yv[2], yv[3]);
+                    else *reinterpret_cast<float4*>(mine + 4 * ((PP - 1 - v) ^ swz)) = make_float4(yv[3], yv[2], yv[1], yv[0]);
+                }
+            }
+        }
+        cp_async_wait<kWarmRing - 3>();        // this thread's copies of stage st + 1 have landed
+        __syncthreads();
+        issue(st + kWarmRing - 1);
+        if (write) {
+            const int u0 = !REV ? sbase + PE * pc : sbase + (kWSub - PE) - PE * pc;
+            const int off = !REV ? u0 : -u0 - PE;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                const int r = tid / PP + j * (NT / PP);
+                const int hi = lohi[r].y;
+                float* g = y + doff[r] + off;
+                const float4 v4 = *reinterpret_cast<const float4*>(tile + r * kWPitch + PE * (pc ^ ((r / RPB) & (PP - 1))));
+                if (VEC) {
+                    if (u0 + PE <= hi) *reinterpret_cast<float4*>(g) = v4;
+                } else {
+                    const float ve[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                    for (int e = 0; e < PE; ++e) {
+                        const int u = !REV ? u0 + e : u0 + PE - 1 - e;
+                        if (u < hi) g[e] = ve[e];
+                    }
+                }
+            }
+        }
+    }
+    cp_async_wait<0>();
+
+    // forward sweep: the thread that owns a row's last chunk runs on through the right odd-extension
+    // pad (float32 like scipy's odd_ext) and keeps the filtered pad in float64 for the backward start-up
+    if (!REV && zero_phase && valid && k == nChunks - 1) {
+        const float* xr = x + row * ldx;
+        const float xe = xr[T - 1];
+        double* pb = padbuf + row * padlen;
+        for (int i = 0; i < padlen; ++i) {
+            const float e = 2.0f * xe - xr[T - 2 - i];
+            pb[i] = sos_step<NSEC, NUM, NUMB>(IN((double)e), c, s);
+        }
+    }
+}
+#undef IN
+
+
+// numerator form of sections [j0, j1): 2 = unit (1 + beta z^-1 + z^-2), 5 = unit (1 - z^-2), 0 = general.
+// `lead` = the section allowed to carry the gain in b0.
+inline int unit_form(const SosCoef& coef, int j0, int j1, int lead) {
+    bool b1z = true, unit_p = true, unit_m = true;
+    for (int j = j0; j < j1; ++j) {
+        const double b0 = coef.c[j][0], b2 = coef.c[j][2];
+        b1z = b1z && coef.c[j][1] == 0.0;
+        const bool b0ok = b0 != 0.0 && (j == lead || b0 == 1.0);
+        unit_p = unit_p && b0ok && b2 == b0;
+        unit_m = unit_m && b0ok && b2 == -b0;
+    }
+    return unit_p ? 2 : (unit_m && b1z ? 5 : 0);
+}
+
+// defined in sosfilt_pair.cu
+int run_sos_warm_pair(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                      const ecog_sos_plan& p, const SosCoef& coef_in, float* tmp, int64_t ldt, double* padbuf,
+                      cudaStream_t st);
+
+}  // namespace ecog

@@ -285,6 +285,18 @@ class SosDesign:
         return int(self.sos.shape[0])
 
 
+NUMERATOR_TOL = 1e-6      # max-norm relative output difference (white noise) that still counts as "the same filter"
+
+
+def numerator_deviation(sos_exact: np.ndarray, sos_alt: np.ndarray, n: int = 1 << 17) -> float:
+    """max|y_exact - y_alt| / max|y_exact| for a fixed white-noise input through the two cascades
+    (same poles, different numerator factorisations), float64, zero state."""
+    u = np.random.default_rng(20230101).standard_normal(n)
+    y1 = sp_signal.sosfilt(sos_exact, u)
+    y2 = sp_signal.sosfilt(sos_alt, u)
+    return float(np.max(np.abs(y1 - y2)) / np.max(np.abs(y1)))
+
+
 @functools.lru_cache(maxsize=64)
 def _butter_design(order: int, freqs: Tuple[float, ...], fs: float, btype: str, causal: bool) -> SosDesign:
     wn = np.asarray(freqs, dtype=float) / (0.5 * fs)
@@ -296,28 +308,34 @@ def _butter_design(order: int, freqs: Tuple[float, ...], fs: float, btype: str, 
     # ref: frequency_filter.py:226-227 -- (b, a) + filtfilt defaults
     b, a = sp_signal.butter(order, wn, btype=btype)
     sos = ba_to_sos(b, a)
-    if btype == "bandpass":
-        # scipy's rounded numerator IS b[0] (1 - z^-2)^order to the last bit; use that factorisation
-        # ((1, 0, -1) sections, b1 == 0: one DFMA less per section) instead of the numerically
-        # split 4-fold roots at +1 and -1
+    # Cheaper numerator forms (csrc/sos_common.cuh).  Butterworth zeros sit ON the unit circle, so the
+    # ideal numerator is b[0] (1 - z^-2)^order (band-pass) or b[0] (1 + beta z^-1 + z^-2)^nsec (band-stop,
+    # low-/high-pass), and it equals scipy's ROUNDED b to ~1e-16 in every coefficient.  That is not the
+    # same as "the same filter": next to a multiple zero the polynomial's VALUE is tiny (|B| ~ 1e-12 at the
+    # edges of a 4-Hz notch at 3 kHz), so a 1e-16 change of the coefficients moves the response there by
+    # 1e-4 -- the rounded b has its zeros on a ring of radius ~(1e-16)^(1/nsec) around the ideal one.
+    # The reference's filter IS the rounded (b, a); its exact factors (`sos`, mpmath) reproduce the
+    # long-double evaluation of the reference to 2e-7 (58-62 Hz at 3 kHz), the ideal form only to 5e-4.
+    # So the ideal form is used only when the two give the same output to NUMERATOR_TOL on white noise.
+    unit = None
+    if btype == "bandpass" and sos.shape[0] == order:
         ideal = b[0] * np.poly(np.r_[np.ones(order), -np.ones(order)])
-        if np.max(np.abs(ideal - b)) <= 4e-16 * np.max(np.abs(b)) and sos.shape[0] == order:
-            sos[:, :3] = [1.0, 0.0, -1.0]
-            sos[0, :3] *= b[0]
+        if np.max(np.abs(ideal - b)) <= 4e-16 * np.max(np.abs(b)):
+            unit = sos.copy()
+            unit[:, :3] = [1.0, 0.0, -1.0]
+            unit[0, :3] *= b[0]
     elif btype in ("bandstop", "lowpass", "highpass") and sos.shape[0] * 2 == len(b) - 1:
-        # likewise b[0] (1 + beta z^-1 + z^-2)^nsec with the zeros ON the unit circle (beta = -2 cos w0
-        # for a band-stop, +2 / -2 for low- / high-pass).  The roots of the ROUNDED polynomial are a
-        # ring of radius ~(1e-16)^(1/nsec) around them; the unit-circle sections reproduce the
-        # reference's coefficients to rounding and cost one FP64 operation less per section
-        # (b2 == b0: csrc/sosfilt.cu, numerator form 2).
         nsec = sos.shape[0]
         beta = b[1] / (nsec * b[0])
         ideal = np.array([1.0])
         for _ in range(nsec):
             ideal = np.convolve(ideal, [1.0, beta, 1.0])
         if np.max(np.abs(b[0] * ideal - b)) <= 2e-15 * np.max(np.abs(b)):
-            sos[:, :3] = [1.0, beta, 1.0]
-            sos[0, :3] *= b[0]
+            unit = sos.copy()
+            unit[:, :3] = [1.0, beta, 1.0]
+            unit[0, :3] *= b[0]
+    if unit is not None and numerator_deviation(sos, unit) <= NUMERATOR_TOL:
+        sos = unit
     zi_direct = sp_signal.lfilter_zi(b, a)          # the installed scipy's own arithmetic
     zi = zi_to_cascade(b, a, sos, zi_direct)
     padlen = 3 * max(len(a), len(b))
@@ -331,10 +349,10 @@ def butter_design(freqs, fs, order=4, causal=False, filter_type="bandpass") -> S
 
 def pair_design(A: SosDesign, B: SosDesign):
     """Two 4-section zero-phase designs as ONE 8-section cascade for the fused sweep pair
-    (csrc/sosfilt.cu, split = 4): sections 0-3 = A with the product of both gains on section 0,
-    sections 4-7 = B with a monic first section.  Returns ``(design, tail_b)`` -- ``tail_b`` is the
+    (csrc/sosfilt_pair.cu, split = 4): sections 0-3 = A, sections 4-7 = B; when B is of unit form its
+    first section is made monic and its gain joins A's section 0.  Returns ``(design, tail_b)`` -- ``tail_b`` is the
     warm-up length of the second cascade (it forgets faster than the pair and joins the warm-up
-    late) -- or None when either numerator is not of unit form."""
+    late) -- or None for a combination of numerator forms the kernel is not instantiated for."""
     return _pair_design(A.sos.tobytes(), B.sos.tobytes(), A.padlen, B.padlen)
 
 
@@ -345,17 +363,22 @@ def _pair_design(a_bytes: bytes, b_bytes: bytes, pad_a: int, pad_b: int):
     if sa.shape[0] != 4 or sb.shape[0] != 4:
         return None
 
-    def unit(sos):
-        g = sos[0, 0]
-        ok = g != 0.0 and np.all(sos[1:, 0] == 1.0) and np.all(np.abs(sos[:, 2]) == np.abs(sos[:, 0]))
-        same = np.all(sos[:, 2] == sos[:, 0]) or (np.all(sos[:, 2] == -sos[:, 0]) and np.all(sos[:, 1] == 0.0))
-        return bool(ok and same and np.all(sos[:, 3] == 1.0))
+    def form(sos):
+        """Numerator form as the kernel classifies it (csrc/sos_common.cuh::unit_form)."""
+        ok = sos[0, 0] != 0.0 and np.all(sos[1:, 0] == 1.0) and np.all(sos[:, 3] == 1.0)
+        if ok and np.all(sos[:, 2] == sos[:, 0]):
+            return 2
+        if ok and np.all(sos[:, 2] == -sos[:, 0]) and np.all(sos[:, 1] == 0.0):
+            return 5
+        return 0
 
-    if not (unit(sa) and unit(sb)):
+    fa, fb = form(sa), form(sb)
+    if (fa, fb) not in {(2, 5), (0, 5), (5, 2), (5, 0), (5, 5), (2, 2), (0, 0)}:
         return None
-    gb = sb[0, 0]
-    sb[0, :3] /= gb
-    sa[0, :3] *= gb
+    if fb:                      # unit second half: monic, its gain joins section 0 of the first half
+        gb = sb[0, 0]
+        sb[0, :3] /= gb
+        sa[0, :3] *= gb
     sos = np.ascontiguousarray(np.vstack([sa, sb]))
     zi = sp_signal.sosfilt_zi(sos)          # unit-step steady state in the kernel's DF2T coordinates
     dsg = SosDesign(sos, np.ascontiguousarray(zi), max(pad_a, pad_b), True)

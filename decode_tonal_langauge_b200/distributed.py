@@ -68,13 +68,15 @@ def car_sharded(x_local: torch.Tensor, c_lo: int, n_channels: int, exclude_chann
 
 
 def preprocess_signal_sharded(x_local, steps: List[dict], block_params: Namespace, c_lo: int, n_channels: int,
-                              group=None, backend=None, fuse: Optional[bool] = None, timing: Optional[list] = None):
+                              group=None, backend=None, fuse: Optional[bool] = None, timing: Optional[list] = None,
+                              profile: Optional[list] = None):
     """``preprocess_signal`` for a channel shard resident on this rank's device: identical step
     semantics (same shared parameter Namespace, same fusion groups), except that the CAR column
     sums are all-reduced between the two kernel enqueues.  Returns ``(local tensor, signal_freq,
     bands)`` where ``bands`` is the number of concatenated band copies the local rows are organised
     in (see ``gather_channels``).  ``timing``: optional list; a (start, end) CUDA-event pair is appended
-    around every all-reduce (recorded on the current stream)."""
+    around every all-reduce (recorded on the current stream); ``profile``: optional list, one (group name,
+    start, end) CUDA-event triple per executed group (the all-reduce lies inside its CAR group)."""
     from . import preprocessor as P
     x = x_local
     bands = 1
@@ -94,6 +96,9 @@ def preprocess_signal_sharded(x_local, steps: List[dict], block_params: Namespac
             dist.all_reduce(colsum, op=dist.ReduceOp.SUM, group=group)
 
     for g in groups:
+        if profile is not None and x.is_cuda:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
         if g[0] == "step" and P._short(g[1]) == "car_rereference":
             P.apply_step_params(block_params, g[1])
             excl = getattr(block_params, "exclude_channels", None)
@@ -112,6 +117,10 @@ def preprocess_signal_sharded(x_local, steps: List[dict], block_params: Namespac
             x = P._run_group(x, g, block_params, False)
             if g[0] == "step" and P._short(g[1]) == "frequency_filter":
                 bands *= max(1, len(getattr(block_params, "bands", []) or []))
+        if profile is not None and x.is_cuda:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            profile.append((P._group_name(g), ev0, ev1))
     return x, block_params.signal_freq, bands
 
 

@@ -243,7 +243,7 @@ def copy2d(dst: torch.Tensor, src: torch.Tensor) -> None:
 
 def pair_plan(Cn: int, T: int, ld_ok: bool, A: D.SosDesign, B: D.SosDesign):
     """Plan of the fused cascade pair for a (Cn, T) recording, or None when the pair cannot run
-    (short rows, too few chunks for the 512-thread kernel, non-unit numerators, misaligned rows)."""
+    (rows too short for the warm-up, non-unit numerators, misaligned rows)."""
     if not (A.zero_phase and B.zero_phase and A.nsec == 4 and B.nsec == 4 and ld_ok and T % 4 == 0):
         return None
     comb = D.pair_design(A, B)
@@ -252,7 +252,7 @@ def pair_plan(Cn: int, T: int, ld_ok: bool, A: D.SosDesign, B: D.SosDesign):
     dsg, tail_b = comb
     L = D.choose_warm_chunk(Cn, T, _sos_threads_per_sm())
     n_chunks = -(-T // L)
-    if n_chunks < 2 or Cn * n_chunks < 2 * D.NUM_SMS * 512:
+    if n_chunks < 2:
         return None
     # forgetting time judged in the two filters' own state scaling (folding both gains onto the input
     # only rescales the first cascade's states; it does not make the pair remember longer)
@@ -260,7 +260,8 @@ def pair_plan(Cn: int, T: int, ld_ok: bool, A: D.SosDesign, B: D.SosDesign):
     tail = D.warm_tail(natural, min(int(D.WARM_MAX_OVERHEAD * L), T + D.SUB))
     if tail < 0 or 4 * tail + 64 > T:
         return None
-    plan = nat.SosPlan(8, 1, dsg.padlen, L, tail, nat.SOS_WARMUP, 512, 4, min(tail_b, tail))
+    threads = 512 if Cn * n_chunks >= 2 * D.NUM_SMS * 512 else 256
+    plan = nat.SosPlan(8, 1, dsg.padlen, L, tail, nat.SOS_WARMUP, threads, 4, min(tail_b, tail))
     return dsg, plan, tail
 
 

@@ -120,22 +120,31 @@ def odd_extension(x: np.ndarray, n: int) -> np.ndarray:
     return np.concatenate((left, x, right), axis=-1)
 
 
-def filtfilt_pad(b, a, x, dtype=np.float64) -> np.ndarray:
+def filtfilt_pad(b, a, x, dtype=np.float64, reference_edges: bool = False) -> np.ndarray:
     """scipy ``filtfilt`` defaults (padtype='odd', padlen=3*max(len(a),len(b)),
     method='pad'), scipy: signal/_signaltools.py:4892-4960, as called by
     ref: frequency_filter.py:226-227.  ``dtype=np.longdouble`` gives the
-    extended-precision "truth" of SURVEY.md section 8c."""
+    extended-precision "truth" of SURVEY.md section 8c.  ``reference_edges=True`` keeps the two
+    edge ingredients exactly as the float64 reference forms them -- the odd extension in the INPUT's
+    dtype and ``lfilter_zi`` in float64 -- and widens only the recursion: the error that is left is the
+    round-off of the 8th-order direct form, which is what the long-double rule is about."""
+    b64 = np.asarray(b, dtype=np.float64)
+    a64 = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=dtype)
     a = np.asarray(a, dtype=dtype)
     x = np.asarray(x)
-    if dtype != np.float64:
+    if dtype != np.float64 and not reference_edges:
         x = x.astype(dtype)
     edge = 3 * max(len(a), len(b))
     if x.shape[-1] <= edge:
         raise ValueError(
             f"The length of the input vector x must be greater than padlen, which is {edge}.")
     ext = odd_extension(x, edge)     # in the INPUT's dtype (float32 data -> float32 pad), as scipy does
-    zi = lfilter_zi(b, a)            # same arithmetic width as the recursion
+    if reference_edges:
+        ext = ext.astype(dtype)
+        zi = lfilter_zi(b64, a64).astype(dtype)
+    else:
+        zi = lfilter_zi(b, a)        # same arithmetic width as the recursion
     zshape = [1] * x.ndim
     zshape[-1] = zi.size
     zi = zi.reshape(zshape)

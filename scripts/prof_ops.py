@@ -12,11 +12,12 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from decode_tonal_langauge_b200 import fftplan as FP  # noqa: E402
+from decode_tonal_langauge_b200 import design as DSG  # noqa: E402
 from decode_tonal_langauge_b200 import ops  # noqa: E402
 
 op, C, T = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
-fs = 2000.0
+fs = float(os.environ.get("ECOG_PROF_FS", "2000"))
 x = torch.randn((C, T), device="cuda") * 30
 
 
@@ -36,7 +37,12 @@ FN = {
     "bandpass_scan": lambda: ops.butter(x, [70, 150], fs, 4, False, "bandpass", mode="scan"),
     "car": lambda: ops.car(x),
     "zscore": lambda: ops.zscore(x),
+    "pair": lambda: ops.sosfilt_pair(x, DSG.butter_design([58, 62], fs, 4, False, "bandstop"),
+                                     DSG.butter_design([70, 150], fs, 4, False, "bandpass")),
+    "colsum": lambda: ops.car_colsum(x),
+    "hilbert_car": lambda: ops.hilbert(x, fs, [70.0, 150.0], car=(COLSUM, C)),
 }
+COLSUM = torch.zeros(T, device="cuda") if "hilbert_car" in op or op == "all" else None
 
 
 def run(name):
