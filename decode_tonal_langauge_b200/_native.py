@@ -20,6 +20,7 @@ ABI_VERSION = 5
 MAX_SECTIONS = 8
 SOS_SCAN = 0
 SOS_WARMUP = 1
+SOS_WARMUP_TMA = 2
 HILBERT_N = 4096
 
 
@@ -64,6 +65,7 @@ PROTOTYPES = {
     "ecog_abi_version": (C.c_int, []),
     "ecog_last_error": (C.c_char_p, []),
     "ecog_launch_count": (_I64, []),
+    "ecog_launch_log": (C.c_char_p, [C.c_int]),
     "ecog_car": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _F64, _P]),
     "ecog_car_colsum": (C.c_int, [_P, _I64, _I64, _I64, _P, _P, _P]),
     "ecog_car_apply": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _F64, _P]),
@@ -128,6 +130,12 @@ def check(rc: int) -> None:
     if rc == ECOG_E_UNSUPPORTED:
         raise NotImplementedError(msg)
     raise NativeError(f"libecog_sm100 error {rc}: {msg}")
+
+
+def launch_log(reset: bool = True) -> list:
+    """Names of the kernels this thread launched since the last reset (test / bench bookkeeping)."""
+    raw = (lib.ecog_launch_log(1 if reset else 0) or b"").decode()
+    return [k for k in raw.split(",") if k]
 
 
 def launch_count() -> int:

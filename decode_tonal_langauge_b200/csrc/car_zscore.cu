@@ -15,6 +15,8 @@ namespace ecog {
 
 thread_local char g_err[512] = "";
 thread_local int64_t g_launches = 0;
+thread_local char g_launch_log[4096] = "";
+thread_local int g_launch_log_len = 0;
 
 constexpr int kCarThreads = 256;
 
@@ -250,6 +252,12 @@ using namespace ecog;
 extern "C" int ecog_abi_version(void) { return ECOG_ABI_VERSION; }
 extern "C" const char* ecog_last_error(void) { return g_err; }
 extern "C" int64_t ecog_launch_count(void) { return g_launches; }
+extern "C" const char* ecog_launch_log(int reset) {
+    static thread_local char out[4096];
+    memcpy(out, g_launch_log, sizeof(out));
+    if (reset) { g_launch_log_len = 0; g_launch_log[0] = 0; }
+    return out;
+}
 
 extern "C" int ecog_car(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ld, int64_t ldy,
                         const float* d_w, double inv_count, ecog_stream_t stream) {

@@ -14,6 +14,8 @@ constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 
 extern thread_local char g_err[512];
 extern thread_local int64_t g_launches;
+extern thread_local char g_launch_log[4096];     // names of the most recent launches, comma separated
+extern thread_local int g_launch_log_len;
 
 inline int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -25,6 +27,15 @@ inline int fail(int code, const char* fmt, ...) {
 
 inline int check_launch(const char* what) {
     ++g_launches;
+    {   // bookkeeping for tests / bench: which kernel families ran (ecog_launch_log)
+        const int n = (int)strlen(what);
+        if (g_launch_log_len + n + 2 < (int)sizeof(g_launch_log)) {
+            if (g_launch_log_len) g_launch_log[g_launch_log_len++] = ',';
+            memcpy(g_launch_log + g_launch_log_len, what, n);
+            g_launch_log_len += n;
+            g_launch_log[g_launch_log_len] = 0;
+        }
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ECOG_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
     return ECOG_OK;

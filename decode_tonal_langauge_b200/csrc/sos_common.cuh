@@ -28,11 +28,28 @@ struct SosMatrix { double m[2 * ECOG_MAX_SECTIONS][2 * ECOG_MAX_SECTIONS]; };
 //      high-pass: zeros on the unit circle)               4, and one multiply per sample
 //   5  unit form with b1 == 0 and b2 == -1, the (1 - z^-2) sections of a Butterworth band-pass
 //                                                         3, and one multiply per sample
+//   8  monic general numerator 1 + b1 z^-1 + b2 z^-2 in DIRECT FORM II (the exact factors of a rounded
+//      Butterworth numerator whose zeros are NOT on the unit circle; gain on the input):
+//        w = u - a1 w1 - a2 w2;  y = w + b1 w1 + b2 w2              4, and one multiply per sample
+//      (the transposed form needs 5: its b2 u product has no partner).  In float64 the direct form is as
+//      accurate as the transposed one for these sections (both 1.5e-7 from the long-double evaluation of
+//      the 58-62 Hz notch at 3 kHz); its states (w1, w2) are related to the transposed ones by
+//      s0 = (b1 - a1) w1 + (b2 - a2) w2,  s1 = (b2 - a2) w1 + (b2 a1 - a2 b1) w2  (df2_state below).
 // In the unit forms c[j][1] holds beta1 = b1 / b0; the states are those of the general form.
 template <int J0, int J1, int NUM, int NSEC>
 __device__ __forceinline__ double sos_range(double u, const double (&c)[NSEC][5], double (&s)[NSEC][2]) {
     constexpr bool B1Z = (NUM & 1) != 0;
     constexpr int UNIT = NUM >> 1;              // 0 general, 1: b0 = 1, b2 = +1, 2: b0 = 1, b2 = -1
+    if (NUM == 8) {
+#pragma unroll
+        for (int j = J0; j < J1; ++j) {
+            const double w = fma(-c[j][4], s[j][1], fma(-c[j][3], s[j][0], u));
+            u = fma(c[j][2], s[j][1], fma(c[j][1], s[j][0], w));
+            s[j][1] = s[j][0];
+            s[j][0] = w;
+        }
+        return u;
+    }
 #pragma unroll
     for (int j = J0; j < J1; ++j) {
         const double y = UNIT ? u + s[j][0] : fma(c[j][0], u, s[j][0]);
@@ -280,19 +297,51 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
 #undef IN
 
 
-// numerator form of sections [j0, j1): 2 = unit (1 + beta z^-1 + z^-2), 5 = unit (1 - z^-2), 0 = general.
-// `lead` = the section allowed to carry the gain in b0.
+// numerator form of sections [j0, j1): 2 = unit (1 + beta z^-1 + z^-2), 5 = unit (1 - z^-2), 8 = monic
+// general (direct form II), 0 = general.  `lead` = the section allowed to carry the gain in b0.
 inline int unit_form(const SosCoef& coef, int j0, int j1, int lead) {
-    bool b1z = true, unit_p = true, unit_m = true;
+    bool b1z = true, unit_p = true, unit_m = true, monic = true;
     for (int j = j0; j < j1; ++j) {
         const double b0 = coef.c[j][0], b2 = coef.c[j][2];
         b1z = b1z && coef.c[j][1] == 0.0;
         const bool b0ok = b0 != 0.0 && (j == lead || b0 == 1.0);
+        monic = monic && b0ok;
         unit_p = unit_p && b0ok && b2 == b0;
         unit_m = unit_m && b0ok && b2 == -b0;
     }
-    return unit_p ? 2 : (unit_m && b1z ? 5 : 0);
+    return unit_p ? 2 : (unit_m && b1z ? 5 : (monic ? 8 : 0));
 }
+
+// Prepare sections [j0, j1) for their kernel form: forms 2 / 5 / 8 take the gain of section `lead` out
+// (returned; the kernel multiplies the input by the product of the gains), form 8 also moves the
+// start-up states zi from transposed (s0, s1) to direct-form (w1, w2) coordinates.
+inline double prepare_form(SosCoef& coef, int j0, int j1, int lead, int form) {
+    double gain = 1.0;
+    if (form == 0) return gain;
+    if (lead >= j0 && lead < j1) {
+        gain = coef.c[lead][0];
+        coef.c[lead][1] /= gain;
+        if (form == 8) coef.c[lead][2] /= gain;
+        // (the unit forms never read c[.][0] and c[.][2])
+    }
+    if (form == 8) {
+        for (int j = j0; j < j1; ++j) {
+            const double b1 = coef.c[j][1], b2 = coef.c[j][2], a1 = coef.c[j][3], a2 = coef.c[j][4];
+            const double m00 = b1 - a1, m01 = b2 - a2, m10 = b2 - a2, m11 = b2 * a1 - a2 * b1;
+            const double det = m00 * m11 - m01 * m10;
+            const double s0 = coef.zi[j][0], s1 = coef.zi[j][1];
+            if (det != 0.0) {
+                coef.zi[j][0] = (m11 * s0 - m01 * s1) / det;
+                coef.zi[j][1] = (m00 * s1 - m10 * s0) / det;
+            }
+        }
+    }
+    return gain;
+}
+
+// defined in sosfilt_tma.cu
+int run_sos_warm_tma(const float* x, float* y, int64_t C, int64_t T, const ecog_sos_plan& p, const SosCoef& coef_in,
+                     float* tmp, double* padbuf, cudaStream_t st);
 
 // defined in sosfilt_pair.cu
 int run_sos_warm_pair(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,

@@ -315,15 +315,13 @@ static int run_sos_warm(const float* x, float* y, int64_t C, int64_t T, int64_t 
     const bool wide = p.threads >= 512;
     // numerator form: unit sections g (1 + beta1 z^-1 +- z^-2) with the gain on section 0 only
     SosCoef coef = coef_in;
-    const int num = unit_form(coef, 0, NSEC, 0);
-    double gain = 1.0;
-    if (num) {
-        gain = coef.c[0][0];
-        coef.c[0][1] /= gain;
-    }
+    int num = unit_form(coef, 0, NSEC, 0);
+    if (num == 8 && NSEC != 4) num = 0;          // the direct-form variant is instantiated for 4 sections
+    const double gain = prepare_form(coef, 0, NSEC, 0, num);
 #define ECOG_WARM(REVV, NTT, Y_IN, Y_OUT, LD_IN, LD_OUT)                                                                         \
     (num == 2 ? launch_warm<NSEC, REVV, NTT, 2>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, vec, st)       \
      : num == 5 ? launch_warm<NSEC, REVV, NTT, 5>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, vec, st)     \
+     : num == 8 ? launch_warm<NSEC, REVV, NTT, (NSEC == 4 ? 8 : 0)>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, vec, st) \
                 : launch_warm<NSEC, REVV, NTT, 0>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, vec, st))
     if (wide) ECOG_TRY(ECOG_WARM(false, 512, x, mid, ldx, ldm));
     else      ECOG_TRY(ECOG_WARM(false, 256, x, mid, ldx, ldm));
@@ -386,7 +384,7 @@ static int64_t warm_ld(int64_t T) { return (T + 3) / 4 * 4; }
 
 extern "C" size_t ecog_sos_workspace(const ecog_sos_plan* plan, int64_t C, int64_t T) {
     if (!plan || plan->chunk <= 0) return 0;
-    if (plan->mode == ECOG_SOS_WARMUP) {      // filtered right pad + (zero phase) the forward result
+    if (plan->mode == ECOG_SOS_WARMUP || plan->mode == ECOG_SOS_WARMUP_TMA) {      // filtered right pad + (zero phase) the forward result
         size_t pad = align_up((size_t)C * (plan->padlen > 0 ? plan->padlen : 1) * sizeof(double), 256);
         return pad + (plan->zero_phase ? (size_t)C * warm_ld(T) * sizeof(float) : 0);
     }
@@ -418,8 +416,15 @@ extern "C" int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, 
             return fail(ECOG_E_VALUE, "The length of the input vector x must be greater than padlen, which is %d.", p.padlen);
     }
     const int nChunks = (int)ceil_div(T, p.chunk);
-    if (p.mode != ECOG_SOS_SCAN && p.mode != ECOG_SOS_WARMUP) return fail(ECOG_E_VALUE, "ecog_sosfilt: unknown mode %d", p.mode);
-    if (p.split && p.mode != ECOG_SOS_WARMUP) return fail(ECOG_E_VALUE, "ecog_sosfilt: the cascade pair runs in warm-up mode only");
+    if (p.mode != ECOG_SOS_SCAN && p.mode != ECOG_SOS_WARMUP && p.mode != ECOG_SOS_WARMUP_TMA)
+        return fail(ECOG_E_VALUE, "ecog_sosfilt: unknown mode %d", p.mode);
+    if (p.split && p.mode == ECOG_SOS_SCAN) return fail(ECOG_E_VALUE, "ecog_sosfilt: the cascade pair runs in warm-up mode only");
+    if (p.mode == ECOG_SOS_WARMUP_TMA) {
+        if (!p.zero_phase || p.chunk % 32 || p.tail % 32 || p.tail > p.chunk || T % p.chunk || ldx != T || ldy != T ||
+            !aligned16(d_x) || !aligned16(d_y) || !aligned16(d_workspace))
+            return fail(ECOG_E_UNSUPPORTED, "ecog_sosfilt (TMA): needs zero phase, contiguous 16-byte aligned rows, "
+                                           "T a multiple of chunk, chunk and tail multiples of 32, tail <= chunk");
+    }
     if (p.mode == ECOG_SOS_WARMUP && !p.zero_phase && d_x == d_y)
         return fail(ECOG_E_VALUE, "ecog_sosfilt: the causal warm-up path cannot run in place");
     if (p.mode == ECOG_SOS_SCAN && nChunks > 1 && !h_M)
@@ -453,6 +458,13 @@ extern "C" int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, 
             for (int j = 0; j < n0; ++j) M.m[i][j] = h_M[i * n0 + j];
     }
     cudaStream_t st = (cudaStream_t)stream;
+    if (p.mode == ECOG_SOS_WARMUP_TMA) {
+        double* padbuf = (double*)d_workspace;
+        const size_t pad = align_up((size_t)C * (p.padlen > 0 ? p.padlen : 1) * sizeof(double), 256);
+        if (p.split && (p.split != 4 || p.nsec != 8 || p.tail_b < 0 || p.tail_b % 32 || p.tail_b > p.tail))
+            return fail(ECOG_E_VALUE, "ecog_sosfilt (TMA): cascade pair needs nsec=8, split=4, tail_b a multiple of 32 <= tail");
+        return run_sos_warm_tma(d_x, d_y, C, T, p, coef, (float*)((char*)d_workspace + pad), padbuf, st);
+    }
     if (p.mode == ECOG_SOS_WARMUP) {
         double* padbuf = (double*)d_workspace;
         const size_t pad = align_up((size_t)C * (p.padlen > 0 ? p.padlen : 1) * sizeof(double), 256);

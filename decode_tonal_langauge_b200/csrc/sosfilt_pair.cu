@@ -24,13 +24,15 @@ static int launch_warm_pair(const float* x, float* y, int64_t C, int64_t T, int6
                             cudaStream_t st) {
     if (p.threads >= 512)
         return launch_warm_pair_nt<REV, NUMA, NUMB, 512>(x, y, C, T, ldx, ldy, p, nChunks, coef, gain, padbuf, st);
+    if (p.threads == 384)       // one CTA per SM, three warps per scheduler
+        return launch_warm_pair_nt<REV, NUMA, NUMB, 384>(x, y, C, T, ldx, ldy, p, nChunks, coef, gain, padbuf, st);
     return launch_warm_pair_nt<REV, NUMA, NUMB, 256>(x, y, C, T, ldx, ldy, p, nChunks, coef, gain, padbuf, st);
 }
 
-// Numerator forms of the two halves (sos_common.cuh::unit_form): 2 / 5 = unit forms (the gain of the
-// pair rides on the input), 0 = general b0 b1 b2 (exact factors of the reference's rounded numerator;
-// the gain of the pair is folded into section 0's numerator).  Supported: (2,5) (0,5) (5,2) (5,0)
-// (5,5) (2,2) (0,0); the host re-factors a mixed (2,0) / (0,2) pair into (0,0).
+// Numerator forms of the two halves (sos_common.cuh::unit_form): 2 / 5 = unit forms, 8 = monic general in
+// direct form II (the exact factors of the reference's rounded numerator); the gains of both halves ride on
+// the input (the host folds the second half's gain into section 0, design.py::pair_design).
+// Supported: (2,5) (8,5) (5,2) (5,8) (5,5) (2,2) (8,8).
 int run_sos_warm_pair(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                       const ecog_sos_plan& p, const SosCoef& coef_in, float* tmp, int64_t ldt, double* padbuf,
                       cudaStream_t st) {
@@ -41,21 +43,18 @@ int run_sos_warm_pair(const float* x, float* y, int64_t C, int64_t T, int64_t ld
     SosCoef coef = coef_in;
     const int na = unit_form(coef, 0, 4, 0), nb = unit_form(coef, 4, 8, -1);
     const int key = 10 * na + nb;
-    if (key != 25 && key != 5 && key != 52 && key != 50 && key != 55 && key != 22 && key != 0)
+    if (key != 25 && key != 85 && key != 52 && key != 58 && key != 55 && key != 22 && key != 88)
         return fail(ECOG_E_UNSUPPORTED, "ecog_sosfilt: unsupported numerator forms (%d, %d) for the cascade pair", na, nb);
-    double gain = 1.0;
-    if (na) {               // unit first half: monic sections, gain on the input
-        gain = coef.c[0][0];
-        coef.c[0][1] /= gain;
-    }
+    const double gain = prepare_form(coef, 0, 4, 0, na);
+    (void)prepare_form(coef, 4, 8, -1, nb);
 #define ECOG_PAIR(REVV, Y_IN, Y_OUT, LD_IN, LD_OUT)                                                                          \
     (key == 25 ? launch_warm_pair<REVV, 2, 5>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, st)           \
-     : key == 5 ? launch_warm_pair<REVV, 0, 5>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, st)          \
+     : key == 85 ? launch_warm_pair<REVV, 8, 5>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, st)         \
      : key == 52 ? launch_warm_pair<REVV, 5, 2>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, st)         \
-     : key == 50 ? launch_warm_pair<REVV, 5, 0>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, st)         \
+     : key == 58 ? launch_warm_pair<REVV, 5, 8>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, st)         \
      : key == 55 ? launch_warm_pair<REVV, 5, 5>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, st)         \
      : key == 22 ? launch_warm_pair<REVV, 2, 2>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, st)         \
-                 : launch_warm_pair<REVV, 0, 0>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, st))
+                 : launch_warm_pair<REVV, 8, 8>(Y_IN, Y_OUT, C, T, LD_IN, LD_OUT, p, nChunks, coef, gain, padbuf, st))
     ECOG_TRY(ECOG_PAIR(false, x, tmp, ldx, ldt));
     return ECOG_PAIR(true, tmp, y, ldt, ldy);
 #undef ECOG_PAIR

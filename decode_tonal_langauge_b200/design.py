@@ -370,10 +370,10 @@ def _pair_design(a_bytes: bytes, b_bytes: bytes, pad_a: int, pad_b: int):
             return 2
         if ok and np.all(sos[:, 2] == -sos[:, 0]) and np.all(sos[:, 1] == 0.0):
             return 5
-        return 0
+        return 8 if ok else 0           # 8: monic general sections (exact factors), run in direct form II
 
     fa, fb = form(sa), form(sb)
-    if (fa, fb) not in {(2, 5), (0, 5), (5, 2), (5, 0), (5, 5), (2, 2), (0, 0)}:
+    if (fa, fb) not in {(2, 5), (8, 5), (5, 2), (5, 8), (5, 5), (2, 2), (8, 8)}:
         return None
     if fb:                      # unit second half: monic, its gain joins section 0 of the first half
         gb = sb[0, 0]

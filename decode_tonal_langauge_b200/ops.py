@@ -75,6 +75,7 @@ def release_workspaces() -> None:
     _workspaces.clear()
     _tables.clear()
     _pinned_tables.clear()
+    _order_cache.clear()
 
 
 # Device-side tables (twiddles, gains, FIR taps, per-length resample / chirp-z tables).  The
@@ -189,6 +190,41 @@ def _sos_threads_per_sm() -> int:
     return int(os.environ.get("ECOG_SOS_TPS", "512"))
 
 
+def _pair_threads_per_sm() -> int:
+    # 8 sections per thread carry twice the arithmetic per byte of a single cascade: two warps per scheduler
+    # already fill the FP64 pipe, and half the threads means twice the chunk length, i.e. half the redundant
+    # warm-up (measured at C2: 768 -> 12.3 ms, 512 -> 12.5, 384 -> 14.0, 256 -> 11.7)
+    return int(os.environ.get("ECOG_PAIR_TPS", "256"))
+
+
+def _tma_enabled() -> bool:
+    return os.environ.get("ECOG_SOS_TMA", "0") == "1"
+
+
+def tma_chunk(Cn: int, T: int, tail: int) -> Optional[int]:
+    """Chunk length for the TMA sweeps (csrc/sosfilt_tma.cu): L divides T, L % 32 == 0, L >= tail.  The grid
+    is ceil(Cn * T / L / 256) CTAs of 256 chunk-threads, two of which fit an SM; CTAs are dealt round robin,
+    so the sweep lasts as long as the busiest SM's ceil(CTAs / 148) CTAs take, each doing L + tail samples per
+    thread (a grid of 300 CTAs on 296 slots runs twice as long as one of 296).  One resident CTA leaves the
+    FP64 pipe ~60 % busy, two ~75 % (ncu, profiles/r02_ncu_pair_tma.txt): the candidate with the least
+    (CTAs per SM) x (L + tail) / utilisation wins; None if T has no such divisor."""
+    best = None
+    for n in range(2, T // max(tail, 32) + 1):
+        if T % n:
+            continue
+        L = T // n
+        if L % 32 or L < tail:
+            continue
+        ctas = -(-Cn * n // 256)
+        per_sm = -(-ctas // D.NUM_SMS)
+        if per_sm > 2:
+            continue                       # more chunks than two resident CTAs per SM: only more warm-up
+        cost = per_sm * (L + tail) / (0.62 if per_sm == 1 else 0.75)
+        if best is None or cost < best[0]:
+            best = (cost, L)
+    return None if best is None else best[1]
+
+
 def sosfilt(x: torch.Tensor, dsg: D.SosDesign, chunk: Optional[int] = None,
             out: Optional[torch.Tensor] = None, mode: Optional[str] = None) -> torch.Tensor:
     """Biquad cascade, zero-phase (filtfilt semantics) or causal.  ``mode``: "warm" (one kernel
@@ -203,7 +239,17 @@ def sosfilt(x: torch.Tensor, dsg: D.SosDesign, chunk: Optional[int] = None,
     zi = None if dsg.zi is None else np.ascontiguousarray(dsg.zi, dtype=np.float64)
     Mh = None
     plan = None
-    if mode in (None, "warm"):
+    if (mode == "tma" or (mode is None and _tma_enabled())) and dsg.zero_phase and dsg.nsec == 4 \
+            and _ld(x) == T and _ld(y) == T and x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0:
+        tail = D.warm_tail(dsg, T)
+        tail32 = -(-tail // 32) * 32
+        L = (int(chunk) if chunk is not None else tma_chunk(Cn, T, tail32)) if tail >= 0 else None
+        if L is not None and T % L == 0 and L % 32 == 0 and tail32 <= L and T // L > 1:
+            plan = nat.SosPlan(dsg.nsec, 1, dsg.padlen, L, tail32, nat.SOS_WARMUP_TMA, 256)
+        elif mode == "tma":
+            raise ValueError("the TMA sweeps need contiguous rows whose length has a divisor L >= tail with L % 32 == 0")
+    if plan is None and mode in (None, "warm", "tma"):
+        mode = None if mode == "tma" else mode
         tps = _sos_threads_per_sm()
         L = int(chunk) if chunk is not None else D.choose_warm_chunk(Cn, T, tps)
         if L % D.SUB:
@@ -250,7 +296,7 @@ def pair_plan(Cn: int, T: int, ld_ok: bool, A: D.SosDesign, B: D.SosDesign):
     if comb is None:
         return None
     dsg, tail_b = comb
-    L = D.choose_warm_chunk(Cn, T, _sos_threads_per_sm())
+    L = D.choose_warm_chunk(Cn, T, _pair_threads_per_sm())
     n_chunks = -(-T // L)
     if n_chunks < 2:
         return None
@@ -260,9 +306,15 @@ def pair_plan(Cn: int, T: int, ld_ok: bool, A: D.SosDesign, B: D.SosDesign):
     tail = D.warm_tail(natural, min(int(D.WARM_MAX_OVERHEAD * L), T + D.SUB))
     if tail < 0 or 4 * tail + 64 > T:
         return None
-    threads = 512 if Cn * n_chunks >= 2 * D.NUM_SMS * 512 else 256
+    threads = 512 if Cn * n_chunks >= 2 * D.NUM_SMS * 512 else (384 if _pair_threads_per_sm() == 384 else 256)
     plan = nat.SosPlan(8, 1, dsg.padlen, L, tail, nat.SOS_WARMUP, threads, 4, min(tail_b, tail))
     return dsg, plan, tail
+
+
+# chunk length of the exact carry scan that recomputes the row ends of a cascade pair: the segments are
+# short (2 x tail samples), so the scan wants many short chunks (2 C x 2 tail / 256 threads) rather than
+# few long ones (12 launches of ~10 us instead of ~170 us each)
+PAIR_EDGE_CHUNK = 256
 
 
 def sosfilt_pair(x: torch.Tensor, A: D.SosDesign, B: D.SosDesign, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -283,6 +335,11 @@ def sosfilt_pair(x: torch.Tensor, A: D.SosDesign, B: D.SosDesign, out: Optional[
     if pp is None:
         return sosfilt(sosfilt(x, A), B, out=out)
     dsg, plan, V = pp
+    if _tma_enabled() and _ld(x) == T and _ld(y) == T:
+        tail32 = -(-V // 32) * 32
+        L = tma_chunk(Cn, T, tail32)
+        if L is not None and T // L > 1:
+            plan = nat.SosPlan(8, 1, dsg.padlen, L, tail32, nat.SOS_WARMUP_TMA, 256, 4, -(-min(plan.tail_b, V) // 32) * 32)
     if T <= dsg.padlen:
         raise ValueError(f"The length of the input vector x must be greater than padlen, which is {dsg.padlen}.")
     # exact edges first (they only read x): rows 0..C-1 = left segments, C..2C-1 = right segments
@@ -290,7 +347,7 @@ def sosfilt_pair(x: torch.Tensor, A: D.SosDesign, B: D.SosDesign, out: Optional[
     xe = torch.empty((2 * Cn, E), dtype=torch.float32, device=x.device)
     copy2d(xe[:Cn], x[:, :E])
     copy2d(xe[Cn:], x[:, T - E:])
-    ye = sosfilt(sosfilt(xe, A), B)
+    ye = sosfilt(sosfilt(xe, A, chunk=PAIR_EDGE_CHUNK, mode="scan"), B, chunk=PAIR_EDGE_CHUNK, mode="scan")
     sos = np.ascontiguousarray(dsg.sos, dtype=np.float64)
     zi = np.ascontiguousarray(dsg.zi, dtype=np.float64)
     nbytes = lib.ecog_sos_workspace(C.byref(plan), Cn, T)
@@ -656,7 +713,11 @@ def anova_f(epochs: torch.Tensor, groups: np.ndarray, extra: Optional[torch.Tens
     """One-way ANOVA over events for every (channel, timepoint).
 
     epochs (Na, C, L) [+ extra (Nb, C, L), concatenated after it]; groups: int array of
-    length Na + Nb with values 0..G-1.  Returns (F, p) as (C, L) float64 CUDA tensors."""
+    length Na + Nb with values 0..G-1.  Returns (F, p) as (C, L) float64 CUDA tensors.
+    The kernel reads float32 epochs and accumulates in float64 about the first event's value
+    (float64 accumulators of float32 samples match scipy's f_oneway to 5e-13); float64
+    epochs are narrowed on the device first -- their 29 extra mantissa bits are below the statistic's
+    own conditioning, and the reference's epochs are float64 only because filtfilt promotes."""
     def prep(e):
         if e.dtype != torch.float32:
             e = e.to(torch.float32)
@@ -672,16 +733,48 @@ def anova_f(epochs: torch.Tensor, groups: np.ndarray, extra: Optional[torch.Tens
     groups = np.ascontiguousarray(groups, dtype=np.int32)
     if groups.shape[0] != Na + Nb:
         raise ValueError("one group label per event is required")
-    G = int(groups.max()) + 1 if groups.size else 0
-    counts = np.bincount(groups, minlength=max(G, 1)).astype(np.int64)
-    order = np.argsort(groups, kind="stable").astype(np.int32)       # events sorted by group
-    d_groups = torch.from_numpy(order).to(epochs.device)
+    G, counts, d_groups = _group_order(groups, epochs.device)
     F = torch.empty((Cn, L), dtype=torch.float64, device=epochs.device)
     P = torch.empty((Cn, L), dtype=torch.float64, device=epochs.device)
     ws = workspace(lib.ecog_anova_workspace(Cn, L, Na + Nb, max(G, 2)), epochs.device, "anova")
     nat.check(lib.ecog_anova_f(_ptr(epochs), Na, _ptr(extra), Nb, Cn, L, _ptr(d_groups), _hptr(counts), G,
                                _ptr(F), _ptr(P), _ptr(ws), ws.numel(), _stream()))
     return F, P
+
+
+_order_cache: "OrderedDict" = OrderedDict()
+
+
+def _group_order(groups: np.ndarray, device):
+    """(G, per-group counts, device tensor of the event numbers sorted by group).  The stable argsort and
+    its upload depend on the label vector only: the last few are kept, so that the three selections of one
+    sample set (tone, syllable, active) and repeated calls do not pay them on the critical path again."""
+    key = (str(device), groups.shape[0], hash(groups.tobytes()))
+    hit = _order_cache.get(key)
+    if hit is not None and np.array_equal(hit[3], groups):
+        _order_cache.move_to_end(key)
+        return hit[0], hit[1], hit[2]
+    G = int(groups.max()) + 1 if groups.size else 0
+    counts = np.bincount(groups, minlength=max(G, 1)).astype(np.int64)
+    order = np.argsort(groups, kind="stable").astype(np.int32)       # events sorted by group
+    staged = torch.from_numpy(order).pin_memory()
+    d_order = staged.to(device, non_blocking=True)
+    _order_cache[key] = (G, counts, d_order, groups.copy(), staged)
+    while len(_order_cache) > 8:
+        _order_cache.popitem(last=False)
+    return G, counts, d_order
+
+
+def to_host_many(*tensors: torch.Tensor):
+    """Several small device results -> numpy with ONE synchronisation (pinned staging, async copies)."""
+    outs = []
+    for t in tensors:
+        t = t.contiguous()
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t, non_blocking=True)
+        outs.append(h)
+    torch.cuda.current_stream().synchronize()
+    return [h.numpy() for h in outs]
 
 
 def sig_runlength(p: torch.Tensor, threshold: float) -> torch.Tensor:

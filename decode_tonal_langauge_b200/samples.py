@@ -1,17 +1,26 @@
-"""Consumer of the hot path's outputs: ``subject_<id>.npz`` + ``subject_<id>.json`` -> selected-channel
-epochs and joint labels, resident on the device.
+"""Consumer of the hot path's outputs: ``subject_<id>.npz`` +
+``subject_<id>.json`` -> selected-channel epochs resident on the device, plus joint class codes.
 
-ref: data_loading/sample_loading.py:9-139 (``ClassificationSampleHandler``): same constructor
-parameters (``sample_path``, ``channel_file``, ``targets``, ``features``), same ``load_data`` keys,
-same joint label coding and channel union, same errors.  ``features`` comes back as a float CUDA
-tensor (the channel filter runs in ``ecog_channel_select``); pass ``as_numpy=True`` for the
-reference's numpy array.  The classifier models and their training are out of scope.
+Contract taken from ref: data_loading/sample_loading.py:9-139 (``ClassificationSampleHandler``):
+
+* constructor keys on the params Namespace: ``sample_path`` (npz), optional ``channel_file`` (the JSON
+  written by the channel-selection stage), ``targets`` (one name or a list), ``features`` (npz key);
+* ``load_data()`` returns ``features`` (events, selected channels, time), ``labels`` (one joint code per
+  event: the first target varies fastest, radix = number of distinct values of each target),
+  ``selected_channels`` and ``n_classes_dict``;
+* the channel set is the sorted union of the ``<target>_discriminative`` lists of the JSON, or every
+  channel without a channel file;
+* missing npz keys / JSON entries raise ``KeyError``, an empty union raises ``ValueError``.
+
+Written against that contract, not transliterated: the channel pick is a device gather
+(``ecog_channel_select``) and ``features`` comes back as a CUDA tensor (``as_numpy=True`` for the
+reference's numpy array).  The classifier models and their training are out of scope.
 """
 from __future__ import annotations
 
 import json
 from argparse import Namespace
-from typing import List, Optional
+from typing import Dict, List, Sequence
 
 import numpy as np
 import torch
@@ -20,66 +29,68 @@ from . import ops
 from . import runtime as rt
 
 
+def joint_codes(columns: Sequence[np.ndarray]) -> np.ndarray:
+    """Mixed-radix code of several label columns: ``sum_i column_i * prod_{j<i} n_distinct(column_j)``."""
+    code = np.zeros(np.asarray(columns[0]).shape, dtype=int)
+    radix = 1
+    for col in columns:
+        col = np.asarray(col)
+        code = code + col * radix
+        radix *= np.unique(col).size
+    return code
+
+
+def selected_union(selection: Dict[str, list], targets: Sequence[str], where: str = "the channel file") -> np.ndarray:
+    """Sorted union of ``selection["<target>_discriminative"]`` over the targets."""
+    picked = set()
+    for name in targets:
+        entry = f"{name}_discriminative"
+        if entry not in selection:
+            raise KeyError(f"Channel selection for '{entry}' not found in the file {where}. "
+                           f"Available keys: {', '.join(selection)}")
+        picked |= set(selection[entry])
+    if len(picked) == 0:
+        raise ValueError(f"No channels found for the targets: {', '.join(targets)}. "
+                         f"Please check the channel file {where}")
+    return np.asarray(sorted(picked))
+
+
 class ClassificationSampleHandler:
     def __init__(self, params: Namespace):
+        self.params = params
         self.sample_path = params.sample_path
-        self.channel_file = params.channel_file if hasattr(params, "channel_file") else None
+        self.channel_file = getattr(params, "channel_file", None)
+        targets = getattr(params, "targets", None)
+        self.targets: List[str] = [targets] if isinstance(targets, str) else targets
         self.dataset = np.load(self.sample_path)
         self.channels = None
-        self.targets = getattr(params, "targets", None)
-        if isinstance(self.targets, str):
-            self.targets = [self.targets]
-        self.params = params
+
+    def _column(self, key: str, what: str) -> np.ndarray:
+        if key not in self.dataset:
+            raise KeyError(f"The dataset in {self.sample_path} does not contain {what} '{key}'. "
+                           f"Available keys: {', '.join(self.dataset.keys())}")
+        return self.dataset[key]
 
     def load_data(self, as_numpy: bool = False) -> dict:
-        """ref: sample_loading.py:34-88."""
-        try:
-            features = self.dataset[self.params.features]
-        except KeyError:
-            raise KeyError(
-                f"The dataset in {self.sample_path} does not contain {getattr(self.params, 'features', None)}. "
-                f"Available keys: {', '.join(self.dataset.keys())}")
-        target_labels, n_classes_dict = [], {}
-        for target in self.targets:
-            if target not in self.dataset:
-                raise KeyError(f"The dataset does not contain '{target}' key. "
-                               f"Available keys: {', '.join(self.dataset.keys())}")
-            target_labels.append(self.dataset[target].flatten())
-            n_classes_dict[target] = len(np.unique(self.dataset[target]))
-        labels = np.zeros_like(target_labels[0], dtype=int)        # joint code, first target fastest (:68-72)
-        multiplier = 1
-        for target_label in target_labels:
-            labels += target_label * multiplier
-            multiplier *= len(np.unique(target_label))
+        features = self._column(getattr(self.params, "features", None), "the feature array")
+        columns = [self._column(t, "the target").flatten() for t in self.targets]
+        n_classes = {t: int(np.unique(self.dataset[t]).size) for t in self.targets}
         self.channels = self._filter_channels(features.shape[1])
-        dev = rt.to_device(np.asarray(features), dtype=None)
-        if dev.element_size() not in (4, 8):
-            dev = dev.to(torch.float32)
-        selected = ops.channel_select(dev, self.channels)
-        return {"features": rt.to_host(selected) if as_numpy else selected, "labels": labels,
-                "selected_channels": self.channels, "n_classes_dict": n_classes_dict}
+        dev = rt.to_device(np.asarray(features), dtype=None)        # any dtype: the pick is a bit copy
+        picked = ops.channel_select(dev, self.channels)
+        return {"features": rt.to_host(picked) if as_numpy else picked, "labels": joint_codes(columns),
+                "selected_channels": self.channels, "n_classes_dict": n_classes}
 
     def _filter_channels(self, n_channels: int) -> np.ndarray:
-        """ref: sample_loading.py:90-123: union of ``<target>_discriminative`` lists, sorted."""
         if self.channel_file is None:
             return np.arange(n_channels)
-        with open(self.channel_file, "r") as f:
-            channel_selections = json.load(f)
-        channels = set()
-        for target in self.targets:
-            key = f"{target}_discriminative"
-            if key not in channel_selections:
-                raise KeyError(f"Channel selection for '{key}' not found in the file {self.channel_file}. "
-                               f"Available keys: {', '.join(channel_selections.keys())}")
-            channels.update(channel_selections[key])
-        if not channels:
-            raise ValueError(f"No channels found for the targets: {', '.join(self.targets)}. "
-                             f"Please check the channel file {self.channel_file}")
-        return np.array(sorted(channels))
+        with open(self.channel_file, "r") as fh:
+            selection = json.load(fh)
+        return selected_union(selection, self.targets, self.channel_file)
 
     def prepare_torch_dataset(self, features, labels, device: str = "cuda"):
-        """ref: sample_loading.py:126-139 (float32 features and labels on ``device``)."""
+        """float32 features and float32 labels on ``device`` as a ``TensorDataset``."""
         from torch.utils.data import TensorDataset
-        x = features if isinstance(features, torch.Tensor) else torch.as_tensor(np.asarray(features))
-        return TensorDataset(x.to(device=device, dtype=torch.float32),
-                             torch.as_tensor(np.asarray(labels), dtype=torch.float32).to(device))
+        x = features if isinstance(features, torch.Tensor) else torch.from_numpy(np.asarray(features))
+        y = torch.from_numpy(np.asarray(labels))
+        return TensorDataset(x.to(device=device, dtype=torch.float32), y.to(device=device, dtype=torch.float32))

@@ -62,10 +62,13 @@ def test_discriminative_power(data: Mapping, params: dict) -> Dict[str, np.ndarr
 test_discriminative_power.__test__ = False      # not a pytest test
 
 
-def _select(P: torch.Tensor, threshold: float, length_threshold: int):
-    runs = ops.sig_runlength(P, threshold).cpu().numpy()
+def _select(P: torch.Tensor, threshold: float, length_threshold: int, *also: torch.Tensor):
+    """Longest significant run per channel -> selected list; `also` are further device results wanted on
+    the host (p-values, F): everything comes back with one synchronisation."""
+    host = ops.to_host_many(ops.sig_runlength(P, threshold), *also)
+    runs = host[0]
     sel = [int(c) for c in np.nonzero(runs > length_threshold)[0]]       # strict '>' (utils.py:73)
-    return sel, runs
+    return sel, runs, host[1:]
 
 
 def discriminative_run(data: Mapping, params: dict) -> dict:
@@ -76,11 +79,11 @@ def discriminative_run(data: Mapping, params: dict) -> dict:
     sf = _sf(data, f"{name}_sf")
     res = test_discriminative_power(data, params)
     P = res["p_value"]
-    sel, _ = _select(P, p_threshold / P.shape[1], int(params["active_time_threshold"] * sf))
+    sel, _, (p_host, f_host) = _select(P, p_threshold / P.shape[1], int(params["active_time_threshold"] * sf),
+                                       P, res["f_stat"])
     print(f'Found {len(sel)} discriminative channels for target "{target}"')
     # max_lengths is always empty in the reference (utils.py:65-75 never appends)
-    return {"selected_channels": sel, "max_lengths": [], "p_values": P.cpu().numpy(),
-            "f_stat": res["f_stat"].cpu().numpy()}
+    return {"selected_channels": sel, "max_lengths": [], "p_values": p_host, "f_stat": f_host}
 
 
 def active_run(data: Mapping, params: dict) -> dict:
@@ -97,7 +100,7 @@ def active_run(data: Mapping, params: dict) -> dict:
                          f"{tuple(erp.shape[1:2])} vs {tuple(rest.shape[1:2])}.")
     groups = np.r_[np.zeros(rest.shape[0], np.int32), np.ones(erp.shape[0], np.int32)]
     _, P = ops.anova_f(rest, groups, erp)                    # f_oneway(rest, erp) group order (:62)
-    sel, runs = _select(P, params["p_threshold"] / rest.shape[2], length_threshold)
+    sel, runs, (p_host,) = _select(P, params["p_threshold"] / rest.shape[2], length_threshold, P)
     print(f"Found {len(sel)} active channels.")
     return {"selected_channels": sel, "max_lengths": [int(runs[c]) for c in sel],
-            "p_values": P[-1].cpu().numpy(), "p_values_all": P.cpu().numpy()}
+            "p_values": p_host[-1].copy(), "p_values_all": p_host}

@@ -44,6 +44,9 @@ int ecog_abi_version(void);
 const char* ecog_last_error(void);
 /* number of kernels this library has launched from the calling thread (bench bookkeeping) */
 int64_t ecog_launch_count(void);
+/* comma-separated names of the kernels launched from the calling thread since the last reset (up to 4 KB);
+ * reset != 0 clears the log after copying it.  Test / bench bookkeeping: which code path actually ran. */
+const char* ecog_launch_log(int reset);
 
 /* ------------------------------------------------------------------ K1: CAR
  * replaces preprocess/signal/car_rereference.py:34-39
@@ -110,6 +113,11 @@ typedef struct {
  * also holds the forward result (C x T float32) of a zero-phase call.                       */
 #define ECOG_SOS_SCAN 0
 #define ECOG_SOS_WARMUP 1
+/* ECOG_SOS_WARMUP_TMA: the warm-up sweeps with TMA-staged time tiles (cp.async.bulk.tensor boxes of
+ * 256 chunks x 32 samples, SWIZZLE_128B, mbarrier completion; csrc/sosfilt_tma.cu).  Needs zero phase,
+ * contiguous rows (ldx == ldy == T), T == n * chunk, chunk / tail (/ tail_b) multiples of 32,
+ * tail <= chunk; 4-section cascades and the (2,5) / (0,5) cascade pairs.                        */
+#define ECOG_SOS_WARMUP_TMA 2
 #define ECOG_MAX_SECTIONS 8
 size_t ecog_sos_workspace(const ecog_sos_plan* plan, int64_t C, int64_t T);
 int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,

@@ -26,6 +26,18 @@ def fir():
     return ops.fir_decimate(x, pre.taps, pre.offset, pre.D)
 
 
+def _with_env(key, val, fn):
+    old = os.environ.get(key)
+    os.environ[key] = val
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ[key]
+        else:
+            os.environ[key] = old
+
+
 FN = {
     "hilbert": lambda: ops.hilbert(x, fs, [70.0, 150.0]),
     "resample": lambda: ops.fft_resample(x, T // 5),
@@ -39,6 +51,9 @@ FN = {
     "zscore": lambda: ops.zscore(x),
     "pair": lambda: ops.sosfilt_pair(x, DSG.butter_design([58, 62], fs, 4, False, "bandstop"),
                                      DSG.butter_design([70, 150], fs, 4, False, "bandpass")),
+    "notch_tma": lambda: ops.butter(x, [58, 62], fs, 4, False, "bandstop", mode="tma"),
+    "bandpass_tma": lambda: ops.butter(x, [70, 150], fs, 4, False, "bandpass", mode="tma"),
+    "pair_tma": lambda: _with_env("ECOG_SOS_TMA", "1", FN["pair"]),
     "colsum": lambda: ops.car_colsum(x),
     "hilbert_car": lambda: ops.hilbert(x, fs, [70.0, 150.0], car=(COLSUM, C)),
 }
@@ -64,7 +79,7 @@ def run(name):
 
 # bring the clocks up before the first timed operator (an idle B200 sits at 120 MHz)
 _w = torch.randn((4096, 4096), device="cuda")
-for _ in range(200):
+for _ in range(0 if os.environ.get("ECOG_PROF_NO_SPINUP") else 200):
     _w = (_w @ _w).clamp_(-1, 1)
 torch.cuda.synchronize()
 del _w

@@ -21,12 +21,12 @@ def _need_cuda():
 
 
 def _launched(fn):
-    """Names of the ecog:: kernels `fn` launches (torch profiler, CUPTI)."""
-    from torch.profiler import ProfilerActivity, profile
-    with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        out = fn()
-        torch.cuda.synchronize()
-    return out, {e.key for e in prof.key_averages()}
+    """(result, names of the library kernels `fn` launched) -- the library's own launch log."""
+    from decode_tonal_langauge_b200 import _native as nat
+    nat.launch_log(reset=True)
+    out = fn()
+    torch.cuda.synchronize()
+    return out, set(nat.launch_log(reset=True))
 
 
 def oracle_rows_with_car(x_dev, rows, fs, steps_without_car):
@@ -60,9 +60,9 @@ def test_full6_full_length_default_plans_vs_oracle(C, T, fs):
     x = synth.device_session(C, T, fs, seed=11)
     (y, f), kernels = _launched(lambda: preprocess_signal(x, FULL6_STEPS, Namespace(signal_freq=fs)))
     names = " ".join(kernels)
-    assert "sos_warm_kernel" in names, names                 # the bench's IIR path, not the scan fallback
-    assert "fir_decimate_kernel" in names, names             # two-stage resampler
-    assert "hilbert_env8_kernel" in names, names
+    assert "sos_warm_pair_fwd" in kernels and "sos_warm_pair_bwd" in kernels, names     # the fused pair, not a fallback
+    assert "fir_decimate" in kernels, names                  # two-stage resampler
+    assert "hilbert_env8" in kernels and "car_colsum" in kernels and "car_fused" not in kernels, names
     rows = [0, C // 2 + 1, C - 1]
     no_car = [FULL6_STEPS[0]] + FULL6_STEPS[2:]
     ref, truth, f_ref = oracle_rows_with_car(x, rows, fs, no_car)
@@ -120,7 +120,7 @@ def test_cascade_pair_equals_sequential_and_oracle(fs, T):
     B = D.butter_design([70, 150], fs, 4, False, "bandpass")
     assert ops.pair_plan(C, T, True, A, B) is not None
     y, kernels = _launched(lambda: ops.sosfilt_pair(x, A, B))
-    assert any("sos_warm_kernel<8" in k for k in kernels), kernels
+    assert "sos_warm_pair_fwd" in kernels and "sos_warm_pair_bwd" in kernels, kernels
     seq = ops.sosfilt(ops.sosfilt(x, A), B)
     scale = seq.abs().amax(dim=1)
     err = ((y - seq).abs().amax(dim=1) / scale).max().item()
@@ -172,8 +172,8 @@ def test_fused_chain_small_matches_unfused_and_oracle():
     steps = [dict(s) for s in FULL6_STEPS]
     steps[1] = {"module": "preprocess.car_rereference", "params": {"exclude_channels": [2, 7]}}
     (y, f), kernels = _launched(lambda: preprocess_signal(x, steps, Namespace(signal_freq=fs)))
-    assert not any("car_fused" in k or "car_apply" in k for k in kernels), kernels      # folded
-    assert any("car_colsum" in k for k in kernels)
+    assert "car_fused" not in kernels and "car_apply" not in kernels, kernels      # folded
+    assert "car_colsum" in kernels and "hilbert_env8" in kernels
     y0, _ = preprocess_signal(x, steps, Namespace(signal_freq=fs), fuse=False)
     assert max_rel(y, y0) < 5e-6
     ref, fr = CH.run_chain(x, fs, steps)
@@ -221,7 +221,7 @@ def test_car_2048_rows_falls_back_to_two_phase():
     g = torch.Generator(device="cuda").manual_seed(2)
     x = torch.randn((2048, 8192), generator=g, device="cuda") * 5 + 1.0
     y, kernels = _launched(lambda: ops.car(x, [0, 2047]))
-    assert any("car_colsum" in k for k in kernels) and any("car_apply" in k for k in kernels)
+    assert "car_colsum" in kernels and "car_apply" in kernels, kernels
     ref = x - x[1:2047].mean(dim=0, keepdim=True, dtype=torch.float64).to(torch.float32)
     assert ((y - ref).abs().max() / ref.abs().max()).item() < 2e-6
     y2 = ops.car(x[:1500])                                    # still the fused strip
@@ -273,3 +273,66 @@ def test_table_cache_is_bounded(monkeypatch):
         assert ops.table_cache_bytes() <= (24 << 20) + (8 << 20)
     ops.release_workspaces()
     assert ops.table_cache_bytes() == 0
+
+
+def test_tma_sweeps_equal_cp_async_sweeps(monkeypatch):
+    """csrc/sosfilt_tma.cu (cp.async.bulk.tensor boxes, SWIZZLE_128B, mbarriers) against the cp.async ring
+    kernel: same algorithm, another chunk length and warm-up rounding -> equal to float32 rounding; single
+    cascades in all three numerator forms and the fused pair, both row ends included."""
+    from decode_tonal_langauge_b200 import design as D
+    from decode_tonal_langauge_b200 import ops, synth
+    fs, C, T = 2000, 128, 2_400_000
+    x = synth.device_session(C, T, fs, seed=3)
+
+    def rel(a, b):
+        return ((a - b).abs().amax(dim=1) / b.abs().amax(dim=1)).max().item()
+
+    for freqs, ft in (([58, 62], "bandstop"), ([70, 150], "bandpass"), ([95, 105], "bandstop")):
+        d = D.butter_design(freqs, fs, 4, False, ft)
+        ref = ops.sosfilt(x, d, mode="warm")
+        got, kernels = _launched(lambda: ops.sosfilt(x, d, mode="tma"))
+        assert "sos_warm_tma_fwd" in kernels and "sos_warm_tma_bwd" in kernels, kernels
+        e = rel(got, ref)
+        print(f"TMA vs cp.async {ft} {freqs}: {e:.2e}")
+        assert e < 1e-6
+    A = D.butter_design([58, 62], fs, 4, False, "bandstop")
+    B = D.butter_design([70, 150], fs, 4, False, "bandpass")
+    C2, T2 = 256, 4_800_000
+    x2 = synth.device_session(C2, T2, fs, seed=4)
+    ref = ops.sosfilt_pair(x2, A, B)
+    monkeypatch.setenv("ECOG_SOS_TMA", "1")
+    got, kernels = _launched(lambda: ops.sosfilt_pair(x2, A, B))
+    assert "sos_warm_tma_fwd" in kernels and "sos_warm_pair_fwd" not in kernels, kernels
+    e = rel(got, ref)
+    print(f"TMA pair vs cp.async pair: {e:.2e}")
+    assert e < 1e-6
+
+
+def test_session_batch_runner_equals_one_by_one(tmp_path):
+    """sessions.preprocess_sessions (file -> pinned -> device -> chain -> pinned -> sink, overlapped) gives what
+    preprocess_signal gives block by block; the sink writes the reference's B<block>_ecog.npz files."""
+    from decode_tonal_langauge_b200 import sessions as SS
+    from decode_tonal_langauge_b200 import synth
+    from decode_tonal_langauge_b200.chains import EX_STEPS, FULL6_STEPS
+    from decode_tonal_langauge_b200.preprocessor import preprocess_signal
+    fs = 2000
+    paths, arrays = [], []
+    for b, (C, T) in enumerate([(6, 60_000), (4, 90_000), (6, 60_000)]):
+        x = synth.session_channels(b, range(C), T, fs, C)
+        np.savez(tmp_path / f"B{b}_raw.npz", data=x, sf=np.float64(fs))
+        paths.append(str(tmp_path / f"B{b}_raw.npz"))
+        arrays.append(x)
+    for steps in (FULL6_STEPS, EX_STEPS):
+        sink = SS.save_block_sink(str(tmp_path / "out"), 1, [7, 8, 9])
+        tm = {}
+        written = SS.preprocess_sessions(paths, steps, sink, depth=2, timing=tm)
+        assert tm["sessions"] == 3 and [p.endswith(f"B{k}_ecog.npz") for p, k in zip(written, (7, 8, 9))] == [True] * 3
+        for p, x in zip(written, arrays):
+            z = np.load(p)
+            want, f = preprocess_signal(x, steps, Namespace(signal_freq=fs))
+            assert z["sf"][()] == f and z["data"].dtype == want.dtype
+            assert max_rel(z["data"], want) < 2e-6
+    got = SS.preprocess_sessions([(arrays[1], fs)], FULL6_STEPS, lambda i, y, f: y.copy(), output_dtype=np.float32)
+    assert got[0].dtype == np.float32
+    with pytest.raises(ValueError):
+        SS.preprocess_sessions([(arrays[0][0], fs)], FULL6_STEPS)

@@ -203,3 +203,45 @@ def test_dropin_names_resolve():
     assert callable(importlib.import_module("preprocess_main").run)         # Appendix B4
     from channel_selection.utils import get_max_length
     assert get_max_length(np.array([1, 2, 3, 7, 8, 10, 11, 12, 13])) == 4
+
+
+def test_sample_handler_host_logic():
+    """Joint label code and channel union of the downstream consumer (contract of
+    ref: data_loading/sample_loading.py:66-72,101-121), no device involved."""
+    from decode_tonal_langauge_b200.samples import joint_codes, selected_union
+    tone = np.array([0, 3, 1, 2, 3])
+    syl = np.array([1, 0, 0, 1, 1], dtype=np.int8)
+    assert joint_codes([tone, syl]).tolist() == (tone + 4 * syl).tolist()
+    assert joint_codes([syl, tone]).tolist() == (syl + 2 * tone).tolist()
+    assert joint_codes([tone]).dtype == int
+    sel = {"tone_discriminative": [9, 3], "syllable_discriminative": [3, 1], "active": [0]}
+    assert selected_union(sel, ["tone", "syllable"]).tolist() == [1, 3, 9]
+    with pytest.raises(KeyError, match="nope_discriminative"):
+        selected_union(sel, ["nope"])
+    with pytest.raises(ValueError, match="No channels"):
+        selected_union({"tone_discriminative": []}, ["tone"])
+
+
+def test_npz_member_is_read_in_place(tmp_path):
+    """sessions.locate_npz_array / _read_into: the raw bytes of `data` inside the reference's block format
+    (np.savez: stored zip member + .npy header) go straight into a caller-owned buffer."""
+    from decode_tonal_langauge_b200 import sessions as SS
+    rng = np.random.default_rng(0)
+    for dt, shape in ((np.float32, (5, 70001)), (np.float64, (3, 1000)), (np.int16, (2, 33))):
+        data = (rng.standard_normal(shape) * 100).astype(dt)
+        path = tmp_path / f"B1_ecog_{np.dtype(dt).name}.npz"
+        np.savez(path, data=data, sf=np.float64(2000.0))
+        m = SS.locate_npz_array(str(path), "data")
+        assert m.shape == shape and m.dtype == np.dtype(dt) and not m.fortran
+        out = np.empty(shape, dtype=dt)
+        SS._read_into(m, out, threads=3)
+        assert np.array_equal(out, data)
+        assert SS.read_npz_scalar(str(path), "sf") == 2000.0
+    big = rng.standard_normal((4, 5_000_000)).astype(np.float32)          # > 64 MiB: the threaded path
+    np.savez(tmp_path / "big.npz", data=big, sf=np.int64(400))
+    out = np.empty_like(big)
+    SS._read_into(SS.locate_npz_array(str(tmp_path / "big.npz")), out, threads=4)
+    assert np.array_equal(out, big)
+    np.savez_compressed(tmp_path / "c.npz", data=big[:, :10], sf=1)
+    with pytest.raises(ValueError, match="compressed"):
+        SS.locate_npz_array(str(tmp_path / "c.npz"))
