@@ -16,7 +16,7 @@ ECOG_E_VALUE = -1
 ECOG_E_CUDA = -2
 ECOG_E_WORKSPACE = -3
 ECOG_E_UNSUPPORTED = -4
-ABI_VERSION = 5
+ABI_VERSION = 6
 MAX_SECTIONS = 8
 SOS_SCAN = 0
 SOS_WARMUP = 1
@@ -40,8 +40,7 @@ class ResamplePlan(C.Structure):
 
 
 class ResampleTables(C.Structure):
-    _fields_ = [("perm_fa", C.c_void_p), ("perm_fb", C.c_void_p), ("perm_ia", C.c_void_p), ("perm_ib", C.c_void_p),
-                ("tw_fa", C.c_void_p), ("tw_fb", C.c_void_p), ("tw_ia", C.c_void_p), ("tw_ib", C.c_void_p),
+    _fields_ = [("tw_fa", C.c_void_p), ("tw_fb", C.c_void_p), ("tw_ia", C.c_void_p), ("tw_ib", C.c_void_p),
                 ("tw_big_f_hi", C.c_void_p), ("tw_big_f_lo", C.c_void_p),
                 ("tw_big_i_hi", C.c_void_p), ("tw_big_i_lo", C.c_void_p),
                 ("big_f_split", C.c_int32), ("big_i_split", C.c_int32),
@@ -50,7 +49,7 @@ class ResampleTables(C.Structure):
 
 
 class FftTables(C.Structure):
-    _fields_ = [("perm_a", C.c_void_p), ("perm_b", C.c_void_p), ("tw_a", C.c_void_p), ("tw_b", C.c_void_p),
+    _fields_ = [("tw_a", C.c_void_p), ("tw_b", C.c_void_p),
                 ("tw_big_hi", C.c_void_p), ("tw_big_lo", C.c_void_p), ("tw_q", C.c_void_p)]
 
 

@@ -40,7 +40,6 @@ struct PassParams {
     float2* out;
     long long in_ch_stride, out_ch_stride;   // float2 elements per channel
     int n, m;                                // matrix view: n rows (FFT length) x m columns
-    const int* perm;
     const float2* tw;
     const float2* tw_hi;
     const float2* tw_lo;
@@ -478,7 +477,7 @@ static int run_c2c(const float2* in, float2* out, int64_t C, int64_t ld_in, int6
     PassParams P;
     memset(&P, 0, sizeof(P));
     P.in = in; P.in_ch_stride = ld_in;
-    P.n = fa.n; P.m = fb.n; P.perm = tb->perm_a; P.tw = (const float2*)tb->tw_a;
+    P.n = fa.n; P.m = fb.n; P.tw = (const float2*)tb->tw_a;
     P.tw_hi = (const float2*)tb->tw_big_hi; P.tw_lo = (const float2*)tb->tw_big_lo;
     P.tw_q = (const double2*)tb->tw_q;
     P.conj_in = inverse ? 1 : 0; P.scale = 1.f; P.keep_lo = 1 << 30; P.keep_hi = 0;
@@ -492,7 +491,7 @@ static int run_c2c(const float2* in, float2* out, int64_t C, int64_t ld_in, int6
     ECOG_TRY(launch_pass(P, C, st, "fft_c2c_a"));
     memset(&P, 0, sizeof(P));
     P.in = tmp; P.in_ch_stride = N; P.out = out; P.out_ch_stride = ld_out;
-    P.n = fb.n; P.m = fa.n; P.perm = tb->perm_b; P.tw = (const float2*)tb->tw_b;
+    P.n = fb.n; P.m = fa.n; P.tw = (const float2*)tb->tw_b;
     P.conj_out = inverse ? 1 : 0; P.scale = scale; P.keep_lo = 1 << 30; P.keep_hi = 0;
     ECOG_TRY(fill_axis(fb, P.ax));
     return launch_pass(P, C, st, "fft_c2c_b");
@@ -543,7 +542,7 @@ extern "C" int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_
     memset(&P, 0, sizeof(P));
     P.in = reinterpret_cast<const float2*>(d_x); P.in_ch_stride = ldx / 2;
     P.out = plan->fb.n > 1 ? bufA : bufZ; P.out_ch_stride = N;
-    P.n = plan->fa.n; P.m = plan->fb.n; P.perm = tb->perm_fa; P.tw = (const float2*)tb->tw_fa;
+    P.n = plan->fa.n; P.m = plan->fb.n; P.tw = (const float2*)tb->tw_fa;
     P.tw_hi = (const float2*)tb->tw_big_f_hi; P.tw_lo = (const float2*)tb->tw_big_f_lo;
     P.tw_q = (const double2*)tb->tw_q_f;
     P.twiddle = plan->fb.n > 1; P.transposed = 1; P.scale = 1.f; P.keep_lo = 1 << 30; P.keep_hi = 0;
@@ -553,7 +552,7 @@ extern "C" int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_
         // ---- forward pass B: (fb.n x fa.n), natural-order store of the needed rows only
         memset(&P, 0, sizeof(P));
         P.in = bufA; P.in_ch_stride = N; P.out = bufZ; P.out_ch_stride = N;
-        P.n = plan->fb.n; P.m = plan->fa.n; P.perm = tb->perm_fb; P.tw = (const float2*)tb->tw_fb;
+        P.n = plan->fb.n; P.m = plan->fa.n; P.tw = (const float2*)tb->tw_fb;
         P.scale = 1.f;
         // bins k = p * fa.n + q needed: k <= kneed or k >= N - kneed
         P.keep_lo = (int)(kneed / plan->fa.n);
@@ -574,7 +573,7 @@ extern "C" int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_
     memset(&P, 0, sizeof(P));
     P.in = bufG; P.in_ch_stride = Nh;
     P.out = two ? bufI : reinterpret_cast<float2*>(d_y); P.out_ch_stride = two ? Nh : ldy / 2;
-    P.n = plan->ia.n; P.m = plan->ib.n; P.perm = tb->perm_ia; P.tw = (const float2*)tb->tw_ia;
+    P.n = plan->ia.n; P.m = plan->ib.n; P.tw = (const float2*)tb->tw_ia;
     P.tw_hi = (const float2*)tb->tw_big_i_hi; P.tw_lo = (const float2*)tb->tw_big_i_lo;
     P.tw_q = (const double2*)tb->tw_q_i;
     P.conj_in = 0; P.twiddle = two; P.transposed = 1; P.scale = 1.f; P.keep_lo = 1 << 30; P.keep_hi = 0;
@@ -587,7 +586,7 @@ extern "C" int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_
     ECOG_TRY(launch_pass(P, C, st, "fft_inv_a"));
     memset(&P, 0, sizeof(P));
     P.in = bufI; P.in_ch_stride = Nh; P.out = reinterpret_cast<float2*>(d_y); P.out_ch_stride = ldy / 2;
-    P.n = plan->ib.n; P.m = plan->ia.n; P.perm = tb->perm_ib; P.tw = (const float2*)tb->tw_ib;
+    P.n = plan->ib.n; P.m = plan->ia.n; P.tw = (const float2*)tb->tw_ib;
     P.conj_out = 1; P.scale = (float)(1.0 / (double)Nh); P.keep_lo = 1 << 30; P.keep_hi = 0;
     ECOG_TRY(fill_axis(plan->ib, P.ax));
     return launch_pass(P, C, st, "fft_inv_b");

@@ -72,6 +72,49 @@ __device__ __forceinline__ double sos_step(double u, const double (&c)[NSEC][5],
     return u;
 }
 
+// N consecutive samples through sections [0, NS) in WAVEFRONT order: on diagonal d section j handles sample
+// d - j, so the NS section steps of one diagonal are independent of each other (different sections'
+// states, different samples) and sit next to each other in program order.  Same operations as N calls of
+// sos_step, another schedule: a thread then has ~NS independent FP64 chains in flight instead of one, which
+// is what two warps per scheduler need to keep the FP64 pipe busy (ncu: the sample-by-sample order stalls
+// on `wait`, the fixed-latency dependency of consecutive DFMAs).  GAIN: the input is multiplied by `gain`.
+template <int NSEC, int NS, int NUM, int NUMB, int N, bool GAIN, bool STORE>
+__device__ __forceinline__ void sos_block(const float (&x)[N], float (&y)[N], double gain,
+                                          const double (&c)[NSEC][5], double (&s)[NSEC][2]) {
+    double pipe[9];
+#pragma unroll
+    for (int d = 0; d < N + NS - 1; ++d) {
+#pragma unroll
+        for (int j = NS - 1; j >= 0; --j) {
+            const int n = d - j;
+            if (n >= 0 && n < N) {
+                const double u = j == 0 ? (GAIN ? gain * (double)x[n] : (double)x[n]) : pipe[j];
+                if (NUMB < 0 || j < NSEC / 2) {
+                    switch (j) {     // compile-time j after unrolling
+                        case 0: pipe[1] = sos_range<0, 1, NUM, NSEC>(u, c, s); break;
+                        case 1: pipe[2] = sos_range<(NSEC > 1 ? 1 : 0), (NSEC > 1 ? 2 : 1), NUM, NSEC>(u, c, s); break;
+                        case 2: pipe[3] = sos_range<(NSEC > 2 ? 2 : 0), (NSEC > 2 ? 3 : 1), NUM, NSEC>(u, c, s); break;
+                        case 3: pipe[4] = sos_range<(NSEC > 3 ? 3 : 0), (NSEC > 3 ? 4 : 1), NUM, NSEC>(u, c, s); break;
+                        case 4: pipe[5] = sos_range<(NSEC > 4 ? 4 : 0), (NSEC > 4 ? 5 : 1), NUM, NSEC>(u, c, s); break;
+                        case 5: pipe[6] = sos_range<(NSEC > 5 ? 5 : 0), (NSEC > 5 ? 6 : 1), NUM, NSEC>(u, c, s); break;
+                        case 6: pipe[7] = sos_range<(NSEC > 6 ? 6 : 0), (NSEC > 6 ? 7 : 1), NUM, NSEC>(u, c, s); break;
+                        default: pipe[8] = sos_range<(NSEC > 7 ? 7 : 0), (NSEC > 7 ? 8 : 1), NUM, NSEC>(u, c, s); break;
+                    }
+                } else {
+                    constexpr int NB = NUMB < 0 ? 0 : NUMB;
+                    switch (j) {
+                        case 4: pipe[5] = sos_range<(NSEC > 4 ? 4 : 0), (NSEC > 4 ? 5 : 1), NB, NSEC>(u, c, s); break;
+                        case 5: pipe[6] = sos_range<(NSEC > 5 ? 5 : 0), (NSEC > 5 ? 6 : 1), NB, NSEC>(u, c, s); break;
+                        case 6: pipe[7] = sos_range<(NSEC > 6 ? 6 : 0), (NSEC > 6 ? 7 : 1), NB, NSEC>(u, c, s); break;
+                        default: pipe[8] = sos_range<(NSEC > 7 ? 7 : 0), (NSEC > 7 ? 8 : 1), NB, NSEC>(u, c, s); break;
+                    }
+                }
+            }
+        }
+        if (STORE && d >= NS - 1) y[d - (NS - 1)] = (float)pipe[NS];
+    }
+}
+
 // WRITE=false: tail pass (zero state, last `tail` samples, end state -> slot k+1)
 // WRITE=true : main pass (state from slot k, float32 output)
 // ------------------------------------------------------------------ warm-up path
@@ -89,7 +132,7 @@ __device__ __forceinline__ double sos_step(double u, const double (&c)[NSEC][5],
 // The backward sweep cannot run in place (its warm-up reads the forward result of the
 // neighbouring chunk), so the forward result lives in the workspace.
 template <int NSEC, bool REV, bool VEC, int NT, int NUM, int NUMB = -1>
-__global__ void __launch_bounds__(NT, 512 / NT)
+__global__ void __launch_bounds__(NT, (NSEC >= 8 ? 1 : 512 / NT))     // 8 sections: 64 coefficient + 32 state registers
 sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, int64_t T,
                 int64_t ldx, int64_t ldy, int L, int tail, int nChunks, int padlen, int zero_phase,
                 SosCoef coef, double* __restrict__ padbuf, double gain, int tail_b) {
@@ -218,25 +261,21 @@ sos_warm_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t C, i
         const int sbase = st * kWSub;
         if (NUMB >= 0 && st < s_full) {                      // early warm-up of a pair: first cascade only, nothing stored
             if (sbase >= ulo && sbase + kWSub <= uhi) {
+                float xs[kWSub], ys[kWSub];
 #pragma unroll
-                for (int v = 0; v < kWSub / 4; ++v) {
-                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].x), c, s, false);
-                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].y), c, s, false);
-                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].z), c, s, false);
-                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].w), c, s, false);
-                }
+                for (int v = 0; v < kWSub / 4; ++v) { xs[4 * v] = xin[v].x; xs[4 * v + 1] = xin[v].y; xs[4 * v + 2] = xin[v].z; xs[4 * v + 3] = xin[v].w; }
+                sos_block<NSEC, (NSEC / 2 > 0 ? NSEC / 2 : 1), NUM, NUMB, kWSub, (NUM >> 1) != 0, false>(xs, ys, gain, c, s);
             }
         } else if (sbase >= ulo && sbase + kWSub <= uhi) {          // whole stage inside the row: the common case
+            float xs[kWSub], ys[kWSub];
 #pragma unroll
-            for (int v = 0; v < kWSub / 4; ++v) {
-                float4 yv;
-                yv.x = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].x), c, s);
-                yv.y = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].y), c, s);
-                yv.z = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].z), c, s);
-                yv.w = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].w), c, s);
-                if (write) {
-                    if (!REV) *reinterpret_cast<float4*>(mine + 4 * (v ^ swz)) = yv;
-                    else *reinterpret_cast<float4*>(mine + 4 * ((PP - 1 - v) ^ swz)) = make_float4(yv.w, yv.z, yv.y, yv.x);
+            for (int v = 0; v < kWSub / 4; ++v) { xs[4 * v] = xin[v].x; xs[4 * v + 1] = xin[v].y; xs[4 * v + 2] = xin[v].z; xs[4 * v + 3] = xin[v].w; }
+            sos_block<NSEC, NSEC, NUM, NUMB, kWSub, (NUM >> 1) != 0, true>(xs, ys, gain, c, s);
+            if (write) {
+#pragma unroll
+                for (int v = 0; v < kWSub / 4; ++v) {
+                    if (!REV) *reinterpret_cast<float4*>(mine + 4 * (v ^ swz)) = make_float4(ys[4 * v], ys[4 * v + 1], ys[4 * v + 2], ys[4 * v + 3]);
+                    else *reinterpret_cast<float4*>(mine + 4 * ((PP - 1 - v) ^ swz)) = make_float4(ys[4 * v + 3], ys[4 * v + 2], ys[4 * v + 1], ys[4 * v]);
                 }
             }
         } else {                                            // outside the row / ragged chunk end: state frozen

@@ -66,7 +66,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // Thread q = blockIdx.x * 256 + tid owns MEMORY chunk q (row q / nChunks, chunk j = q % nChunks) in both
 // sweep directions; the backward sweep walks its chunk from the end and warms up on chunk q + 1.
 template <int NSEC, bool REV, int NUM, int NUMB>
-__global__ void __launch_bounds__(kTNT, 2)
+__global__ void __launch_bounds__(kTNT, (NSEC >= 8 ? 1 : 2))
 sos_warm_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                     const float* __restrict__ x, int64_t C, int64_t T, int L, int tail, int nChunks, int padlen,
                     int zero_phase, SosCoef coef, double* __restrict__ padbuf, double gain, int tail_b) {
@@ -167,26 +167,19 @@ sos_warm_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                         xin[v] = make_float4(t4.w, t4.z, t4.y, t4.x);
                     }
                 }
+                float xs[16], ys[16];
+#pragma unroll
+                for (int v = 0; v < 4; ++v) { xs[4 * v] = xin[v].x; xs[4 * v + 1] = xin[v].y; xs[4 * v + 2] = xin[v].z; xs[4 * v + 3] = xin[v].w; }
                 if (early) {
-#pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].x), c, s, false);
-                        (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].y), c, s, false);
-                        (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].z), c, s, false);
-                        (void)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].w), c, s, false);
-                    }
+                    sos_block<NSEC, (NSEC / 2 > 0 ? NSEC / 2 : 1), NUM, NUMB, 16, (NUM >> 1) != 0, false>(xs, ys, gain, c, s);
                 } else {
+                    sos_block<NSEC, NSEC, NUM, NUMB, 16, (NUM >> 1) != 0, true>(xs, ys, gain, c, s);
+                    if (write) {
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        const int p = 4 * h + v;
-                        float4 yv;
-                        yv.x = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].x), c, s);
-                        yv.y = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].y), c, s);
-                        yv.z = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].z), c, s);
-                        yv.w = (float)sos_step<NSEC, NUM, NUMB>(IN((double)xin[v].w), c, s);
-                        if (write) {
-                            if (!REV) *reinterpret_cast<float4*>(mine + 4 * (p ^ swz)) = yv;
-                            else *reinterpret_cast<float4*>(mine + 4 * ((kTSub / 4 - 1 - p) ^ swz)) = make_float4(yv.w, yv.z, yv.y, yv.x);
+                        for (int v = 0; v < 4; ++v) {
+                            const int p = 4 * h + v;
+                            if (!REV) *reinterpret_cast<float4*>(mine + 4 * (p ^ swz)) = make_float4(ys[4 * v], ys[4 * v + 1], ys[4 * v + 2], ys[4 * v + 3]);
+                            else *reinterpret_cast<float4*>(mine + 4 * ((kTSub / 4 - 1 - p) ^ swz)) = make_float4(ys[4 * v + 3], ys[4 * v + 2], ys[4 * v + 1], ys[4 * v]);
                         }
                     }
                 }

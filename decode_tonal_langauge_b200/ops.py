@@ -201,7 +201,7 @@ def _tma_enabled() -> bool:
     return os.environ.get("ECOG_SOS_TMA", "0") == "1"
 
 
-def tma_chunk(Cn: int, T: int, tail: int) -> Optional[int]:
+def tma_chunk(Cn: int, T: int, tail: int, max_per_sm: int = 2) -> Optional[int]:
     """Chunk length for the TMA sweeps (csrc/sosfilt_tma.cu): L divides T, L % 32 == 0, L >= tail.  The grid
     is ceil(Cn * T / L / 256) CTAs of 256 chunk-threads, two of which fit an SM; CTAs are dealt round robin,
     so the sweep lasts as long as the busiest SM's ceil(CTAs / 148) CTAs take, each doing L + tail samples per
@@ -217,8 +217,8 @@ def tma_chunk(Cn: int, T: int, tail: int) -> Optional[int]:
             continue
         ctas = -(-Cn * n // 256)
         per_sm = -(-ctas // D.NUM_SMS)
-        if per_sm > 2:
-            continue                       # more chunks than two resident CTAs per SM: only more warm-up
+        if per_sm > max_per_sm:
+            continue                       # more chunks than the resident CTAs per SM: only more warm-up
         cost = per_sm * (L + tail) / (0.62 if per_sm == 1 else 0.75)
         if best is None or cost < best[0]:
             best = (cost, L)
@@ -306,7 +306,9 @@ def pair_plan(Cn: int, T: int, ld_ok: bool, A: D.SosDesign, B: D.SosDesign):
     tail = D.warm_tail(natural, min(int(D.WARM_MAX_OVERHEAD * L), T + D.SUB))
     if tail < 0 or 4 * tail + 64 > T:
         return None
-    threads = 512 if Cn * n_chunks >= 2 * D.NUM_SMS * 512 else (384 if _pair_threads_per_sm() == 384 else 256)
+    # one CTA per SM (the 8-section kernel holds 64 coefficient and 32 state registers per thread)
+    tps = _pair_threads_per_sm()
+    threads = 512 if tps >= 512 else (384 if tps == 384 else 256)
     plan = nat.SosPlan(8, 1, dsg.padlen, L, tail, nat.SOS_WARMUP, threads, 4, min(tail_b, tail))
     return dsg, plan, tail
 
@@ -337,7 +339,7 @@ def sosfilt_pair(x: torch.Tensor, A: D.SosDesign, B: D.SosDesign, out: Optional[
     dsg, plan, V = pp
     if _tma_enabled() and _ld(x) == T and _ld(y) == T:
         tail32 = -(-V // 32) * 32
-        L = tma_chunk(Cn, T, tail32)
+        L = tma_chunk(Cn, T, tail32, max_per_sm=1)       # the 8-section kernel keeps its coefficients in registers: one CTA per SM
         if L is not None and T // L > 1:
             plan = nat.SosPlan(8, 1, dsg.padlen, L, tail32, nat.SOS_WARMUP_TMA, 256, 4, -(-min(plan.tail_b, V) // 32) * 32)
     if T <= dsg.padlen:
@@ -540,8 +542,7 @@ def _fft_resample(x: torch.Tensor, num: int, bin_gain: Optional[np.ndarray], gai
     t = lambda name, arr: _dev_table(key + (name,), lambda: arr, dev)
     tables = nat.ResampleTables()
     keep = []
-    for name, arr in (("perm_fa", rp.fwd.a.perm), ("perm_fb", rp.fwd.b.perm), ("perm_ia", rp.inv.a.perm),
-                      ("perm_ib", rp.inv.b.perm), ("tw_fa", rp.fwd.a.tw), ("tw_fb", rp.fwd.b.tw),
+    for name, arr in (("tw_fa", rp.fwd.a.tw), ("tw_fb", rp.fwd.b.tw),
                       ("tw_ia", rp.inv.a.tw), ("tw_ib", rp.inv.b.tw), ("tw_big_f_hi", rp.fwd.tw_hi),
                       ("tw_big_f_lo", rp.fwd.tw_lo), ("tw_big_i_hi", rp.inv.tw_hi), ("tw_big_i_lo", rp.inv.tw_lo),
                       ("tw_T", rp.tw_T), ("tw_num", rp.tw_num), ("tw_q_f", rp.fwd.tw_q), ("tw_q_i", rp.inv.tw_q)):
@@ -570,9 +571,9 @@ def _fft_resample(x: torch.Tensor, num: int, bin_gain: Optional[np.ndarray], gai
 def _fft_tables(bp: FP.BigPlan, key, dev):
     t = lambda name, arr: _dev_table(key + (name,), lambda: arr, dev)
     tb = nat.FftTables()
-    keep = [t("perm_a", bp.a.perm), t("perm_b", bp.b.perm), t("tw_a", bp.a.tw), t("tw_b", bp.b.tw),
+    keep = [t("tw_a", bp.a.tw), t("tw_b", bp.b.tw),
             t("tw_hi", bp.tw_hi), t("tw_lo", bp.tw_lo), t("tw_q", bp.tw_q)]
-    tb.perm_a, tb.perm_b, tb.tw_a, tb.tw_b, tb.tw_big_hi, tb.tw_big_lo, tb.tw_q = [k.data_ptr() for k in keep]
+    tb.tw_a, tb.tw_b, tb.tw_big_hi, tb.tw_big_lo, tb.tw_q = [k.data_ptr() for k in keep]
     return tb, keep
 
 

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ECOG_ABI_VERSION 5
+#define ECOG_ABI_VERSION 6
 
 #define ECOG_OK 0
 #define ECOG_E_VALUE (-1)     /* bad argument (reference raises ValueError)          */
@@ -166,12 +166,10 @@ typedef struct {
     ecog_fft_axis ia, ib;   /* inverse: N' = num/2 = ia.n * ib.n                       */
 } ecog_resample_plan;
 /* device tables, all built on the host in float64 and rounded once:
- *   d_perm_*  int32 digit-reversal permutations (length = axis n)
  *   d_tw_*    float2 roots of unity W_n^k (length = axis n)
  *   d_tw_big_f / d_tw_big_i  float2 four-step twiddle factors, two-level tables
  *   d_untangle float2 x (num/2 + 1) pairs used by the spectrum repack                 */
 typedef struct {
-    const int32_t *perm_fa, *perm_fb, *perm_ia, *perm_ib;
     const float *tw_fa, *tw_fb, *tw_ia, *tw_ib;
     const float *tw_big_f_hi, *tw_big_f_lo, *tw_big_i_hi, *tw_big_i_lo;
     int32_t big_f_split, big_i_split;
@@ -199,7 +197,6 @@ int ecog_fft_resample(const float* d_x, float* d_y, int64_t C, int64_t ldx, int6
  *                       or complex input and complex or real-part output (zero padding, chirp
  *                       and spectrum multiplications).  May run in place.                      */
 typedef struct {
-    const int32_t *perm_a, *perm_b;      /* digit reversal per axis                           */
     const float *tw_a, *tw_b;            /* W_n^k per axis                                    */
     const float *tw_big_hi, *tw_big_lo;  /* four-step twiddles, two-level table (split 4096)  */
     const double *tw_q;                  /* double2 W_N^q, q < fa.n                           */

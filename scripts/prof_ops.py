@@ -54,6 +54,9 @@ FN = {
     "notch_tma": lambda: ops.butter(x, [58, 62], fs, 4, False, "bandstop", mode="tma"),
     "bandpass_tma": lambda: ops.butter(x, [70, 150], fs, 4, False, "bandpass", mode="tma"),
     "pair_tma": lambda: _with_env("ECOG_SOS_TMA", "1", FN["pair"]),
+    "pair256": lambda: _with_env("ECOG_PAIR_TPS", "256", FN["pair"]),
+    "pair384": lambda: _with_env("ECOG_PAIR_TPS", "384", FN["pair"]),
+    "pair512": lambda: _with_env("ECOG_PAIR_TPS", "512", FN["pair"]),
     "colsum": lambda: ops.car_colsum(x),
     "hilbert_car": lambda: ops.hilbert(x, fs, [70.0, 150.0], car=(COLSUM, C)),
 }
