@@ -43,17 +43,34 @@ def _default_backend():
     return ops
 
 
-def car_sharded(x_local: torch.Tensor, c_lo: int, n_channels: int, exclude_channels: Sequence[int] = (),
-                group=None, backend=None, reduce=None) -> torch.Tensor:
-    """CAR of a channel shard.  ``x_local`` holds global rows [c_lo, c_lo + x_local.shape[0])."""
-    backend = backend or _default_backend()
+def local_exclusions(exclude_channels: Sequence[int], c_lo: int, rows_local: int, n_channels: int, bands: int = 1):
+    """Validated global ``exclude_channels`` -> (local row indices, global included count).
+
+    After a multi-band ``frequency_filter`` the reference's array is band-major: global row
+    ``b * n_channels + c`` (ref: frequency_filter.py:75 concatenates the bands along the channel axis) and
+    CAR spans all ``bands * n_channels`` rows.  A shard holds rows ``c_lo .. c_lo + rows_local / bands`` of
+    every band, band-major as well, so global row (b, c) is local row ``b * (rows_local / bands) + c - c_lo``."""
     if not isinstance(exclude_channels, (list, tuple)):
         raise ValueError("exclude_channels must be a list of integers.")
-    if any(ch < 0 or ch >= n_channels for ch in exclude_channels):
+    total = bands * n_channels
+    if any(ch < 0 or ch >= total for ch in exclude_channels):
         raise ValueError("exclude_channels contains invalid channel indices.")
-    c_hi = c_lo + x_local.shape[0]
+    per = rows_local // bands
+    local = []
+    for ch in exclude_channels:
+        b, c = divmod(int(ch), n_channels)
+        if c_lo <= c < c_lo + per:
+            local.append(b * per + c - c_lo)
+    return local, total - len(set(exclude_channels))
+
+
+def car_sharded(x_local: torch.Tensor, c_lo: int, n_channels: int, exclude_channels: Sequence[int] = (),
+                group=None, backend=None, reduce=None, bands: int = 1) -> torch.Tensor:
+    """CAR of a channel shard.  ``x_local`` holds global channels [c_lo, c_lo + rows / bands) of each of the
+    ``bands`` concatenated band copies (``bands`` = 1: plain rows [c_lo, c_lo + rows))."""
+    backend = backend or _default_backend()
+    local_excl, n_included = local_exclusions(exclude_channels, c_lo, x_local.shape[0], n_channels, bands)
     weights = None
-    local_excl = [ch - c_lo for ch in exclude_channels if c_lo <= ch < c_hi]
     if local_excl:
         w = np.ones(x_local.shape[0], dtype=np.float32)
         w[local_excl] = 0.0
@@ -63,7 +80,6 @@ def car_sharded(x_local: torch.Tensor, c_lo: int, n_channels: int, exclude_chann
         reduce(partial)
     elif dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)     # T floats over NVLink
-    n_included = n_channels - len(set(exclude_channels))
     return backend.car_apply(x_local, partial, n_included)
 
 
@@ -105,14 +121,10 @@ def preprocess_signal_sharded(x_local, steps: List[dict], block_params: Namespac
             if excl is None:
                 excl = block_params.exclude_channels = []
             # after a multi-band frequency_filter the global layout is band-major; CAR then spans
-            # bands * n_channels rows and this shard holds `bands` disjoint slices of them
-            if bands != 1:
-                raise NotImplementedError("channel-sharded CAR after a multi-band frequency_filter")
-            x = car_sharded(x, c_lo, n_channels, excl, group, backend, reduce=reduce)
+            # bands * n_channels rows and this shard holds `bands` slices of them (local_exclusions)
+            x = car_sharded(x, c_lo, n_channels, excl, group, backend, reduce=reduce, bands=bands)
         elif g[0] == "car_hilbert":
-            if bands != 1:
-                raise NotImplementedError("channel-sharded CAR after a multi-band frequency_filter")
-            x = P._run_group(x, g, block_params, False, shard=(c_lo, n_channels, reduce))
+            x = P._run_group(x, g, block_params, False, shard=(c_lo, n_channels, reduce, bands))
         else:
             x = P._run_group(x, g, block_params, False)
             if g[0] == "step" and P._short(g[1]) == "frequency_filter":

@@ -142,9 +142,9 @@ def _group_name(group: tuple) -> str:
 
 def _run_group(x, group: tuple, params: Namespace, strict: bool, shard=None):
     """Run one fusion group on a device tensor; ``params`` is the shared Namespace.
-    ``shard`` (channel-sharded recordings, distributed.py): ``(c_lo, n_channels, reduce)`` -- the local
-    rows are global rows [c_lo, c_lo + C_local), ``exclude_channels`` holds global indices and
-    ``reduce(colsum)`` all-reduces the column sums in place."""
+    ``shard`` (channel-sharded recordings, distributed.py): ``(c_lo, n_channels, reduce[, bands])`` -- the
+    local rows are global channels [c_lo, c_lo + C_local / bands) of each band copy, ``exclude_channels``
+    holds global (band-major) row indices and ``reduce(colsum)`` all-reduces the column sums in place."""
     from . import design as D
     from . import ops
     kind = group[0]
@@ -170,13 +170,14 @@ def _run_group(x, group: tuple, params: Namespace, strict: bool, shard=None):
             w, n_inc = ops._car_weights(x.shape[0], excl, x.device)
             colsum = ops.car_colsum(x, w)
         else:
-            c_lo, n_channels, reduce = shard
-            excl = S.car_exclusions(params, n_channels)
-            local = [ch - c_lo for ch in excl if c_lo <= ch < c_lo + x.shape[0]]
+            from .distributed import local_exclusions
+            c_lo, n_channels, reduce = shard[:3]
+            bands = shard[3] if len(shard) > 3 else 1
+            excl = S.car_exclusions(params, bands * n_channels)
+            local, n_inc = local_exclusions(excl, c_lo, x.shape[0], n_channels, bands)
             w, _ = ops._car_weights(x.shape[0], local, x.device)
             colsum = ops.car_colsum(x, w)
             reduce(colsum)
-            n_inc = n_channels - len(set(excl))
         apply_step_params(params, hil_step, strict)
         (_, p), = S.band_plan(params)
         return ops.hilbert(x, params.signal_freq, car=(colsum, n_inc), **p)

@@ -46,10 +46,17 @@ def _worker(rank, world, port, C, T, excl, out_dir):
         # band-major layout after a 2-band frequency_filter: local rows [band0 shard; band1 shard]
         two = torch.cat([y_local, -y_local], dim=0)
         full2 = D.gather_channels(two, C, bands=2)
+        # CAR over the band-major array of a 2-band frequency_filter: (2 C) rows, exclusions are global rows
+        xb = rng.standard_normal((2 * C, T)).astype(np.float32)
+        local_b = torch.from_numpy(np.concatenate([xb[lo:hi], xb[C + lo:C + hi]]).copy())
+        excl_b = [e for e in (1, C + 2) if e < 2 * C]
+        yb = D.car_sharded(local_b, lo, C, excl_b, backend=NumpyBackend(), bands=2)
+        full_b = D.gather_channels(yb, C, bands=2)
         runs = torch.arange(lo, hi, dtype=torch.int32) * 7 % 50
         sel = D.gather_selection(runs, lo, C, 40)
         if rank == 0:
-            np.savez(os.path.join(out_dir, "out.npz"), full=full.numpy(), full2=full2.numpy(), sel=np.array(sel))
+            np.savez(os.path.join(out_dir, "out.npz"), full=full.numpy(), full2=full2.numpy(), sel=np.array(sel),
+                     full_b=full_b.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -64,6 +71,10 @@ def test_channel_sharded_car_over_gloo(tmp_path, C, excl):
     ref = S.car_rereference(x, excl)
     assert np.max(np.abs(out["full"] - ref)) < 1e-6
     assert np.max(np.abs(out["full2"][:C] - ref)) < 1e-6 and np.max(np.abs(out["full2"][C:] + ref)) < 1e-6
+    rng = np.random.default_rng(0)
+    rng.standard_normal((C, T))
+    xb = rng.standard_normal((2 * C, T)).astype(np.float32)
+    assert np.max(np.abs(out["full_b"] - S.car_rereference(xb, [1, C + 2]))) < 1e-6
     runs = np.arange(C) * 7 % 50
     assert out["sel"].tolist() == [int(c) for c in np.nonzero(runs > 40)[0]]
 
@@ -85,3 +96,12 @@ def test_car_sharded_validates_like_reference():
         D.car_sharded(x, 0, 2, exclude_channels="1", backend=NumpyBackend())
     with pytest.raises(ValueError):
         D.car_sharded(x, 0, 2, exclude_channels=[5], backend=NumpyBackend())
+
+
+def test_local_exclusions_band_major():
+    # 10 channels, 3 bands, shard = channels [4, 7): local rows [b0: 4,5,6 | b1: 4,5,6 | b2: 4,5,6]
+    local, n_inc = D.local_exclusions([5, 10 + 4, 20 + 9, 3], 4, 9, 10, bands=3)
+    assert local == [1, 3] and n_inc == 30 - 4
+    assert D.local_exclusions([], 0, 5, 5) == ([], 5)
+    with pytest.raises(ValueError):
+        D.local_exclusions([30], 4, 9, 10, bands=3)
