@@ -230,6 +230,35 @@ def czt_plan(T: int, num: int) -> CztPlan:
     return _czt_plan(int(T), int(num), None)
 
 
+@dataclass(frozen=True)
+class BluesteinPlan:
+    """DFT of ANY length T as a circular convolution of smooth length M >= 2 T - 1 (chirp-z with all T bins):
+
+      forward  X[k] = conj(w[k]) * sum_n (x[n] conj(w[n])) w[k - n]
+      inverse  x[n] = (1/T) w[n] * sum_k (X[k] w[k]) conj(w[n - k]),      w[j] = exp(i pi j^2 / T)
+
+    Used by the whole-record Gaussian-Hilbert path (ref: frequency_filter.py:154-184) when the row length has a
+    prime factor other than 2, 3, 5 (real TDT rates).  FBf / FBi: FFTs of the two chirp kernels, 1/M folded in."""
+    T: int
+    M: int
+    fft: BigPlan
+    w: np.ndarray        # (T,) complex128 chirp
+    FBf: np.ndarray      # (M, 2) float32
+    FBi: np.ndarray      # (M, 2) float32
+
+
+@functools.lru_cache(maxsize=4)
+def bluestein_plan(T: int) -> BluesteinPlan:
+    from scipy import fft as sp_fft
+    T = int(T)
+    M = next_smooth_even(2 * T - 1)
+    w = _chirp(T, T)
+    b = np.zeros(M, dtype=np.complex128)
+    b[:T] = w
+    b[M - np.arange(1, T)] = w[1:T]
+    return BluesteinPlan(T, M, big_plan(M, MAX_AXIS_NARROW), w, _c2(sp_fft.fft(b) / M), _c2(sp_fft.fft(np.conj(b)) / M))
+
+
 # ------------------------------------------------------- two-stage resampling
 FIR_MAX_TAPS = 256
 FIR_ATTENUATION_DB = 120.0

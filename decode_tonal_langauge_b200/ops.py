@@ -422,24 +422,16 @@ def _hilbert_global(x: torch.Tensor, fs: float, cfs, sds, envelope: bool, out: O
     """Whole-record Gaussian-Hilbert bank, exactly as the reference does it (ref:
     frequency_filter.py:154-184): FFT of the row, Gaussian x analytic mask per band, inverse FFT,
     |.| or real part, mean over bands.  Used when the bands' time kernels do not fit the 4096-sample
-    blocks of the fused kernel (low-frequency bands).  Complex four-step FFTs of length T."""
+    blocks of the fused kernel (low-frequency bands).  Complex four-step FFTs of length T, or chirp-z
+    convolutions when T is not a product of two 2-3-5 smooth factors (_hilbert_global_bluestein)."""
     Cn, T = x.shape
     try:
         bp = FP.big_plan(int(T), FP.MAX_AXIS_NARROW)
-    except NotImplementedError as e:
-        raise NotImplementedError(
-            f"low-frequency Gaussian bands need a whole-record FFT, and the row length {T} is not a "
-            f"product of two 2-3-5 smooth factors <= {FP.MAX_AXIS_NARROW} ({e})")
+    except NotImplementedError:
+        return _hilbert_global_bluestein(x, fs, cfs, sds, envelope, out)      # non-smooth row length
     dev = x.device
     nb = len(cfs)
-    freqs = np.fft.fftfreq(T, 1.0 / fs)
-    h = np.zeros(T)
-    if T % 2 == 0:
-        h[0] = h[T // 2] = 1.0
-        h[1:T // 2] = 2.0
-    else:
-        h[0] = 1.0
-        h[1:(T + 1) // 2] = 2.0
+    H = _global_band_gains(T, fs, cfs, sds)
     y = out if out is not None else torch.empty((Cn, T), dtype=torch.float32, device=dev)
     blk = int(max(1, min(Cn, HILBERT_GLOBAL_BLOCK_BYTES // (3 * T * 8))))
     for c0 in range(0, Cn, blk):
@@ -450,15 +442,69 @@ def _hilbert_global(x: torch.Tensor, fs: float, cfs, sds, envelope: bool, out: O
                                          _stream()))
         fft_c2c(Z, bp)
         for b in range(nb):
-            H = np.exp(-0.5 * ((freqs - cfs[b]) / sds[b]) ** 2)
-            H[0] = 0.0
-            g = torch.from_numpy(FP._c2((H * h / T).astype(np.complex128))).to(dev)     # 1/T of the inverse FFT
+            g = torch.from_numpy(FP._c2((H[b] / T).astype(np.complex128))).to(dev)     # 1/T of the inverse FFT
             _modulate(Z, T, g, W, T)
             fft_c2c(W, bp, inverse=True)
             nat.check(lib.ecog_cplx_abs_accumulate(_ptr(W), T, _ptr(y[c0:c1]), _ld(y), T, c1 - c0,
                                                    1 if envelope else 0, 1.0 / nb, 1 if b else 0, _stream()))
             del g
         del Z, W
+    return y
+
+
+def _global_band_gains(T: int, fs: float, cfs, sds) -> np.ndarray:
+    """(nb, T) float64: Gaussian x analytic mask on the fftfreq grid, H[0] = 0 (ref: frequency_filter.py:155-175)."""
+    freqs = np.fft.fftfreq(T, 1.0 / fs)
+    h = np.zeros(T)
+    if T % 2 == 0:
+        h[0] = h[T // 2] = 1.0
+        h[1:T // 2] = 2.0
+    else:
+        h[0] = 1.0
+        h[1:(T + 1) // 2] = 2.0
+    H = np.exp(-0.5 * ((freqs[None, :] - np.asarray(cfs)[:, None]) / np.asarray(sds)[:, None]) ** 2)
+    H[:, 0] = 0.0
+    return H * h[None, :]
+
+
+def _hilbert_global_bluestein(x: torch.Tensor, fs: float, cfs, sds, envelope: bool, out: Optional[torch.Tensor]):
+    """The whole-record bank for rows of ANY length (real TDT rates: 600 s at 3051.76 Hz = 1 831 054 = 2 x 915 527
+    samples): both DFTs of frequency_filter.py:167,177 run as chirp-z convolutions of a smooth length
+    M >= 2 T - 1 (fftplan.BluesteinPlan).  Per band: X g w -> FFT_M -> x FBi -> IFFT_M -> (x w) -> |.| or Re."""
+    Cn, T = x.shape
+    p = FP.bluestein_plan(int(T))
+    dev = x.device
+    nb = len(cfs)
+    H = _global_band_gains(T, fs, cfs, sds)
+    key = ("bluestein", T)
+    pre = _dev_table(key + ("pre",), lambda: FP._c2(np.conj(p.w)), dev)
+    FBf = _dev_table(key + ("FBf",), lambda: p.FBf, dev)
+    FBi = _dev_table(key + ("FBi",), lambda: p.FBi, dev)
+    post = _dev_table(key + ("post",), lambda: FP._c2(p.w), dev) if not envelope else None
+    y = out if out is not None else torch.empty((Cn, T), dtype=torch.float32, device=dev)
+    blk = int(max(1, min(Cn, HILBERT_GLOBAL_BLOCK_BYTES // (2 * p.M * 8 + T * 8))))
+    for c0 in range(0, Cn, blk):
+        c1 = min(Cn, c0 + blk)
+        A = torch.empty((c1 - c0, p.M, 2), dtype=torch.float32, device=dev)
+        _modulate(x[c0:c1], T, pre, A, p.M)                                   # x conj(w), zero padded
+        fft_c2c(A, p.fft)
+        _modulate(A, p.M, FBf, A, p.M)
+        fft_c2c(A, p.fft, inverse=True)                                       # A[:T] conj(w) = X
+        Z = torch.empty((c1 - c0, T, 2), dtype=torch.float32, device=dev)
+        nat.check(lib.ecog_cplx_modulate(_ptr(A), 1, T, p.M, C.c_void_p(0), _ptr(Z), 1, T, T, c1 - c0, _stream()))
+        for b in range(nb):
+            # X[k] = A[k] conj(w[k]); the inverse wants X[k] g[k] w[k] = A[k] g[k] (|w| = 1): a REAL table
+            g = torch.from_numpy(FP._c2((H[b] / T).astype(np.complex128))).to(dev)
+            _modulate(Z, T, g, A, p.M)
+            fft_c2c(A, p.fft)
+            _modulate(A, p.M, FBi, A, p.M)
+            fft_c2c(A, p.fft, inverse=True)
+            if not envelope:
+                _modulate(A, T, post, A, T)                                   # the unit phasor w[n] matters for Re
+            nat.check(lib.ecog_cplx_abs_accumulate(_ptr(A), p.M, _ptr(y[c0:c1]), _ld(y), T, c1 - c0,
+                                                   1 if envelope else 0, 1.0 / nb, 1 if b else 0, _stream()))
+            del g
+        del A, Z
     return y
 
 

@@ -87,7 +87,7 @@ class _PinnedPool:
         self.free.put(buf)
 
 
-READ_THREADS = 4          # concurrent readers per file: one thread copies ~3-5 GB/s out of the page cache
+READ_THREADS = 8          # concurrent readers per file: one thread copies ~3-5 GB/s out of the page cache
 
 
 def _read_range(path: str, offset: int, view: memoryview) -> None:

@@ -50,8 +50,9 @@ def _import(name: str):
 # ------------------------------------------------------------------ block IO
 def load_block(block_path: str) -> dict:
     """Read one recording block.  A directory holding ``ecog.npz`` / ``audio.npz`` (keys ``data``,
-    ``sf``) is read directly; a TDT tank needs the ``tdt`` wheel like the reference
-    (ref: preprocess/io/tdt_blocks.py:6-18, streams EOG1 / ANIN)."""
+    ``sf``) is read directly; a TDT tank block goes through ``tdt.read_block`` like the reference
+    (ref: preprocess/io/tdt_blocks.py:6-18, streams EOG1 / ANIN) or, without that wheel, through the
+    native stream reader ``tdt_io.read_block``."""
     if os.path.exists(os.path.join(block_path, "ecog.npz")):
         out = {}
         for key in ("ecog", "audio"):
@@ -62,10 +63,14 @@ def load_block(block_path: str) -> dict:
                 out[f"{key}_sf"] = z["sf"][()]
         return out
     try:
-        import tdt
-    except ImportError as exc:
-        raise ImportError(f"{block_path} is not an npz block and the 'tdt' package is not installed") from exc
-    blk = tdt.read_block(block_path)
+        import tdt                                     # the vendor's reader when it is installed
+        reader = getattr(tdt, "read_block", None)
+    except ImportError:
+        reader = None
+    if reader is None:
+        from . import tdt_io                           # stream stores read natively (.tsq / .tev)
+        reader = tdt_io.read_block
+    blk = reader(block_path)
     return {"ecog": blk.streams.EOG1.data, "audio": blk.streams.ANIN.data[:1, :],
             "ecog_sf": blk.streams.EOG1.fs, "audio_sf": blk.streams.ANIN.fs}
 

@@ -193,14 +193,16 @@ def test_hilbert_low_frequency_bands_whole_record(ops, golden, envelope):
     assert max_rel(y, ref) < TOL
 
 
-def test_hilbert_delta_band_and_its_declared_limit(ops):
+@pytest.mark.parametrize("envelope", [True, False])
+def test_hilbert_delta_band_any_row_length(ops, envelope):
+    """Low-frequency bands need the whole-record transform (frequency_filter.py:154-184 accepts any T):
+    smooth lengths through the four-step FFT, prime lengths (real TDT rates) through the chirp-z form."""
     from oracle import steps as S
     rng = np.random.default_rng(2)
-    x = (np.cumsum(rng.standard_normal((2, 8000)), axis=1)).astype(np.float32)
-    y = host(ops.hilbert(dev(x), 400.0, [0.5, 4.0]))
-    assert max_rel(y, S.hilbert_filter(x, 400.0, [0.5, 4.0])) < TOL
-    with pytest.raises(NotImplementedError):          # whole-record path on a prime row length
-        ops.hilbert(dev(np.zeros((1, 8009), np.float32)), 400.0, [0.5, 4.0])
+    for T in (8000, 8009, 100003):
+        x = (np.cumsum(rng.standard_normal((2, T)), axis=1)).astype(np.float32)
+        y = host(ops.hilbert(dev(x), 400.0, [0.5, 4.0], envelope=envelope))
+        assert max_rel(y, S.hilbert_filter(x, 400.0, [0.5, 4.0], envelope=envelope)) < TOL, T
 
 
 # ------------------------------------------------------------------ K6 / K7

@@ -245,3 +245,35 @@ def test_npz_member_is_read_in_place(tmp_path):
     np.savez_compressed(tmp_path / "c.npz", data=big[:, :10], sf=1)
     with pytest.raises(ValueError, match="compressed"):
         SS.locate_npz_array(str(tmp_path / "c.npz"))
+
+
+def test_tdt_tank_stream_reader_round_trip(tmp_path):
+    """tdt_io: the .tsq / .tev stream stores the reference reads through tdt.read_block
+    (ref: preprocess/io/tdt_blocks.py:6-18), on a synthetic tank in the TTank layout."""
+    from decode_tonal_langauge_b200 import tdt_io
+    rng = np.random.default_rng(1)
+    ecog = rng.standard_normal((5, 4096)).astype(np.float32)
+    audio = (rng.standard_normal((2, 8192)) * 1000).astype(np.int16)
+    wide = rng.standard_normal((1, 512))
+    blk_dir = tmp_path / "Sub1" / "HS1-B3"
+    tdt_io.write_block(str(blk_dir), {"EOG1": (ecog, 3051.7578125), "ANIN": (audio, 24414.0625), "Wav8": (wide, 100.0)},
+                       chunk=256)
+    blk = tdt_io.read_block(str(blk_dir))
+    assert np.array_equal(blk.streams.EOG1.data, ecog) and blk.streams.EOG1.data.dtype == np.float32
+    assert blk.streams.EOG1.fs == pytest.approx(3051.7578125) and blk.streams.EOG1.channels == [1, 2, 3, 4, 5]
+    assert np.array_equal(blk.streams.ANIN.data, audio) and blk.streams.ANIN.fs == pytest.approx(24414.0625)
+    assert np.array_equal(blk.streams.Wav8.data, wide) and blk.info.stop > blk.info.start
+    only = tdt_io.read_block(str(blk_dir), store="ANIN")
+    assert list(vars(only.streams)) == ["ANIN"]
+    # records out of time order and channels interleaved arbitrarily: sorted per channel by timestamp
+    tsq = sorted(blk_dir.glob("*.tsq"))[0]
+    heads = np.fromfile(tsq, dtype=tdt_io.TSQ_DTYPE)
+    body = heads[2:-1].copy()
+    rng.shuffle(body)
+    np.concatenate([heads[:2], body, heads[-1:]]).tofile(tsq)
+    assert np.array_equal(tdt_io.read_block(str(blk_dir)).streams.EOG1.data, ecog)
+    # the stage driver's loader falls back to the native reader (no tdt wheel here)
+    data = stages.load_block(str(blk_dir))
+    assert np.array_equal(data["ecog"], ecog) and data["audio"].shape == (1, 8192) and data["audio_sf"] == pytest.approx(24414.0625)
+    with pytest.raises(FileNotFoundError):
+        tdt_io.read_block(str(tmp_path))
