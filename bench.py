@@ -326,22 +326,29 @@ def run_sharded_record(args, torch, dist, world, rank, local, workload="C4"):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ar_events, group_events = [], []
+    def timed(overlap):
+        ar_ev, grp_ev = [], []
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out, _, _ = D.preprocess_signal_sharded(x, FULL6_STEPS, Namespace(signal_freq=fs), c_lo, C, timing=ar_ev,
+                                                    profile=grp_ev, overlap_allreduce=overlap)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / steps, sum(a.elapsed_time(b) for a, b in ar_ev) / steps],
+                         dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return out, float(t[0].item()), float(t[1].item()), len(ar_ev) // steps, _mean_ms([grp_ev])
+
     l0 = nat.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(steps):
-        y, _, _ = D.preprocess_signal_sharded(x, FULL6_STEPS, Namespace(signal_freq=fs), c_lo, C, timing=ar_events,
-                                              profile=group_events)
-    ev1.record()
-    barrier()
+    y, ms_ov, ar_ov, n_ar, step_ms = timed(True)           # all-reduce by time-tile groups on a side stream
     launches = nat.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    ms = torch.tensor([ev0.elapsed_time(ev1) / steps], dtype=torch.float64, device="cuda")
-    ar = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in ar_events]))], dtype=torch.float64, device="cuda")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    dist.all_reduce(ar, op=dist.ReduceOp.MAX)
-    step_ms = _mean_ms([group_events])
+    _, ms_seq, ar_seq, _, step_ms_seq = timed(False)       # one all-reduce of the whole vector on the compute stream
+    ms = torch.tensor([ms_ov], dtype=torch.float64, device="cuda")
+    ar = torch.tensor([ar_seq], dtype=torch.float64, device="cuda")
     # parity: three local rows of rank 0 against the oracle, with the GLOBAL column mean (float64, all-reduced)
     col = x.sum(dim=0, dtype=torch.float64)
     dist.all_reduce(col, op=dist.ReduceOp.SUM)
@@ -361,11 +368,17 @@ def run_sharded_record(args, torch, dist, world, rank, local, workload="C4"):
     return {"workload": desc, "channels": C, "samples": T, "fs": fs, "scaling": "strong", "n_gpus": world,
             "channels_per_rank": c_hi - c_lo, "steps": steps, "ms_per_step": float(ms.item()),
             "value": C * T / (float(ms.item()) * 1e-3), "unit": "channel-samples/s",
-            "allreduce": {"ms": float(ar.item()), "bytes": 4 * T, "share_of_step": float(ar.item()) / float(ms.item()),
-                          "what": "dist.all_reduce(SUM) of the T float32 CAR column sums, CUDA events around the "
-                                  "call on the compute stream (max over ranks); between ecog_car_colsum and the "
-                                  "Hilbert kernel that subtracts the mean in its load"},
-            "step_ms": step_ms, "gpu_launches": int(launches), "clocks": clocks, "parity": parity}
+            "allreduce": {"ms": float(ar.item()), "bytes": 4 * T, "share_of_step": float(ar.item()) / ms_seq,
+                          "what": "dist.all_reduce(SUM) of the T float32 CAR column sums as ONE collective on the compute "
+                                  "stream (overlap off), CUDA events around the call, max over ranks; it sits between "
+                                  "ecog_car_colsum and the Hilbert kernel that subtracts the mean in its load",
+                          "ms_per_step_sequential": ms_seq,
+                          "overlapped": {"ms_per_step": ms_ov, "collectives_per_step": n_ar, "sum_ms": ar_ov,
+                                         "what": "default: column sums, all-reduce and Hilbert blocks by time-tile groups, "
+                                                 "the collectives on a side stream (distributed.OVERLAP_GROUPS); "
+                                                 "sum_ms = time the side stream spent in the collectives"}},
+            "step_ms": step_ms, "step_ms_sequential": step_ms_seq, "gpu_launches": int(launches), "clocks": clocks,
+            "parity": parity}
 
 
 def run_c5_record(args, torch, dist, world, rank, local, n_sessions=64):

@@ -77,6 +77,9 @@ PROTOTYPES = {
     "ecog_hilbert_twiddle_floats": (_SZ, []),
     "ecog_hilbert_twiddles": (C.c_int, [_P]),
     "ecog_hilbert_env": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _I32, _I32, _P, _P, _I32, _I32, _P, _P, _F64, _P]),
+    "ecog_hilbert_blocks": (_I64, [_I64, _I32]),
+    "ecog_hilbert_env_range": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _I32, _I32, _P, _P, _I32, _I32, _P, _P, _F64,
+                                         _I64, _I64, _P]),
     "ecog_resample_workspace": (_SZ, [C.POINTER(ResamplePlan), _I64]),
     "ecog_fft_resample": (C.c_int, [_P, _P, _I64, _I64, _I64, C.POINTER(ResamplePlan),
                                     C.POINTER(ResampleTables), _P, _SZ, _P]),

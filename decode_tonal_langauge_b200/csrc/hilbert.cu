@@ -205,14 +205,15 @@ template <int CNT>
 __global__ void __launch_bounds__(kHT, 2)
 hilbert_env_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t ldx, int64_t ldy,
                    const float* __restrict__ gain, int nb, BandShift shift, int halo, int envelope,
-                   const float2* __restrict__ tw, int64_t nBlocks, const float* __restrict__ colsum, float inv_count) {
+                   const float2* __restrict__ tw, int64_t nBlocks, const float* __restrict__ colsum, float inv_count,
+                   int64_t blk_begin, int64_t blk_end) {
     extern __shared__ __align__(16) float2 hsm[];
     float2* bufA = hsm;                       // [4096 + 256]  conj spectra of block 0 | block 1 (2048 each)
     float2* bufB = hsm + (kN + kN / 16);      // [4096 + 256]  exchange buffer
     const int tid = threadIdx.x;
     const int64_t ch = blockIdx.y;
     const int U = kN - 2 * halo;
-    const int64_t b0 = 2 * (int64_t)blockIdx.x, b1 = b0 + 1;
+    const int64_t b0 = blk_begin + 2 * (int64_t)blockIdx.x, b1 = b0 + 1;
     const float* xr = x + ch * ldx;
     const float2* tw1 = tw;                 // [16][256] : W_256^{(tid>>4) k0}
     const float2* tw2 = tw + 16 * kHT;      // [16][256] : W_4096^{(tid&15)((tid>>4) + 16 k1)}
@@ -224,7 +225,7 @@ hilbert_env_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T
     {   // two real blocks as one complex signal, circular halo
         int64_t s0 = (b0 * U - halo) % T; if (s0 < 0) s0 += T;
         int64_t s1 = (b1 * U - halo) % T; if (s1 < 0) s1 += T;
-        const bool has1 = b1 < nBlocks;
+        const bool has1 = b1 < blk_end;
         const bool wrap = (s0 + kN > T) || (s1 + kN > T);
         if (!wrap) {
 #pragma unroll
@@ -322,7 +323,7 @@ hilbert_env_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T
         for (int k2 = 0; k2 < 16; ++k2) ob[nat0 + 272 * k2] = acc[k2];
         __syncthreads();
         const int64_t bb = sel == 0 ? b0 : b1;
-        if (bb < nBlocks) {
+        if (bb < blk_end) {
             for (int i = tid; i < U; i += kHT) {
                 const int64_t t = bb * U + i;
                 if (t < T) yr[t] = ob[padi(halo + i)];
@@ -409,7 +410,8 @@ template <bool ENV, bool EDGE>
 __global__ void __launch_bounds__(kHT, 2)
 hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t ldx, int64_t ldy,
                     const float* __restrict__ gain, int nb, BandShift shift, int halo,
-                    const float2* __restrict__ tw, int64_t nBlocks, const float* __restrict__ colsum, float inv_count) {
+                    const float2* __restrict__ tw, int64_t nBlocks, const float* __restrict__ colsum, float inv_count,
+                   int64_t blk_begin, int64_t blk_end) {
     extern __shared__ __align__(16) float2 hsm[];
     float2* bufA = hsm;                                   // [4608] forward exchange buffer / inverse exchange
     float2* bufB = bufA + kXchg;                          // [4096 + 256] natural-order spectrum / output staging
@@ -418,7 +420,7 @@ hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t 
     const int tid = threadIdx.x;
     const int64_t ch = blockIdx.y;
     const int U = kN - 2 * halo;
-    const int64_t b0 = 2 * (int64_t)blockIdx.x, b1 = b0 + 1;
+    const int64_t b0 = blk_begin + 2 * (int64_t)blockIdx.x, b1 = b0 + 1;
     const float* xr = x + ch * ldx;
     const float2* tw1 = tw;                               // [16][256]
     const float2* tw2 = tw + 16 * kHT;                    // [16][256]
@@ -431,7 +433,7 @@ hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t 
     {   // two real blocks as one complex signal, circular halo
         int64_t s0 = (b0 * U - halo) % T; if (s0 < 0) s0 += T;
         int64_t s1 = (b1 * U - halo) % T; if (s1 < 0) s1 += T;
-        const bool has1 = b1 < nBlocks;
+        const bool has1 = b1 < blk_end;
         const bool wrap = (s0 + kN > T) || (s1 + kN > T);
         if (!wrap) {
 #pragma unroll
@@ -535,7 +537,7 @@ hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t 
         for (int k2 = EDGE ? 0 : 1; k2 < (EDGE ? 16 : 15); ++k2) ob[nat0 + 272 * k2] = acc[k2];
         __syncthreads();
         const int64_t bb = sel == 0 ? b0 : b1;
-        if (bb < nBlocks) {
+        if (bb < blk_end) {
             float* yo = yr + bb * U;
             const int64_t left = T - bb * U;
             const int lim = left < U ? (int)left : U;
@@ -578,10 +580,24 @@ extern "C" int ecog_hilbert_twiddles(float* h_out) {
     return ECOG_OK;
 }
 
+extern "C" int64_t ecog_hilbert_blocks(int64_t T, int32_t halo) {
+    const int U = kN - 2 * halo;
+    return U > 0 ? ceil_div(T, U) : 0;
+}
+
 extern "C" int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                                 const float* d_gain, int32_t nbands, int32_t rows, const int32_t* h_shift,
                                 const int32_t* h_nz, int32_t halo, int32_t envelope, const float* d_twiddle,
                                 const float* d_colsum, double inv_count, ecog_stream_t stream) {
+    return ecog_hilbert_env_range(d_x, d_y, C, T, ldx, ldy, d_gain, nbands, rows, h_shift, h_nz, halo, envelope, d_twiddle,
+                                  d_colsum, inv_count, 0, -1, stream);
+}
+
+extern "C" int ecog_hilbert_env_range(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                                      const float* d_gain, int32_t nbands, int32_t rows, const int32_t* h_shift,
+                                      const int32_t* h_nz, int32_t halo, int32_t envelope, const float* d_twiddle,
+                                      const float* d_colsum, double inv_count, int64_t block_begin, int64_t block_end,
+                                      ecog_stream_t stream) {
     if (C <= 0 || T <= 0 || ldx < T || ldy < T || C > 65535) return fail(ECOG_E_VALUE, "ecog_hilbert_env: bad shape");
     if (nbands < 1 || nbands > 64) return fail(ECOG_E_VALUE, "ecog_hilbert_env: 1..64 bands supported, got %d", nbands);
     if (rows != 1 && rows != 2 && rows != 4 && rows != 8)
@@ -604,7 +620,12 @@ extern "C" int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t
     }
     const int U = kN - 2 * halo;
     const int64_t nBlocks = ceil_div(T, U);
-    dim3 grid((unsigned)ceil_div(nBlocks, 2), (unsigned)C);
+    if (block_end < 0 || block_end > nBlocks) block_end = nBlocks;
+    if (block_begin < 0 || block_begin % 2 || block_begin > block_end)
+        return fail(ECOG_E_VALUE, "ecog_hilbert_env_range: block range [%lld, %lld) must start at an even block",
+                    (long long)block_begin, (long long)block_end);
+    if (block_begin == block_end) return ECOG_OK;
+    dim3 grid((unsigned)ceil_div(block_end - block_begin, 2), (unsigned)C);
     const size_t smem = (size_t)2 * (kN + kN / 16) * sizeof(float2);
     const float2* tw = reinterpret_cast<const float2*>(d_twiddle);
     cudaStream_t st = (cudaStream_t)stream;
@@ -614,7 +635,8 @@ extern "C" int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t
     do {                                                                                                            \
         ECOG_TRY((smem_attr<hilbert_env8_kernel<ENVV, EDGEV>>(smem8)));                                             \
         hilbert_env8_kernel<ENVV, EDGEV><<<grid, kHT, smem8, st>>>(d_x, d_y, T, ldx, ldy, d_gain, nbands, sh, halo,  \
-                                                                   tw, nBlocks, d_colsum, (float)inv_count);        \
+                                                                   tw, nBlocks, d_colsum, (float)inv_count,         \
+                                                                   block_begin, block_end);                         \
     } while (0)
         const bool edge = halo < 256;
         if (envelope && edge) ECOG_HILBERT8(true, true);
@@ -628,7 +650,8 @@ extern "C" int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t
     do {                                                                                                         \
         ECOG_TRY((smem_attr<hilbert_env_kernel<R>>(smem)));                                                      \
         hilbert_env_kernel<R><<<grid, kHT, smem, st>>>(d_x, d_y, T, ldx, ldy, d_gain, nbands, sh, halo, envelope, \
-                                                       tw, nBlocks, d_colsum, (float)inv_count);                 \
+                                                       tw, nBlocks, d_colsum, (float)inv_count, block_begin,     \
+                                                       block_end);                                               \
     } while (0)
     if (rows == 1) ECOG_HILBERT_LAUNCH(1);
     else if (rows == 2) ECOG_HILBERT_LAUNCH(2);

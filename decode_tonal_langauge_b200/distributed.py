@@ -17,6 +17,7 @@ never does.
 """
 from __future__ import annotations
 
+import os
 from argparse import Namespace
 from copy import deepcopy
 from typing import List, Optional, Sequence, Tuple
@@ -24,6 +25,17 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 import torch.distributed as dist
+
+
+OVERLAP_GROUPS = 8          # time-tile groups of the overlapped CAR all-reduce (5.4 MB of column sums each at C4)
+_comm_streams = {}
+
+
+def _comm_stream(device):
+    key = str(device)
+    if key not in _comm_streams:
+        _comm_streams[key] = torch.cuda.Stream(device=device)
+    return _comm_streams[key]
 
 
 def shard_bounds(n: int, rank: int, world: int) -> Tuple[int, int]:
@@ -85,7 +97,7 @@ def car_sharded(x_local: torch.Tensor, c_lo: int, n_channels: int, exclude_chann
 
 def preprocess_signal_sharded(x_local, steps: List[dict], block_params: Namespace, c_lo: int, n_channels: int,
                               group=None, backend=None, fuse: Optional[bool] = None, timing: Optional[list] = None,
-                              profile: Optional[list] = None):
+                              profile: Optional[list] = None, overlap_allreduce: Optional[bool] = None):
     """``preprocess_signal`` for a channel shard resident on this rank's device: identical step
     semantics (same shared parameter Namespace, same fusion groups), except that the CAR column
     sums are all-reduced between the two kernel enqueues.  Returns ``(local tensor, signal_freq,
@@ -96,6 +108,8 @@ def preprocess_signal_sharded(x_local, steps: List[dict], block_params: Namespac
     from . import preprocessor as P
     x = x_local
     bands = 1
+    if overlap_allreduce is None:
+        overlap_allreduce = os.environ.get("ECOG_OVERLAP_ALLREDUCE", "1") != "0"
     plain = backend is not None            # the CPU test-suite's numpy backend has no fused kernels
     groups = P.fusion_groups(steps) if (P.fusion_enabled(fuse) and not plain) else [("step", s) for s in steps]
 
@@ -111,6 +125,52 @@ def preprocess_signal_sharded(x_local, steps: List[dict], block_params: Namespac
         else:
             dist.all_reduce(colsum, op=dist.ReduceOp.SUM, group=group)
 
+    def overlap(xl, w, n_inc, fs, hp):
+        """CAR column sums -> all-reduce -> Hilbert by TIME-TILE GROUPS: the column sums of group g are
+        all-reduced on a side stream while the kernels of the other groups run; a group's Hilbert blocks
+        start as soon as the sums of its own samples and of the two neighbouring groups (the circular
+        halo) have arrived.  Declines (None) on one rank, on CPU tensors and for whole-record banks."""
+        from . import ops
+        if not (xl.is_cuda and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+            return None
+        info = ops.hilbert_block_info(xl.shape[1], fs, **hp)
+        if info is None:
+            return None
+        halo, U, nblk = info
+        G = min(OVERLAP_GROUPS, nblk // 4)
+        if G < 3:
+            return None
+        T = xl.shape[1]
+        cuts = [2 * ((nblk * g // G) // 2) for g in range(G)] + [nblk]          # even block boundaries
+        main = torch.cuda.current_stream()
+        comm = _comm_stream(xl.device)
+        colsum = torch.empty(T, dtype=torch.float32, device=xl.device)
+        colsum.record_stream(comm)
+        done = []
+        for g in range(G):
+            s0, s1 = cuts[g] * U, min(cuts[g + 1] * U, T)
+            ops.car_colsum(xl[:, s0:s1], w, out=colsum[s0:s1])
+            ready = torch.cuda.Event()
+            ready.record(main)
+            with torch.cuda.stream(comm):
+                comm.wait_event(ready)
+                e0, e1 = torch.cuda.Event(enable_timing=timing is not None), torch.cuda.Event(enable_timing=timing is not None)
+                e0.record(comm)
+                dist.all_reduce(colsum[s0:s1], op=dist.ReduceOp.SUM, group=group)
+                e1.record(comm)
+            done.append(e1)
+            if timing is not None:
+                timing.append((e0, e1))
+        y = torch.empty((xl.shape[0], T), dtype=torch.float32, device=xl.device)
+        waited = set()
+        for g in list(range(1, G)) + [0]:             # group 0 needs the LAST sums (circular halo): it goes last
+            for j in ((g - 1) % G, g, (g + 1) % G):
+                if j not in waited:
+                    main.wait_event(done[j])
+                    waited.add(j)
+            ops.hilbert(xl, fs, car=(colsum, n_inc), out=y, blocks=(cuts[g], cuts[g + 1]), **hp)
+        return y
+
     for g in groups:
         if profile is not None and x.is_cuda:
             ev0 = torch.cuda.Event(enable_timing=True)
@@ -124,7 +184,8 @@ def preprocess_signal_sharded(x_local, steps: List[dict], block_params: Namespac
             # bands * n_channels rows and this shard holds `bands` slices of them (local_exclusions)
             x = car_sharded(x, c_lo, n_channels, excl, group, backend, reduce=reduce, bands=bands)
         elif g[0] == "car_hilbert":
-            x = P._run_group(x, g, block_params, False, shard=(c_lo, n_channels, reduce, bands))
+            x = P._run_group(x, g, block_params, False,
+                             shard=(c_lo, n_channels, reduce, bands, overlap if overlap_allreduce else None))
         else:
             x = P._run_group(x, g, block_params, False)
             if g[0] == "step" and P._short(g[1]) == "frequency_filter":

@@ -144,11 +144,13 @@ def _car_weights(Cn, exclude_channels, device):
     return torch.from_numpy(w).to(device), int(w.sum())
 
 
-def car_colsum(x: torch.Tensor, weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+def car_colsum(x: torch.Tensor, weights: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Phase 1 of the channel-sharded CAR: per-timestep sum over this shard's rows."""
     x = as_signal(x)
     Cn, T = x.shape
-    s = torch.empty(T, dtype=torch.float32, device=x.device)
+    s = out if out is not None else torch.empty(T, dtype=torch.float32, device=x.device)
+    if s.numel() != T or s.dtype != torch.float32 or not s.is_contiguous():
+        raise ValueError("car_colsum: out must be a contiguous float32 vector of T elements")
     nat.check(lib.ecog_car_colsum(_ptr(x), Cn, T, _ld(x), _ptr(weights), _ptr(s), _stream()))
     return s
 
@@ -381,12 +383,15 @@ _hilbert_plans = {}
 
 def hilbert(x: torch.Tensor, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0,
             filterbank_bias=np.log10(0.39), filterbank_slope=0.5, envelope=True,
-            out: Optional[torch.Tensor] = None, car: Optional[Tuple[torch.Tensor, int]] = None) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, car: Optional[Tuple[torch.Tensor, int]] = None,
+            blocks: Optional[Tuple[int, int]] = None) -> torch.Tensor:
     """ref: frequency_filter.py:80-184 (hilbert_filter keyword names kept).
 
     ``car = (colsum, n_included)``: filter ``x - colsum / n_included`` instead of ``x`` -- a
     ``car_rereference`` step directly in front of the bank, folded into the kernel's load
-    (ref: car_rereference.py:34-39; ``colsum`` from ``car_colsum``, all-reduced when channel-sharded)."""
+    (ref: car_rereference.py:34-39; ``colsum`` from ``car_colsum``, all-reduced when channel-sharded).
+    ``blocks = (b0, b1)``: only the overlap-save blocks [b0, b1) are computed (see ``hilbert_block_info``);
+    needs ``out``."""
     x = as_signal(x)
     Cn, T = x.shape
     colsum, inv_count = (None, 0.0) if car is None else (car[0], 1.0 / car[1])
@@ -398,6 +403,8 @@ def hilbert(x: torch.Tensor, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0,
     try:
         halo = FP.hilbert_halo(cfs, sds, float(fs), T)
     except NotImplementedError:
+        if blocks is not None:
+            raise ValueError("block ranges exist only on the block-wise path (hilbert_block_info returned None)")
         if colsum is not None:
             x = car_apply(x, colsum, car[1])
         return _hilbert_global(x, float(fs), cfs, sds, bool(envelope), out)      # low-frequency bands
@@ -409,10 +416,27 @@ def hilbert(x: torch.Tensor, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0,
     gain_h, shift, rows, nz = plan
     gain = _dev_table(key, lambda: gain_h, x.device)
     y = out if out is not None else torch.empty((Cn, T), dtype=torch.float32, device=x.device)
-    nat.check(lib.ecog_hilbert_env(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), _ptr(gain), len(cfs), rows,
-                                   _hptr(shift), _hptr(nz), halo, 1 if envelope else 0,
-                                   _ptr(_hilbert_twiddles(x.device)), _ptr(colsum), float(inv_count), _stream()))
+    if blocks is not None and out is None:
+        raise ValueError("a block range writes into a caller-provided `out`")
+    b0, b1 = (0, -1) if blocks is None else (int(blocks[0]), int(blocks[1]))
+    nat.check(lib.ecog_hilbert_env_range(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), _ptr(gain), len(cfs), rows,
+                                         _hptr(shift), _hptr(nz), halo, 1 if envelope else 0,
+                                         _ptr(_hilbert_twiddles(x.device)), _ptr(colsum), float(inv_count), b0, b1,
+                                         _stream()))
     return y
+
+
+def hilbert_block_info(T: int, fs, freq_ranges, f0=0.018, octspace=1.0 / 7.0, filterbank_bias=np.log10(0.39),
+                       filterbank_slope=0.5, **_):
+    """(halo, useful samples per block U, number of blocks) of the block-wise bank for rows of T samples, or
+    None when this bank runs on the whole-record path.  Block b writes samples [b U, (b+1) U) and reads
+    [b U - halo, (b+1) U + halo) circularly."""
+    cfs, sds = D.gaussian_bank(freq_ranges, f0, octspace, filterbank_bias, filterbank_slope)
+    try:
+        halo = FP.hilbert_halo(cfs, sds, float(fs), int(T))
+    except NotImplementedError:
+        return None
+    return halo, nat.HILBERT_N - 2 * halo, int(lib.ecog_hilbert_blocks(int(T), halo))
 
 
 HILBERT_GLOBAL_BLOCK_BYTES = 3 << 30

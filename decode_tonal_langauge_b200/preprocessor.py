@@ -142,9 +142,11 @@ def _group_name(group: tuple) -> str:
 
 def _run_group(x, group: tuple, params: Namespace, strict: bool, shard=None):
     """Run one fusion group on a device tensor; ``params`` is the shared Namespace.
-    ``shard`` (channel-sharded recordings, distributed.py): ``(c_lo, n_channels, reduce[, bands])`` -- the
-    local rows are global channels [c_lo, c_lo + C_local / bands) of each band copy, ``exclude_channels``
-    holds global (band-major) row indices and ``reduce(colsum)`` all-reduces the column sums in place."""
+    ``shard`` (channel-sharded recordings, distributed.py): ``(c_lo, n_channels, reduce[, bands[, overlap]])`` --
+    the local rows are global channels [c_lo, c_lo + C_local / bands) of each band copy, ``exclude_channels``
+    holds global (band-major) row indices, ``reduce(colsum)`` all-reduces the column sums in place, and
+    ``overlap(x, w, n_inc, fs, hilbert params)`` (optional) runs column sums, all-reduce and Hilbert blocks
+    by time-tile groups with the collective on a side stream (returns None to decline)."""
     from . import design as D
     from . import ops
     kind = group[0]
@@ -176,6 +178,16 @@ def _run_group(x, group: tuple, params: Namespace, strict: bool, shard=None):
             excl = S.car_exclusions(params, bands * n_channels)
             local, n_inc = local_exclusions(excl, c_lo, x.shape[0], n_channels, bands)
             w, _ = ops._car_weights(x.shape[0], local, x.device)
+            overlap = shard[4] if len(shard) > 4 else None
+            if overlap is not None:
+                apply_step_params(params, hil_step, strict)
+                (_, p), = S.band_plan(params)
+                y = overlap(x, w, n_inc, params.signal_freq, p)
+                if y is not None:
+                    return y
+                colsum = ops.car_colsum(x, w)
+                reduce(colsum)
+                return ops.hilbert(x, params.signal_freq, car=(colsum, n_inc), **p)
             colsum = ops.car_colsum(x, w)
             reduce(colsum)
         apply_step_params(params, hil_step, strict)

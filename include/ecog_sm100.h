@@ -150,6 +150,17 @@ int ecog_hilbert_env(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t
                      const float* d_gain, int32_t nbands, int32_t rows, const int32_t* h_shift,
                      const int32_t* h_nz, int32_t halo, int32_t envelope, const float* d_twiddle,
                      const float* d_colsum, double inv_count, ecog_stream_t stream);
+/* The same for overlap-save blocks [block_begin, block_end) only (block_begin even; block_end < 0 = all;
+ * ecog_hilbert_blocks(T, halo) = number of blocks of a row; block b produces samples
+ * [b U, (b+1) U) from inputs [b U - halo, (b+1) U + halo) circularly, U = 4096 - 2 halo).  Lets a
+ * channel-sharded caller start the bank on the time range whose CAR column sums have already been
+ * all-reduced while the collective still runs on the rest (distributed.py).                    */
+int64_t ecog_hilbert_blocks(int64_t T, int32_t halo);
+int ecog_hilbert_env_range(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                           const float* d_gain, int32_t nbands, int32_t rows, const int32_t* h_shift,
+                           const int32_t* h_nz, int32_t halo, int32_t envelope, const float* d_twiddle,
+                           const float* d_colsum, double inv_count, int64_t block_begin, int64_t block_end,
+                           ecog_stream_t stream);
 
 /* ------------------------------------------------- K5: whole-row FFT resample
  * replaces preprocess/signal/downsample.py:21-27 (scipy.signal.resample, real input).
