@@ -154,30 +154,33 @@ sos_warm_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         const int sbase = st * kTSub;
         if (sbase >= ulo) {                     // stages are whole: inside the filtered range or not at all
             const bool early = NUMB >= 0 && st < s_full;     // pair, early warm-up: first cascade only, nothing stored
+            // HALF samples per wavefront block: the ramp-up / ramp-down of a block costs NSEC - 1 diagonals of
+            // reduced parallelism, so the 8-section pair runs the whole 32-sample stage as one block (one CTA per
+            // SM, registers to spare); the 4-section cascades keep two blocks of 16 (two CTAs per SM, 128 registers)
+            constexpr int HALF = NSEC >= 8 ? kTSub : kTSub / 2;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {       // two halves of 16 samples keep the live registers down
-                float4 xin[4];
+            for (int h = 0; h < kTSub / HALF; ++h) {
+                float xs[HALF], ys[HALF];
 #pragma unroll
-                for (int v = 0; v < 4; ++v) {
-                    const int p = 4 * h + v;
+                for (int v = 0; v < HALF / 4; ++v) {
+                    const int p = (HALF / 4) * h + v;
+                    float4 q;
                     if (!REV) {
-                        xin[v] = *reinterpret_cast<const float4*>(mine + 4 * (p ^ swz));
+                        q = *reinterpret_cast<const float4*>(mine + 4 * (p ^ swz));
                     } else {
                         const float4 t4 = *reinterpret_cast<const float4*>(mine + 4 * ((kTSub / 4 - 1 - p) ^ swz));
-                        xin[v] = make_float4(t4.w, t4.z, t4.y, t4.x);
+                        q = make_float4(t4.w, t4.z, t4.y, t4.x);
                     }
+                    xs[4 * v] = q.x; xs[4 * v + 1] = q.y; xs[4 * v + 2] = q.z; xs[4 * v + 3] = q.w;
                 }
-                float xs[16], ys[16];
-#pragma unroll
-                for (int v = 0; v < 4; ++v) { xs[4 * v] = xin[v].x; xs[4 * v + 1] = xin[v].y; xs[4 * v + 2] = xin[v].z; xs[4 * v + 3] = xin[v].w; }
                 if (early) {
-                    sos_block<NSEC, (NSEC / 2 > 0 ? NSEC / 2 : 1), NUM, NUMB, 16, (NUM >> 1) != 0, false>(xs, ys, gain, c, s);
+                    sos_block<NSEC, (NSEC / 2 > 0 ? NSEC / 2 : 1), NUM, NUMB, HALF, (NUM >> 1) != 0, false>(xs, ys, gain, c, s);
                 } else {
-                    sos_block<NSEC, NSEC, NUM, NUMB, 16, (NUM >> 1) != 0, true>(xs, ys, gain, c, s);
+                    sos_block<NSEC, NSEC, NUM, NUMB, HALF, (NUM >> 1) != 0, true>(xs, ys, gain, c, s);
                     if (write) {
 #pragma unroll
-                        for (int v = 0; v < 4; ++v) {
-                            const int p = 4 * h + v;
+                        for (int v = 0; v < HALF / 4; ++v) {
+                            const int p = (HALF / 4) * h + v;
                             if (!REV) *reinterpret_cast<float4*>(mine + 4 * (p ^ swz)) = make_float4(ys[4 * v], ys[4 * v + 1], ys[4 * v + 2], ys[4 * v + 3]);
                             else *reinterpret_cast<float4*>(mine + 4 * ((kTSub / 4 - 1 - p) ^ swz)) = make_float4(ys[4 * v + 3], ys[4 * v + 2], ys[4 * v + 1], ys[4 * v]);
                         }
@@ -249,7 +252,8 @@ static int launch_tma(const float* in, float* out, int64_t C, int64_t T, const e
     const unsigned grid = (unsigned)ceil_div(C * nChunks, kTNT);
     sos_warm_tma_kernel<NSEC, REV, NUM, NUMB><<<grid, kTNT, smem, st>>>(in_map, out_map, in, C, T, p.chunk, p.tail, nChunks,
                                                                         p.padlen, p.zero_phase, coef, padbuf, gain, p.tail_b);
-    return check_launch(REV ? "sos_warm_tma_bwd" : "sos_warm_tma_fwd");
+    return check_launch(NUMB >= 0 ? (REV ? "sos_warm_tma_pair_bwd" : "sos_warm_tma_pair_fwd")
+                                  : (REV ? "sos_warm_tma_bwd" : "sos_warm_tma_fwd"));
 }
 
 // Zero-phase sweeps through TMA tiles.  Requirements (checked by the caller): contiguous rows

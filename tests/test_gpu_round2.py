@@ -60,7 +60,7 @@ def test_full6_full_length_default_plans_vs_oracle(C, T, fs):
     x = synth.device_session(C, T, fs, seed=11)
     (y, f), kernels = _launched(lambda: preprocess_signal(x, FULL6_STEPS, Namespace(signal_freq=fs)))
     names = " ".join(kernels)
-    assert "sos_warm_pair_fwd" in kernels and "sos_warm_pair_bwd" in kernels, names     # the fused pair, not a fallback
+    assert "sos_warm_tma_pair_fwd" in kernels and "sos_warm_tma_pair_bwd" in kernels, names   # the fused pair (TMA tiles), not a fallback
     assert "fir_decimate" in kernels, names                  # two-stage resampler
     assert "hilbert_env8" in kernels and "car_colsum" in kernels and "car_fused" not in kernels, names
     rows = [0, C // 2 + 1, C - 1]
@@ -108,7 +108,7 @@ def test_full6_three_channels_full_length_direct():
 
 
 @pytest.mark.parametrize("fs,T", [(2000, 4_400_000), (3000, 7_000_000)])
-def test_cascade_pair_equals_sequential_and_oracle(fs, T):
+def test_cascade_pair_equals_sequential_and_oracle(fs, T, monkeypatch):
     """ops.sosfilt_pair = band-pass(filtfilt) o notch(filtfilt): against the two sequential device
     filtfilts on every row (interior AND the recomputed row ends) and against scipy on two rows."""
     from oracle import steps as OS
@@ -119,9 +119,10 @@ def test_cascade_pair_equals_sequential_and_oracle(fs, T):
     A = D.butter_design([58, 62], fs, 4, False, "bandstop")
     B = D.butter_design([70, 150], fs, 4, False, "bandpass")
     assert ops.pair_plan(C, T, True, A, B) is not None
+    monkeypatch.setenv("ECOG_SOS_TMA", "0")                         # the cp.async ring kernels
     y, kernels = _launched(lambda: ops.sosfilt_pair(x, A, B))
     assert "sos_warm_pair_fwd" in kernels and "sos_warm_pair_bwd" in kernels, kernels
-    seq = ops.sosfilt(ops.sosfilt(x, A), B)
+    seq = ops.sosfilt(ops.sosfilt(x, A, mode="warm"), B, mode="warm")
     scale = seq.abs().amax(dim=1)
     err = ((y - seq).abs().amax(dim=1) / scale).max().item()
     V = ops.pair_plan(C, T, True, A, B)[2]
@@ -283,6 +284,7 @@ def test_tma_sweeps_equal_cp_async_sweeps(monkeypatch):
     from decode_tonal_langauge_b200 import ops, synth
     fs, C, T = 2000, 128, 2_400_000
     x = synth.device_session(C, T, fs, seed=3)
+    monkeypatch.setenv("ECOG_SOS_TMA", "0")
 
     def rel(a, b):
         return ((a - b).abs().amax(dim=1) / b.abs().amax(dim=1)).max().item()
@@ -297,15 +299,22 @@ def test_tma_sweeps_equal_cp_async_sweeps(monkeypatch):
         assert e < 1e-6
     A = D.butter_design([58, 62], fs, 4, False, "bandstop")
     B = D.butter_design([70, 150], fs, 4, False, "bandpass")
-    C2, T2 = 256, 4_800_000
-    x2 = synth.device_session(C2, T2, fs, seed=4)
-    ref = ops.sosfilt_pair(x2, A, B)
-    monkeypatch.setenv("ECOG_SOS_TMA", "1")
-    got, kernels = _launched(lambda: ops.sosfilt_pair(x2, A, B))
-    assert "sos_warm_tma_fwd" in kernels and "sos_warm_pair_fwd" not in kernels, kernels
-    e = rel(got, ref)
-    print(f"TMA pair vs cp.async pair: {e:.2e}")
-    assert e < 1e-6
+    # a channel chunk of the pipelined host path: 21 rows, the last CTA partly empty
+    d = D.butter_design([58, 62], fs, 4, False, "bandstop")
+    xs = x[:21]
+    got, kernels = _launched(lambda: ops.sosfilt(xs, d, mode="tma"))
+    assert "sos_warm_tma_fwd" in kernels and rel(got, ops.sosfilt(xs, d, mode="scan")) < 1e-6
+    for C2, T2 in ((256, 4_800_000), (96, 9_600_000)):
+        x2 = synth.device_session(C2, T2, fs, seed=4)
+        monkeypatch.setenv("ECOG_SOS_TMA", "0")
+        ref, k0 = _launched(lambda: ops.sosfilt_pair(x2, A, B))
+        monkeypatch.setenv("ECOG_SOS_TMA", "1")
+        got, kernels = _launched(lambda: ops.sosfilt_pair(x2, A, B))
+        assert "sos_warm_pair_fwd" in k0 and "sos_warm_tma_pair_fwd" in kernels and "sos_warm_pair_fwd" not in kernels, (k0, kernels)
+        e = rel(got, ref)
+        print(f"TMA pair vs cp.async pair ({C2} x {T2}): {e:.2e}")
+        assert e < 1e-6
+        del x2, ref, got
 
 
 def test_session_batch_runner_equals_one_by_one(tmp_path):
