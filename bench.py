@@ -585,6 +585,15 @@ def run_ours(args):
                "api": "preprocess_signal(numpy (C,T) float32, pinned) -> numpy float64 (the reference's dtype after its "
                       "first filtfilt); channel-chunked copies overlapped with the kernels",
                "out_dtype": out_dtype, "host_cpus": len(host_cpus) if host_cpus else None}
+        # where one end-to-end step spends its time (one extra, untimed call with the trace on)
+        rt.trace = []
+        barrier()
+        yh, _ = preprocess_signal(xin, FULL6_STEPS, Namespace(signal_freq=fs))
+        del yh
+        tr, rt.trace = rt.trace, None
+        ev0 = next(e for l, e, _ in tr if l == "start")
+        e2e["breakdown_ms"] = {l: {"device": (ev0.elapsed_time(e) if e is not None else None), "host": 1e3 * h}
+                               for l, e, h in tr if l != "start"}
         # the same call with the device's storage dtype handed back (half the return traffic; explicit option)
         sec32, dt32, _, d2h32 = e2e_run(xin, 2, output_dtype=np.float32)
         ceiling = host_copy_ceiling(torch, C * T * 4, out_shape, torch.float64, 12)

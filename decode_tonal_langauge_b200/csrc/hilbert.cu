@@ -411,16 +411,19 @@ __global__ void __launch_bounds__(kHT, 2)
 hilbert_env8_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t ldx, int64_t ldy,
                     const float* __restrict__ gain, int nb, BandShift shift, int halo,
                     const float2* __restrict__ tw, int64_t nBlocks, const float* __restrict__ colsum, float inv_count,
-                   int64_t blk_begin, int64_t blk_end) {
+                    int64_t blk_begin, int64_t blk_end, int chan_fast) {
     extern __shared__ __align__(16) float2 hsm[];
     float2* bufA = hsm;                                   // [4608] forward exchange buffer / inverse exchange
     float2* bufB = bufA + kXchg;                          // [4096 + 256] natural-order spectrum / output staging
     float2* SG = bufB + (kN + kN / 16);                   // [2][kFastBands][16 n0][18] gained band spectra (conjugated)
     float2* twBs = SG + 2 * kFastBands * kSgBand;         // [16 k1][18] W_256^{n0 k1}
     const int tid = threadIdx.x;
-    const int64_t ch = blockIdx.y;
+    // chan_fast: consecutive CTAs are the SAME time blocks of consecutive channels, so the CAR column sums
+    // of a time block are fetched from DRAM once and then hit in L2 for every other channel
+    const int64_t ch = chan_fast ? blockIdx.x : blockIdx.y;
+    const int64_t bpair = chan_fast ? blockIdx.y : blockIdx.x;
     const int U = kN - 2 * halo;
-    const int64_t b0 = blk_begin + 2 * (int64_t)blockIdx.x, b1 = b0 + 1;
+    const int64_t b0 = blk_begin + 2 * bpair, b1 = b0 + 1;
     const float* xr = x + ch * ldx;
     const float2* tw1 = tw;                               // [16][256]
     const float2* tw2 = tw + 16 * kHT;                    // [16][256]
@@ -631,12 +634,14 @@ extern "C" int ecog_hilbert_env_range(const float* d_x, float* d_y, int64_t C, i
     cudaStream_t st = (cudaStream_t)stream;
     if (rows == 1 && nbands <= kFastBands) {
         const size_t smem8 = kFastSmem;
+        const int chan_fast = d_colsum != nullptr && grid.x <= 65535 ? 1 : 0;
+        const dim3 grid8 = chan_fast ? dim3(grid.y, grid.x) : grid;
 #define ECOG_HILBERT8(ENVV, EDGEV)                                                                                  \
     do {                                                                                                            \
         ECOG_TRY((smem_attr<hilbert_env8_kernel<ENVV, EDGEV>>(smem8)));                                             \
-        hilbert_env8_kernel<ENVV, EDGEV><<<grid, kHT, smem8, st>>>(d_x, d_y, T, ldx, ldy, d_gain, nbands, sh, halo,  \
-                                                                   tw, nBlocks, d_colsum, (float)inv_count,         \
-                                                                   block_begin, block_end);                         \
+        hilbert_env8_kernel<ENVV, EDGEV><<<grid8, kHT, smem8, st>>>(d_x, d_y, T, ldx, ldy, d_gain, nbands, sh, halo, \
+                                                                    tw, nBlocks, d_colsum, (float)inv_count,        \
+                                                                    block_begin, block_end, chan_fast);             \
     } while (0)
         const bool edge = halo < 256;
         if (envelope && edge) ECOG_HILBERT8(true, true);

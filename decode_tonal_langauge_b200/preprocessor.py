@@ -260,6 +260,17 @@ def _pipelined_host_run(data: np.ndarray, groups: List[tuple], block_params: Nam
     down.wait_stream(main)
     src = torch.from_numpy(data)
     pinned = src.is_pinned()
+    trace = rt.trace                       # optional: where a step's time goes (bench.py, e2e.breakdown)
+    import time as _time
+    t_host0 = _time.perf_counter()
+
+    def mark(label, stream):
+        if trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(stream)
+            trace.append((label, ev, _time.perf_counter() - t_host0))
+
+    mark("start", main)
     x0 = torch.empty((Cn, T), dtype=src.dtype, device=dev)
     arrived = []
     with torch.cuda.stream(up):
@@ -268,6 +279,7 @@ def _pipelined_host_run(data: np.ndarray, groups: List[tuple], block_params: Nam
             ev = torch.cuda.Event()
             ev.record(up)
             arrived.append(ev)
+    mark("h2d_done", up)
     rt.h2d_bytes += src.numel() * src.element_size()
     # head: per chunk, as soon as it has arrived
     params = block_params
@@ -307,6 +319,7 @@ def _pipelined_host_run(data: np.ndarray, groups: List[tuple], block_params: Nam
         else:
             x1, params = _run_segment(x1, middle, params)
         chunk_mid = lambda i: x1[chunks[i][0]:chunks[i][1]]
+        mark("head_and_middle_done", main)
     else:
         chunk_mid = chunk_in              # no CAR: the whole list runs per chunk, both copies overlap it
     # tail: per chunk, result cast on the device and sent back while the next chunk is computed
@@ -323,14 +336,19 @@ def _pipelined_host_run(data: np.ndarray, groups: List[tuple], block_params: Nam
         yc = yc.to(td) if yc.dtype != td else yc
         if out is None:
             out = torch.empty((Cn, yc.shape[1]), dtype=td, pin_memory=True)
+            mark("result_buffer_ready", main)
         ev = torch.cuda.Event()
         ev.record(main)
         down.wait_event(ev)
         with torch.cuda.stream(down):
             out[a:b].copy_(yc, non_blocking=True)
         keep.append(yc)
+    mark("tail_done", main)
+    mark("d2h_done", down)
     down.synchronize()
     main.synchronize()
+    if trace is not None:
+        trace.append(("host_return", None, _time.perf_counter() - t_host0))
     rt.d2h_bytes += out.numel() * out.element_size()
     for k, v in vars(final).items():          # the shared Namespace the caller handed in sees every step's keys
         setattr(block_params, k, v)

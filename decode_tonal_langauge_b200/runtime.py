@@ -14,6 +14,11 @@ h2d_bytes = 0
 d2h_bytes = 0
 
 
+# optional trace of the pipelined host path: a list that receives (label, CUDA event or None, host seconds
+# since the call started) tuples; None = off
+trace = None
+
+
 def reset_counters() -> None:
     global h2d_bytes, d2h_bytes
     h2d_bytes = 0
