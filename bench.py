@@ -50,7 +50,8 @@ STEP_BYTES_PER_SAMPLE = {
 }
 HILBERT_KEYS = ("car_rereference+frequency_filter[hilbert]", "frequency_filter[hilbert]")
 KERNEL_SOURCES = {"hilbert_env8_kernel": "decode_tonal_langauge_b200/csrc/hilbert.cu",
-                  "sos_warm_kernel": "decode_tonal_langauge_b200/csrc/sos_common.cuh"}
+                  "sos_warm_kernel": "decode_tonal_langauge_b200/csrc/sos_common.cuh",
+                  "sos_warm_tma_kernel": "decode_tonal_langauge_b200/csrc/sosfilt_tma.cu"}
 
 
 def source_sha(rel: str) -> str:
@@ -343,11 +344,11 @@ def run_sharded_record(args, torch, dist, world, rank, local, workload="C4"):
         return out, float(t[0].item()), float(t[1].item()), len(ar_ev) // steps, _mean_ms([grp_ev])
 
     l0 = nat.launch_count()
-    y, ms_ov, ar_ov, n_ar, step_ms = timed(True)           # all-reduce by time-tile groups on a side stream
+    y, ms_seq, ar_seq, _, step_ms = timed(False)           # default: one all-reduce of the whole vector on the compute stream
     launches = nat.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    _, ms_seq, ar_seq, _, step_ms_seq = timed(False)       # one all-reduce of the whole vector on the compute stream
-    ms = torch.tensor([ms_ov], dtype=torch.float64, device="cuda")
+    _, ms_ov, ar_ov, n_ar, step_ms_ov = timed(True)        # option: all-reduce by time-tile groups on a side stream
+    ms = torch.tensor([ms_seq], dtype=torch.float64, device="cuda")
     ar = torch.tensor([ar_seq], dtype=torch.float64, device="cuda")
     # parity: three local rows of rank 0 against the oracle, with the GLOBAL column mean (float64, all-reduced)
     col = x.sum(dim=0, dtype=torch.float64)
@@ -370,14 +371,13 @@ def run_sharded_record(args, torch, dist, world, rank, local, workload="C4"):
             "value": C * T / (float(ms.item()) * 1e-3), "unit": "channel-samples/s",
             "allreduce": {"ms": float(ar.item()), "bytes": 4 * T, "share_of_step": float(ar.item()) / ms_seq,
                           "what": "dist.all_reduce(SUM) of the T float32 CAR column sums as ONE collective on the compute "
-                                  "stream (overlap off), CUDA events around the call, max over ranks; it sits between "
+                                  "stream (the default), CUDA events around the call, max over ranks; it sits between "
                                   "ecog_car_colsum and the Hilbert kernel that subtracts the mean in its load",
-                          "ms_per_step_sequential": ms_seq,
                           "overlapped": {"ms_per_step": ms_ov, "collectives_per_step": n_ar, "sum_ms": ar_ov,
-                                         "what": "default: column sums, all-reduce and Hilbert blocks by time-tile groups, "
-                                                 "the collectives on a side stream (distributed.OVERLAP_GROUPS); "
-                                                 "sum_ms = time the side stream spent in the collectives"}},
-            "step_ms": step_ms, "step_ms_sequential": step_ms_seq, "gpu_launches": int(launches), "clocks": clocks,
+                                         "what": "option ECOG_OVERLAP_ALLREDUCE=1: column sums, all-reduce and Hilbert blocks by "
+                                                 "time-tile groups, the collectives on a side stream (distributed.OVERLAP_GROUPS); "
+                                                 "sum_ms = time the side stream spent in the collectives (waiting for peers included)"}},
+            "step_ms": step_ms, "step_ms_overlapped": step_ms_ov, "gpu_launches": int(launches), "clocks": clocks,
             "parity": parity}
 
 
@@ -646,6 +646,12 @@ def run_ours(args):
                        "floor_ms_at_4_ipc": rec["warp_inst_per_channel_sample"] * C * T / (4.0 * 148 * clocks["sm_mhz"] * 1e6) * 1e3,
                        "peak_source": rec.get("mix_ceiling_source", "4 schedulers x 1 warp instruction per clock"),
                        "source": rec["source"]}
+        pair_key = "frequency_filter[butter_bandstop]+frequency_filter[butter_bandpass]"
+        rec_pair = ncu_record("sos_warm_tma_kernel")
+        if pair_key in step_roofline and rec_pair and not rec_pair.get("stale"):
+            # one sweep of the pair per capture entry; the group runs two (forward, backward)
+            step_roofline[pair_key]["traffic_gb"] = 2 * rec_pair["dram_bytes_per_channel_sample"] * C * T / 1e9
+            step_roofline[pair_key]["traffic_source"] = rec_pair["source"]
         line = {
             "metric": "channel_samples_per_sec", "value": value, "unit": "channel-samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,

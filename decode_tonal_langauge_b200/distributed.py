@@ -109,7 +109,10 @@ def preprocess_signal_sharded(x_local, steps: List[dict], block_params: Namespac
     x = x_local
     bands = 1
     if overlap_allreduce is None:
-        overlap_allreduce = os.environ.get("ECOG_OVERLAP_ALLREDUCE", "1") != "0"
+        # measured (profiles/r02_bench_n{2,4,8}.json, C4): the 43 MB collective takes 0.2-0.4 ms as one call;
+        # split into 8 time-tile groups on a side stream it is hidden, but the 8 partial launches and stream
+        # hops cost more than that at N >= 4 (67.2 vs 65.2 ms at N = 4, 35.2 vs 34.3 ms at N = 8; -0.1 ms at N = 2)
+        overlap_allreduce = os.environ.get("ECOG_OVERLAP_ALLREDUCE", "0") == "1"
     plain = backend is not None            # the CPU test-suite's numpy backend has no fused kernels
     groups = P.fusion_groups(steps) if (P.fusion_enabled(fuse) and not plain) else [("step", s) for s in steps]
 

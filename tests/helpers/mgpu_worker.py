@@ -34,6 +34,9 @@ def main():
     xl = torch.from_numpy(x[lo:hi].copy()).cuda()
     yl, f, bands = D.preprocess_signal_sharded(xl, steps, Namespace(signal_freq=fs), lo, C)
     full = D.gather_channels(yl, C, bands)
+    # the optional overlapped form: column sums / all-reduce / Hilbert blocks by time-tile groups on a side stream
+    yo, fo, _ = D.preprocess_signal_sharded(xl, steps, Namespace(signal_freq=fs), lo, C, overlap_allreduce=True)
+    same = float(((yo - yl).abs().amax(dim=1) / yl.abs().amax(dim=1)).max())
     runs = (torch.arange(lo, hi, device="cuda", dtype=torch.int32) * 7) % 50
     sel = D.gather_selection(runs, lo, C, 40)
     ok = True
@@ -41,8 +44,10 @@ def main():
         ref, f0 = preprocess_signal(torch.from_numpy(x).cuda(), steps, Namespace(signal_freq=fs))
         err = float(((full - ref).abs().amax(dim=1) / ref.abs().amax(dim=1)).max())
         want = [int(c) for c in np.nonzero((np.arange(C) * 7) % 50 > 40)[0]]
-        ok = f == f0 == 400 and full.shape == ref.shape and err < 5e-6 and sel == want
-        print(f"mgpu world={world} err={err:.2e} sel_ok={sel == want} ok={ok}", flush=True)
+        ok = f == f0 == fo == 400 and full.shape == ref.shape and err < 5e-6 and sel == want and same < 1e-6
+        print(f"mgpu world={world} err={err:.2e} overlapped_vs_single={same:.2e} sel_ok={sel == want} ok={ok}", flush=True)
+    if same >= 1e-6:
+        ok = False
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
