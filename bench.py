@@ -644,6 +644,8 @@ def run_ours(args):
                        "peak": rec.get("mix_ceiling_ipc", 4.0), "frac": ipc / rec.get("mix_ceiling_ipc", 4.0),
                        "frac_of_4_ipc": ipc / 4.0, "thread_inst_per_sample": 32 * rec["warp_inst_per_channel_sample"],
                        "floor_ms_at_4_ipc": rec["warp_inst_per_channel_sample"] * C * T / (4.0 * 148 * clocks["sm_mhz"] * 1e6) * 1e3,
+                       "time_ms": hil_ms, "time_note": "live CUDA-event time of the CAR + Hilbert group (the 1.0 ms column-sum "
+                                                        "pass is inside it, so the kernel's own rate is ~4 % higher)",
                        "peak_source": rec.get("mix_ceiling_source", "4 schedulers x 1 warp instruction per clock"),
                        "source": rec["source"]}
         pair_key = "frequency_filter[butter_bandstop]+frequency_filter[butter_bandpass]"

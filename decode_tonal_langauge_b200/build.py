@@ -10,9 +10,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libecog_sm100.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# no --use_fast_math: the kernels ask for approximate instructions explicitly where they are allowed
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "--use_fast_math=false", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
-FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]
+         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
 def sources():
