@@ -63,6 +63,8 @@ def workspace(nbytes: int, device, tag: str = "default") -> torch.Tensor:
     key = (str(device), tag)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < nbytes:
+        if buf is not None:
+            torch.cuda.synchronize(device)      # rare: the old buffer may still be in use on another stream
         buf = None
         _workspaces.pop(key, None)
         buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
@@ -231,7 +233,7 @@ def tma_chunk(Cn: int, T: int, tail: int, max_per_sm: int = 2) -> Optional[int]:
 
 
 def sosfilt(x: torch.Tensor, dsg: D.SosDesign, chunk: Optional[int] = None,
-            out: Optional[torch.Tensor] = None, mode: Optional[str] = None) -> torch.Tensor:
+            out: Optional[torch.Tensor] = None, mode: Optional[str] = None, ws_tag: str = "sos") -> torch.Tensor:
     """Biquad cascade, zero-phase (filtfilt semantics) or causal.  ``mode``: "warm" (one kernel
     per sweep, start states from a zero-state warm-up), "scan" (exact carry scan) or None =
     warm-up whenever the cascade forgets fast enough for the chunk length."""
@@ -277,10 +279,20 @@ def sosfilt(x: torch.Tensor, dsg: D.SosDesign, chunk: Optional[int] = None,
             tail = L
         plan = nat.SosPlan(dsg.nsec, 1 if dsg.zero_phase else 0, dsg.padlen, L, tail, nat.SOS_SCAN, 512)
     nbytes = lib.ecog_sos_workspace(C.byref(plan), Cn, T)
-    ws = workspace(nbytes, x.device, "sos")
+    ws = workspace(nbytes, x.device, ws_tag)
     nat.check(lib.ecog_sosfilt(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), C.byref(plan), _hptr(sos), _hptr(zi),
                                _hptr(Mh), _ptr(ws), ws.numel(), _stream()))
     return y
+
+
+_side_streams = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = str(device)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    return _side_streams[key]
 
 
 def copy2d(dst: torch.Tensor, src: torch.Tensor) -> None:
@@ -349,18 +361,29 @@ def sosfilt_pair(x: torch.Tensor, A: D.SosDesign, B: D.SosDesign, out: Optional[
             plan = nat.SosPlan(8, 1, dsg.padlen, L, tail32, nat.SOS_WARMUP_TMA, 256, 4, -(-min(plan.tail_b, V) // 32) * 32)
     if T <= dsg.padlen:
         raise ValueError(f"The length of the input vector x must be greater than padlen, which is {dsg.padlen}.")
-    # exact edges first (they only read x): rows 0..C-1 = left segments, C..2C-1 = right segments
+    # exact edges (they only read x): rows 0..C-1 = left segments, C..2C-1 = right segments.  Twelve small
+    # launches on a side stream: they run beside the sweeps (whose grid leaves SMs free) instead of before them.
     E = 2 * V
-    xe = torch.empty((2 * Cn, E), dtype=torch.float32, device=x.device)
-    copy2d(xe[:Cn], x[:, :E])
-    copy2d(xe[Cn:], x[:, T - E:])
-    ye = sosfilt(sosfilt(xe, A, chunk=PAIR_EDGE_CHUNK, mode="scan"), B, chunk=PAIR_EDGE_CHUNK, mode="scan")
+    main = torch.cuda.current_stream()
+    side = _side_stream(x.device)
+    side.wait_stream(main)
+    # the three edge buffers live in a persistent workspace (no allocator traffic across the two streams);
+    # side.wait_stream(main) above also orders this call's writes behind the previous call's scatter
+    nbuf = 2 * Cn * E
+    ebuf = workspace(3 * nbuf * 4, x.device, "pair_edges")[:3 * nbuf * 4].view(torch.float32)
+    xe, ze, ye = (ebuf[i * nbuf:(i + 1) * nbuf].view(2 * Cn, E) for i in range(3))
+    with torch.cuda.stream(side):
+        copy2d(xe[:Cn], x[:, :E])
+        copy2d(xe[Cn:], x[:, T - E:])
+        sosfilt(xe, A, chunk=PAIR_EDGE_CHUNK, mode="scan", ws_tag="sos_edge", out=ze)
+        sosfilt(ze, B, chunk=PAIR_EDGE_CHUNK, mode="scan", ws_tag="sos_edge", out=ye)
     sos = np.ascontiguousarray(dsg.sos, dtype=np.float64)
     zi = np.ascontiguousarray(dsg.zi, dtype=np.float64)
     nbytes = lib.ecog_sos_workspace(C.byref(plan), Cn, T)
     ws = workspace(nbytes, x.device, "sos")
     nat.check(lib.ecog_sosfilt(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), C.byref(plan), _hptr(sos), _hptr(zi),
                                _hptr(None), _ptr(ws), ws.numel(), _stream()))
+    main.wait_stream(side)
     copy2d(y[:, :V], ye[:Cn, :V])
     copy2d(y[:, T - V:], ye[Cn:, E - V:])
     return y
