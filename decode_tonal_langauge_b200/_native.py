@@ -16,11 +16,12 @@ ECOG_E_VALUE = -1
 ECOG_E_CUDA = -2
 ECOG_E_WORKSPACE = -3
 ECOG_E_UNSUPPORTED = -4
-ABI_VERSION = 6
+ABI_VERSION = 7
 MAX_SECTIONS = 8
 SOS_SCAN = 0
 SOS_WARMUP = 1
 SOS_WARMUP_TMA = 2
+SOS_SPLIT_F32B = 0x100
 HILBERT_N = 4096
 
 

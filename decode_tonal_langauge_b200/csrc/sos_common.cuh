@@ -30,7 +30,7 @@ struct SosMatrix { double m[2 * ECOG_MAX_SECTIONS][2 * ECOG_MAX_SECTIONS]; };
 //                                                         3, and one multiply per sample
 //   8  monic general numerator 1 + b1 z^-1 + b2 z^-2 in DIRECT FORM II (the exact factors of a rounded
 //      Butterworth numerator whose zeros are NOT on the unit circle; gain on the input):
-//        w = u - a1 w1 - a2 w2;  y = w + b1 w1 + b2 w2              4, and one multiply per sample
+//        w = u - a1 w1 - a2 w2;  y = w + b1 w1 + b2 w2 = u + (b1 - a1) w1 + (b2 - a2) w2      4, and one multiply per sample
 //      (the transposed form needs 5: its b2 u product has no partner).  In float64 the direct form is as
 //      accurate as the transposed one for these sections (both 1.5e-7 from the long-double evaluation of
 //      the 58-62 Hz notch at 3 kHz); its states (w1, w2) are related to the transposed ones by
@@ -43,8 +43,11 @@ __device__ __forceinline__ double sos_range(double u, const double (&c)[NSEC][5]
     if (NUM == 8) {
 #pragma unroll
         for (int j = J0; j < J1; ++j) {
-            const double w = fma(-c[j][4], s[j][1], fma(-c[j][3], s[j][0], u));
-            u = fma(c[j][2], s[j][1], fma(c[j][1], s[j][0], w));
+            // the newest state w1 enters LAST (one dependent DFMA, ~15 cycles, per sample on the recurrence), and
+            // the output is formed beside it, not after it:  y = w + b1 w1 + b2 w2 = u + (b1 - a1) w1 + (b2 - a2) w2
+            // (prepare_form stores the differences in c[j][1], c[j][2])
+            const double w = fma(-c[j][3], s[j][0], fma(-c[j][4], s[j][1], u));
+            u = fma(c[j][1], s[j][0], fma(c[j][2], s[j][1], u));
             s[j][1] = s[j][0];
             s[j][0] = w;
         }
@@ -114,6 +117,20 @@ __device__ __forceinline__ void sos_block(const float (&x)[N], float (&y)[N], do
         if (STORE && d >= NS - 1) y[d - (NS - 1)] = (float)pipe[NS];
     }
 }
+
+// ------------------------------------------------------------------ float32 band-pass half of a cascade pair
+// The second half of a pair (four (1 - z^-2) sections of a Butterworth band-pass, poles well inside the unit
+// circle) in FLOAT32, in delta form: with a1 = e1 - 2, a2 = 1 - e2 the direct-form-II recursion
+//     w[n] = v - a1 w[n-1] - a2 w[n-2],   y = w[n] - w[n-2]
+// is carried in the states w1 = w[n-1] and d = w[n-1] - w[n-2]:
+//     dn = d + (v + (e2 - e1) w1 - e2 d),   y = dn + d,   w1 += dn,   d = dn          (2 FFMA + 3 FADD)
+// The small coefficients c1 = e2 - e1 = -(1 + a1 + a2) and e2 = 1 - a2 are rounded to float32 with an absolute
+// error ~1e-9 instead of the 6e-8 of a1 ~ -1.9, and the recursion adds small increments to the state instead
+// of cancelling large products: measured against the all-float64 pair 3.5e-7 (2 kHz) / 4.5e-7 (3 kHz) of the
+// row maximum for the 70-150 Hz band, where plain float32 direct forms give 2.5e-6 ... 5e-6.
+// It takes 12 of the pair's 29 FP64 operations per sample off the FP64 pipe that bounds the sweeps
+// (csrc/sosfilt_pairws.cu runs the recursion, two sections per packed float32 pair).
+struct Bp32Coef { float c1[4], e2[4]; };
 
 // WRITE=false: tail pass (zero state, last `tail` samples, end state -> slot k+1)
 // WRITE=true : main pass (state from slot k, float32 output)
@@ -373,6 +390,9 @@ inline double prepare_form(SosCoef& coef, int j0, int j1, int lead, int form) {
                 coef.zi[j][0] = (m11 * s0 - m01 * s1) / det;
                 coef.zi[j][1] = (m00 * s1 - m10 * s0) / det;
             }
+            // the kernel forms the output as u + (b1 - a1) w1 + (b2 - a2) w2 (sos_range, NUM == 8)
+            coef.c[j][1] = b1 - a1;
+            coef.c[j][2] = b2 - a2;
         }
     }
     return gain;
@@ -381,6 +401,10 @@ inline double prepare_form(SosCoef& coef, int j0, int j1, int lead, int form) {
 // defined in sosfilt_tma.cu
 int run_sos_warm_tma(const float* x, float* y, int64_t C, int64_t T, const ecog_sos_plan& p, const SosCoef& coef_in,
                      float* tmp, double* padbuf, cudaStream_t st);
+
+// defined in sosfilt_pairws.cu
+int run_sos_pair_ws(const float* x, float* y, int64_t C, int64_t T, const ecog_sos_plan& p, const SosCoef& coef_in,
+                    float* tmp, cudaStream_t st);
 
 // defined in sosfilt_pair.cu
 int run_sos_warm_pair(const float* x, float* y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,

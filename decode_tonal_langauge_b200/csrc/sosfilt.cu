@@ -461,7 +461,7 @@ extern "C" int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, 
     if (p.mode == ECOG_SOS_WARMUP_TMA) {
         double* padbuf = (double*)d_workspace;
         const size_t pad = align_up((size_t)C * (p.padlen > 0 ? p.padlen : 1) * sizeof(double), 256);
-        if (p.split && (p.split != 4 || p.nsec != 8 || p.tail_b < 0 || p.tail_b % 32 || p.tail_b > p.tail))
+        if (p.split && ((p.split & ~ECOG_SOS_SPLIT_F32B) != 4 || p.nsec != 8 || p.tail_b < 0 || p.tail_b % 32 || p.tail_b > p.tail))
             return fail(ECOG_E_VALUE, "ecog_sosfilt (TMA): cascade pair needs nsec=8, split=4, tail_b a multiple of 32 <= tail");
         return run_sos_warm_tma(d_x, d_y, C, T, p, coef, (float*)((char*)d_workspace + pad), padbuf, st);
     }
@@ -472,7 +472,8 @@ extern "C" int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, 
         const int64_t ldt = warm_ld(T);
         if (p.split) {
             if (p.split != 4 || p.nsec != 8 || p.tail_b < 0 || p.tail_b % kSub || p.tail_b > p.tail)
-                return fail(ECOG_E_VALUE, "ecog_sosfilt: cascade pair needs nsec=8, split=4, 0 <= tail_b <= tail (multiples of %d)", kSub);
+                return fail(ECOG_E_VALUE, "ecog_sosfilt: cascade pair needs nsec=8, split=4 (the float32 half exists on the TMA path only), "
+                                          "0 <= tail_b <= tail (multiples of %d)", kSub);
             return run_sos_warm_pair(d_x, d_y, C, T, ldx, ldy, p, coef, tmp, ldt, padbuf, st);
         }
         switch (ns) {

@@ -20,6 +20,7 @@
 #include <cuda.h>
 
 #include "sos_common.cuh"
+#include "tma_common.cuh"
 
 namespace ecog {
 
@@ -27,41 +28,6 @@ constexpr int kTNT = 256;            // threads = chunks per CTA = box rows
 constexpr int kTSub = 32;            // samples per stage (128-byte box rows)
 constexpr int kTSlots = 3;
 constexpr int kTileBytes = kTNT * kTSub * 4;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        :: "r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* src) {
-    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
-                 :: "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(src)) : "memory");
-}
-__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
-template <int N>
-__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" :: "n"(N) : "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Thread q = blockIdx.x * 256 + tid owns MEMORY chunk q (row q / nChunks, chunk j = q % nChunks) in both
 // sweep directions; the backward sweep walks its chunk from the end and warms up on chunk q + 1.
@@ -97,6 +63,7 @@ sos_warm_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         for (int k = 0; k < 5; ++k) c[i][k] = coef.c[i][k];
         s[i][0] = 0.0; s[i][1] = 0.0;
     }
+    auto step = [&](double u) -> double { return sos_step<NSEC, NUM, NUMB>(u, c, s); };
 
     // box of stage st: forward  st >= 0: (32 st, q0)         st < 0: (L + 32 st, q0 - 1)
     //                  backward st >= 0: (L - 32 (st+1), q0)  st < 0: (-32 (st+1), q0 + 1)
@@ -140,14 +107,14 @@ sos_warm_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
                 for (int i = 0; i < NSEC; ++i) { s[i][0] = coef.zi[i][0] * (double)e0; s[i][1] = coef.zi[i][1] * (double)e0; }
                 for (int i = 0; i < padlen; ++i) {
                     const float e = 2.0f * x0 - xr[padlen - i];
-                    (void)sos_step<NSEC, NUM, NUMB>(IN((double)e), c, s);
+                    (void)step(IN((double)e));
                 }
             } else {
                 const double* pb = padbuf + row * padlen;
                 const double y0 = pb[padlen - 1];
 #pragma unroll
                 for (int i = 0; i < NSEC; ++i) { s[i][0] = coef.zi[i][0] * y0; s[i][1] = coef.zi[i][1] * y0; }
-                for (int i = padlen - 1; i >= 0; --i) (void)sos_step<NSEC, NUM, NUMB>(IN(pb[i]), c, s);
+                for (int i = padlen - 1; i >= 0; --i) (void)step(IN(pb[i]));
             }
         }
         const bool write = st >= 0;
@@ -211,34 +178,14 @@ sos_warm_tma_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_con
         double* pb = padbuf + row * padlen;
         for (int i = 0; i < padlen; ++i) {
             const float e = 2.0f * xe - xr[T - 2 - i];
-            pb[i] = sos_step<NSEC, NUM, NUMB>(IN((double)e), c, s);
+            pb[i] = step(IN((double)e));
         }
     }
 #undef IN
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
 static int make_map(CUtensorMap* map, const float* base, int64_t nq, int L) {
-    static EncodeTiledFn encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        ECOG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ECOG_E_CUDA, "cuTensorMapEncodeTiled is not available");
-        encode = reinterpret_cast<EncodeTiledFn>(fn);
-    }
-    const cuuint64_t dims[2] = {(cuuint64_t)L, (cuuint64_t)nq};
-    const cuuint64_t strides[1] = {(cuuint64_t)L * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)kTSub, (cuuint32_t)kTNT};
-    const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(ECOG_E_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
-    return ECOG_OK;
+    return make_chunk_map(map, base, nq, L, kTSub, kTNT);
 }
 
 template <int NSEC, bool REV, int NUM, int NUMB>
@@ -275,6 +222,8 @@ int run_sos_warm_tma(const float* x, float* y, int64_t C, int64_t T, const ecog_
             return fail(ECOG_E_UNSUPPORTED, "ecog_sosfilt (TMA): cascade pair forms (%d, %d) are not instantiated", na, nb);
         gain = prepare_form(coef, 0, 4, 0, na);
         (void)prepare_form(coef, 4, 8, -1, nb);
+        if (p.split & ECOG_SOS_SPLIT_F32B)
+            return run_sos_pair_ws(x, y, C, T, p, coef_in, tmp, st);       // notch threads (float64) + band-pass threads (float32)
         if (na == 2) ECOG_TMA2(8, 2, 5);
         ECOG_TMA2(8, 8, 5);
     }

@@ -386,6 +386,25 @@ def _pair_design(a_bytes: bytes, b_bytes: bytes, pad_a: int, pad_b: int):
     return dsg, int(2 * tb)
 
 
+# float32 second half of a cascade pair (csrc/sos_common.cuh: Bp32, ECOG_SOS_SPLIT_F32B): the delta-form
+# recursion's round-off grows like eps32 / (1 - a2); measured 0.35 * 6e-8 / min(1 - a2) of the row maximum
+# (3.5e-7 at 2 kHz, 4.5e-7 at 3 kHz for the 70-150 Hz band).  Below this bound the estimate stays <= ~1e-6.
+BANDPASS_F32_MIN_E2 = 0.03
+
+
+def bandpass_f32_ok(B: SosDesign) -> bool:
+    """True when the 4-section band-pass ``B`` may run in float32 delta form inside a cascade pair: sections
+    g (1 - z^-2) / (1 + a1 z^-1 + a2 z^-2) whose poles are far enough inside the unit circle."""
+    sos = np.asarray(B.sos, dtype=np.float64)
+    if sos.shape != (4, 6) or not np.all(sos[:, 3] == 1.0):
+        return False
+    if not (np.all(sos[:, 1] == 0.0) and np.all(sos[:, 2] == -sos[:, 0]) and np.all(sos[:, 0] != 0.0)):
+        return False
+    e2 = 1.0 - sos[:, 5]
+    c1 = -(1.0 + sos[:, 4] + sos[:, 5])
+    return bool(np.min(e2) >= BANDPASS_F32_MIN_E2 and np.all(c1 < 0.0))
+
+
 @functools.lru_cache(maxsize=256)
 def _chunk_ops(sos_bytes: bytes, nsec: int, chunk: int):
     sos = np.frombuffer(sos_bytes, dtype=np.float64).reshape(nsec, 6)

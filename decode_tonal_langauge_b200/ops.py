@@ -208,6 +208,10 @@ def _tma_enabled() -> bool:
     return os.environ.get("ECOG_SOS_TMA", "1") != "0"
 
 
+def _pair_f32_enabled() -> bool:
+    return os.environ.get("ECOG_PAIR_F32", "1") != "0"
+
+
 def tma_chunk(Cn: int, T: int, tail: int, max_per_sm: int = 2) -> Optional[int]:
     """Chunk length for the TMA sweeps (csrc/sosfilt_tma.cu): L divides T, L % 32 == 0, L >= tail.  The grid
     is ceil(Cn * T / L / 256) CTAs of 256 chunk-threads, two of which fit an SM; CTAs are dealt round robin,
@@ -358,7 +362,10 @@ def sosfilt_pair(x: torch.Tensor, A: D.SosDesign, B: D.SosDesign, out: Optional[
         tail32 = -(-V // 32) * 32
         L = tma_chunk(Cn, T, tail32, max_per_sm=1)       # the 8-section kernel keeps its coefficients in registers: one CTA per SM
         if L is not None and T // L > 1:
-            plan = nat.SosPlan(8, 1, dsg.padlen, L, tail32, nat.SOS_WARMUP_TMA, 256, 4, -(-min(plan.tail_b, V) // 32) * 32)
+            # band-pass second half in float32 delta form when its poles allow it (12 of 29 FP64 operations per
+            # sample leave the FP64 pipe; <= ~1e-6 of the row maximum, ECOG_PAIR_F32=0 keeps everything in float64)
+            split = 4 | (nat.SOS_SPLIT_F32B if _pair_f32_enabled() and D.bandpass_f32_ok(B) else 0)
+            plan = nat.SosPlan(8, 1, dsg.padlen, L, tail32, nat.SOS_WARMUP_TMA, 256, split, -(-min(plan.tail_b, V) // 32) * 32)
     if T <= dsg.padlen:
         raise ValueError(f"The length of the input vector x must be greater than padlen, which is {dsg.padlen}.")
     # exact edges (they only read x): rows 0..C-1 = left segments, C..2C-1 = right segments.  Twelve small

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define ECOG_ABI_VERSION 6
+#define ECOG_ABI_VERSION 7
 
 #define ECOG_OK 0
 #define ECOG_E_VALUE (-1)     /* bad argument (reference raises ValueError)          */
@@ -94,7 +94,7 @@ typedef struct {
     int32_t tail;        /* multiple of 16; <= chunk in scan mode                     */
     int32_t mode;        /* ECOG_SOS_SCAN (exact carry scan) or ECOG_SOS_WARMUP        */
     int32_t threads;     /* warm-up mode: threads per CTA, 256 or 512                 */
-    int32_t split;       /* 0, or 4: h_sos holds TWO 4-section unit-form cascades      */
+    int32_t split;       /* 0, or 4 (| ECOG_SOS_SPLIT_F32B): h_sos holds TWO 4-section unit-form cascades */
     int32_t tail_b;      /* split: warm-up samples of the second cascade (<= tail)     */
 } ecog_sos_plan;
 /* Cascade pair (split = 4, warm-up mode, zero phase, nsec = 8): two consecutive filtfilt steps
@@ -118,6 +118,14 @@ typedef struct {
  * contiguous rows (ldx == ldy == T), T == n * chunk, chunk / tail (/ tail_b) multiples of 32,
  * tail <= chunk; 4-section cascades and the (2,5) / (0,5) cascade pairs.                        */
 #define ECOG_SOS_WARMUP_TMA 2
+/* ECOG_SOS_SPLIT_F32B (or-ed into `split`, TMA mode only): the SECOND cascade of a pair -- four (1 - z^-2)
+ * band-pass sections -- runs in float32 delta form (states w[n-1] and w[n-1] - w[n-2], coefficients
+ * -(1 + a1 + a2) and 1 - a2 rounded to float32 from the float64 design) while the first (the notch, pole
+ * radius ~0.998) stays in float64: 12 of the pair's 29 FP64 operations per sample leave the FP64 pipe that
+ * bounds the sweeps.  The caller asks for it only when the band-pass poles are far enough inside the unit
+ * circle (min(1 - a2) >= 0.03: error <= ~1e-6 of the row maximum, measured 3.5e-7 / 4.5e-7 for 70-150 Hz at
+ * 2 / 3 kHz against the all-float64 pair; decode_tonal_langauge_b200/design.py::bandpass_f32_ok).       */
+#define ECOG_SOS_SPLIT_F32B 0x100
 #define ECOG_MAX_SECTIONS 8
 size_t ecog_sos_workspace(const ecog_sos_plan* plan, int64_t C, int64_t T);
 int ecog_sosfilt(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,

@@ -57,6 +57,7 @@ FN = {
     "pair256": lambda: _with_env("ECOG_PAIR_TPS", "256", FN["pair"]),
     "pair384": lambda: _with_env("ECOG_PAIR_TPS", "384", FN["pair"]),
     "pair512": lambda: _with_env("ECOG_PAIR_TPS", "512", FN["pair"]),
+    "pair_f64": lambda: _with_env("ECOG_PAIR_F32", "0", FN["pair"]),
     "colsum": lambda: ops.car_colsum(x),
     "hilbert_car": lambda: ops.hilbert(x, fs, [70.0, 150.0], car=(COLSUM, C)),
 }

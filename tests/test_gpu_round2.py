@@ -60,7 +60,7 @@ def test_full6_full_length_default_plans_vs_oracle(C, T, fs):
     x = synth.device_session(C, T, fs, seed=11)
     (y, f), kernels = _launched(lambda: preprocess_signal(x, FULL6_STEPS, Namespace(signal_freq=fs)))
     names = " ".join(kernels)
-    assert "sos_warm_tma_pair_fwd" in kernels and "sos_warm_tma_pair_bwd" in kernels, names   # the fused pair (TMA tiles), not a fallback
+    assert "sos_pair_ws_fwd" in kernels and "sos_pair_ws_bwd" in kernels, names   # the fused pair (TMA tiles, notch and band-pass threads), not a fallback
     assert "fir_decimate" in kernels, names                  # two-stage resampler
     assert "hilbert_env8" in kernels and "car_colsum" in kernels and "car_fused" not in kernels, names
     rows = [0, C // 2 + 1, C - 1]
@@ -309,12 +309,42 @@ def test_tma_sweeps_equal_cp_async_sweeps(monkeypatch):
         monkeypatch.setenv("ECOG_SOS_TMA", "0")
         ref, k0 = _launched(lambda: ops.sosfilt_pair(x2, A, B))
         monkeypatch.setenv("ECOG_SOS_TMA", "1")
+        monkeypatch.setenv("ECOG_PAIR_F32", "0")                    # all-float64 pair: the same arithmetic as the ring kernel
         got, kernels = _launched(lambda: ops.sosfilt_pair(x2, A, B))
         assert "sos_warm_pair_fwd" in k0 and "sos_warm_tma_pair_fwd" in kernels and "sos_warm_pair_fwd" not in kernels, (k0, kernels)
         e = rel(got, ref)
         print(f"TMA pair vs cp.async pair ({C2} x {T2}): {e:.2e}")
         assert e < 1e-6
+        monkeypatch.delenv("ECOG_PAIR_F32")
         del x2, ref, got
+
+
+@pytest.mark.parametrize("fs,C,T", [(2000, 256, 4_800_000), (3000, 128, 10_800_000)])
+def test_pair_float32_bandpass_half(fs, C, T, monkeypatch):
+    """ECOG_SOS_SPLIT_F32B (the default of the TMA pair when design.bandpass_f32_ok): band-pass sections in
+    float32 delta form against the all-float64 pair on every row, and against the long-double truth on two rows.
+    CPU emulation of the same recursion: 3.5e-7 (2 kHz) / 4.5e-7 (3 kHz)."""
+    from oracle import steps as OS
+    from decode_tonal_langauge_b200 import design as D
+    from decode_tonal_langauge_b200 import ops, synth
+    x = synth.device_session(C, T, fs, seed=9)
+    A = D.butter_design([58, 62], fs, 4, False, "bandstop")
+    B = D.butter_design([70, 150], fs, 4, False, "bandpass")
+    assert D.bandpass_f32_ok(B) and not D.bandpass_f32_ok(A)
+    assert not D.bandpass_f32_ok(D.butter_design([70, 150], 6000, 4, False, "bandpass"))      # poles too close to the circle
+    monkeypatch.setenv("ECOG_PAIR_F32", "0")
+    y64, k64 = _launched(lambda: ops.sosfilt_pair(x, A, B))
+    monkeypatch.setenv("ECOG_PAIR_F32", "1")
+    y32, k32 = _launched(lambda: ops.sosfilt_pair(x, A, B))
+    assert "sos_warm_tma_pair_fwd" in k64 and "sos_pair_ws_fwd" in k32 and "sos_pair_ws_bwd" in k32, (k64, k32)
+    e = ((y32 - y64).abs().amax(dim=1) / y64.abs().amax(dim=1)).max().item()
+    rows = [0, C - 1]
+    xin = x[rows].cpu().numpy()
+    n_ld = np.asarray(OS.filtfilt_pad(A.b, A.a, xin, dtype=np.longdouble, reference_edges=True), dtype=np.float64)
+    truth = OS.filtfilt_pad(B.b, B.a, n_ld)
+    e32, e64 = max_rel(y32[rows].cpu().numpy(), truth), max_rel(y64[rows].cpu().numpy(), truth)
+    print(f"pair @ {fs} Hz: float32 band-pass half vs float64 pair {e:.2e}; vs long-double truth {e32:.2e} (float64 pair {e64:.2e})")
+    assert e < 1.5e-6 and e32 < 1.5e-6
 
 
 def test_session_batch_runner_equals_one_by_one(tmp_path):

@@ -290,3 +290,41 @@ def test_bind_host_to_gpu_is_best_effort():
     got = rt.bind_host_to_gpu(0)
     assert got is None or set(got) <= before
     assert os.sched_getaffinity(0) == (set(got) if got else before)
+
+
+def test_bandpass_delta_form_is_the_same_filter():
+    """The float32 half of the cascade pair (csrc/sos_common.cuh: Bp32) carries w[n-1] and w[n-1] - w[n-2]
+    with the coefficients c1 = -(1 + a1 + a2), e2 = 1 - a2.  In float64 the recursion must reproduce
+    scipy's sosfilt of the same band-pass; in float32 it must stay within the bound design.bandpass_f32_ok
+    promises (<= ~1e-6 of the row maximum)."""
+    from scipy import signal as S
+    from decode_tonal_langauge_b200 import design as D
+    fs = 2000.0
+    B = D.butter_design([70, 150], fs, 4, False, "bandpass")
+    assert D.bandpass_f32_ok(B)
+    assert not D.bandpass_f32_ok(D.butter_design([58, 62], fs, 4, False, "bandstop"))
+    assert not D.bandpass_f32_ok(D.butter_design([70, 150], 6000.0, 4, False, "bandpass"))
+    sos = np.asarray(B.sos, dtype=np.float64)
+    x = np.random.default_rng(3).standard_normal(6000) * 30.0
+    ref = S.sosfilt(sos, x)
+
+    def delta(dtype):
+        c1 = (-(1.0 + sos[:, 4] + sos[:, 5])).astype(dtype)
+        e2 = (1.0 - sos[:, 5]).astype(dtype)
+        g = dtype(np.prod(sos[:, 0]))
+        w1 = np.zeros(4, dtype=dtype)
+        d = np.zeros(4, dtype=dtype)
+        y = np.empty(x.size, dtype=dtype)
+        for n in range(x.size):
+            v = dtype(x[n]) * g
+            for j in range(4):
+                dn = dtype(c1[j] * w1[j] + (v - e2[j] * d[j])) + d[j]
+                v = dn + d[j]
+                w1[j] = w1[j] + dn
+                d[j] = dn
+            y[n] = v
+        return y.astype(np.float64)
+
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(delta(np.float64) - ref)) / scale < 1e-12
+    assert np.max(np.abs(delta(np.float32) - ref)) / scale < 1.5e-6
