@@ -1,5 +1,8 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/r3_t7.log 2>&1; tail -3 gpurun_out/r3_t7.log
-timeout 600 python bench.py --steps 10 --warmup 3 --no-c5 > gpurun_out/r3_bench1.json 2> gpurun_out/r3_bench1.err; python -c "
-import json;d=json.load(open('gpurun_out/r3_bench1.json'));print(d['ms_per_step'],d['value']/1e9,d['step_ms'],d['parity'],d['e2e']['ms_per_step'])"
+timeout 600 python -m pytest tests/test_gpu_ops.py -x -q -m gpu -k "resample or fft or hilbert" > gpurun_out/r3_t10.log 2>&1; tail -2 gpurun_out/r3_t10.log
+for v in 0 1; do
+if [ $v = 1 ]; then export ECOG_FFT_TWO_CTAS=1; fi
+timeout 600 python bench.py --steps 8 --warmup 3 --no-c5 --no-e2e --no-cpu > gpurun_out/r3_bench4_$v.json 2> gpurun_out/r3_bench4_$v.err; python -c "
+import json;d=json.load(open('gpurun_out/r3_bench4_$v.json'));print($v, d['ms_per_step'],d['step_ms'],d['parity']['max_rel'])"
+done
