@@ -90,6 +90,7 @@ PROTOTYPES = {
     "ecog_cplx_modulate": (C.c_int, [_P, _I32, _I64, _I64, _P, _P, _I32, _I64, _I64, _I64, _P]),
     "ecog_cplx_abs_accumulate": (C.c_int, [_P, _I64, _P, _I64, _I64, _I64, _I32, C.c_float, _I32, _P]),
     "ecog_fir_decimate": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _I32, _I32, _I32, _P]),
+    "ecog_halfband2_decimate": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _I32, _P, _I32, _P]),
     "ecog_fir_causal": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _P, _I32, _P]),
     "ecog_rolling_workspace": (_SZ, [_I64, _I64]),
     "ecog_rolling_zscore": (C.c_int, [_P, _P, _I64, _I64, _I64, _I64, _I64, _P, C.c_int, _P, _SZ, _P]),

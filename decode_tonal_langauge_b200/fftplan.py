@@ -270,6 +270,36 @@ class PreDecimation:
     taps: np.ndarray        # float32 (ntaps,), ntaps % 4 == 0 (zero padded), DC gain 1
     offset: int             # y1[m] = sum_j taps[j] x[(m D + j - offset) mod T]; offset % 4 == 0
     bin_gain: np.ndarray    # float32 (num/2 + 1,): 1 / H1[k], H1 = DFT_T of the (float32) taps
+    halfband: tuple = None  # D == 4 as two half-band stages: (stage1, stage2), each float32 (1 + K,) = centre tap, odd taps
+
+
+HALFBAND_K = (8, 21)        # odd tap pairs the kernel is built for (csrc/firdecim.cu: kHbK1, kHbK2)
+
+
+def _halfband_stage(f_pass: float, kmax: int):
+    """Half-band low-pass (cut-off at half the Nyquist frequency, every second tap zero) that stops [1 - f_pass, 1]
+    by FIR_ATTENUATION_DB: the shortest Kaiser design with at most ``kmax`` odd tap pairs, float32; None if none does.
+    Returns (centre tap, odd taps g_i at distance 2 i + 1) as one float32 vector."""
+    from scipy import signal as sp_signal
+    f = np.linspace(1.0 - f_pass, 1.0, 4001)
+    for K in range(2, kmax + 1):
+        for att in (FIR_ATTENUATION_DB, FIR_ATTENUATION_DB + 4.0, FIR_ATTENUATION_DB + 8.0):
+            n = 4 * K - 1
+            h = sp_signal.firwin(n, 0.5, window=("kaiser", sp_signal.kaiser_beta(att)))
+            c = 2 * K - 1
+            st = np.concatenate([[h[c]], h[c + 1::2]]).astype(np.float32)
+            i = np.arange(K, dtype=np.float64)
+            H = float(st[0]) + 2.0 * np.sum(st[1:].astype(np.float64)[None, :] * np.cos(np.pi * f[:, None] * (2 * i + 1)[None, :]), axis=1)
+            if 20.0 * np.log10(np.max(np.abs(H)) + 1e-300) <= -FIR_ATTENUATION_DB:
+                return st
+    return None
+
+
+def _halfband_response(st: np.ndarray, k: np.ndarray, period: int) -> np.ndarray:
+    """Exact response of a (float32) half-band stage at the bins k of a `period`-sample row (zero phase)."""
+    i = np.arange(st.size - 1, dtype=np.float64)
+    return float(st[0]) + 2.0 * np.sum(st[1:].astype(np.float64)[None, :]
+                                         * np.cos(2.0 * np.pi * k[:, None] * (2 * i + 1)[None, :] / period), axis=1)
 
 
 @functools.lru_cache(maxsize=16)
@@ -284,6 +314,15 @@ def predecimation(T: int, num: int):
     from scipy import fft as sp_fft
     if num >= T:
         return None
+    if T % 4 == 0 and T // 4 >= 1.15 * num and T > 4 * (4 * HALFBAND_K[1] + 64):
+        # decimation by 4 as two half-band stages (19 instead of 40 products per sample at 2 kHz -> 400 Hz)
+        s1 = _halfband_stage(num / T, HALFBAND_K[0])
+        s2 = _halfband_stage(2.0 * num / T, HALFBAND_K[1])
+        if s1 is not None and s2 is not None:
+            k = np.arange(num // 2 + 1, dtype=np.float64)
+            H = _halfband_response(s1, k, T) * _halfband_response(s2, k, T // 2)
+            if np.min(H) >= 0.5:
+                return PreDecimation(4, np.zeros(4, dtype=np.float32), 0, (1.0 / H).astype(np.float32), (s1, s2))
     for D in (4, 2):
         if T % D:
             continue

@@ -637,6 +637,18 @@ def fir_decimate(x: torch.Tensor, taps: np.ndarray, offset: int, D: int) -> torc
     return y
 
 
+def halfband2_decimate(x: torch.Tensor, stage1: np.ndarray, stage2: np.ndarray) -> torch.Tensor:
+    """Decimation by 4 as two circular half-band stages (ecog_halfband2_decimate); ``stage`` = centre tap, odd taps."""
+    x = as_signal(x)
+    Cn, T = x.shape
+    s1 = np.ascontiguousarray(stage1, dtype=np.float32)
+    s2 = np.ascontiguousarray(stage2, dtype=np.float32)
+    y = torch.empty((Cn, T // 4), dtype=torch.float32, device=x.device)
+    nat.check(lib.ecog_halfband2_decimate(_ptr(x), _ptr(y), Cn, T, _ld(x), _ld(y), _hptr(s1), int(s1.size) - 1,
+                                          _hptr(s2), int(s2.size) - 1, _stream()))
+    return y
+
+
 def _fft_resample(x: torch.Tensor, num: int, bin_gain: Optional[np.ndarray], gain_key=None) -> torch.Tensor:
     Cn, T = x.shape
     rp = FP.resample_plan(int(T), num)
@@ -760,7 +772,7 @@ def fft_resample(x: torch.Tensor, num: int, two_stage: Optional[bool] = None) ->
 
     pre = FP.predecimation(int(T), num) if two_stage in (None, True) else None
     if pre is not None:
-        x1 = fir_decimate(x, pre.taps, pre.offset, pre.D)
+        x1 = halfband2_decimate(x, *pre.halfband) if pre.halfband is not None else fir_decimate(x, pre.taps, pre.offset, pre.D)
         if smooth(int(T) // pre.D):
             return _fft_resample(x1, num, pre.bin_gain, gain_key=(int(T), pre.D))
         return _czt_resample(x1, num, pre.bin_gain, gain_key=(int(T), pre.D))     # non-smooth T/D: Bluestein

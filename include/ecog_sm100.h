@@ -246,6 +246,17 @@ int ecog_cplx_abs_accumulate(const float* d_z, int64_t ld_z, float* d_acc, int64
 int ecog_fir_decimate(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
                       const float* h_taps, int32_t ntaps, int32_t offset, int32_t D,
                       ecog_stream_t stream);
+/* Decimation by 4 as TWO circular half-band stages (the same role in downsample.py:21-27, ABI 7): a decimate-by-2
+ * stage in front of a brick wall at f_pass has the band edges f_pass and 1 - f_pass, symmetric about half the
+ * Nyquist frequency, so every second tap of both stages is zero:
+ *   y1[c, n] = h1[0] x[c, 2n] + sum_{i<k1} h1[1+i] (x[c, (2n-2i-1) mod T] + x[c, (2n+2i+1) mod T]),   n < T/2
+ *   y [c, m] = h2[0] y1[c, 2m] + sum_{i<k2} h2[1+i] (y1[c, (2m-2i-1) mod T/2] + y1[c, (2m+2i+1) mod T/2]),  m < T/4
+ * (19.25 instead of 40 products per input sample for 2 kHz -> 400 Hz; y1 never leaves shared memory).  The FFT stage
+ * then divides bin k by H1[k] H2[k] = (h1[0] + 2 sum h1[1+i] cos(2 pi k (2i+1) / T)) (h2[0] + 2 sum h2[1+i] cos(4 pi k (2i+1) / T)).
+ * h_stage1: 1 + k1 floats (k1 <= 8), h_stage2: 1 + k2 floats (k2 <= 21), host.  T % 4 == 0.           */
+int ecog_halfband2_decimate(const float* d_x, float* d_y, int64_t C, int64_t T, int64_t ldx, int64_t ldy,
+                            const float* h_stage1, int32_t k1, const float* h_stage2, int32_t k2,
+                            ecog_stream_t stream);
 
 /* ------------------------------------------------------- K6: causal FIR (long)
  * replaces preprocess/signal/frequency_filter.py:260-274 (`fir` band method).  The mean over

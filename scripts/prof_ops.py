@@ -23,6 +23,8 @@ x = torch.randn((C, T), device="cuda") * 30
 
 def fir():
     pre = FP.predecimation(T, T // 5)
+    if pre.halfband is not None:
+        return ops.halfband2_decimate(x, *pre.halfband)
     return ops.fir_decimate(x, pre.taps, pre.offset, pre.D)
 
 

@@ -144,8 +144,21 @@ def big_fft(z: np.ndarray, plan) -> np.ndarray:
     return X.reshape(-1)                                    # k = p * na + q
 
 
+def halfband_stage_model(x32: np.ndarray, st: np.ndarray) -> np.ndarray:
+    """One circular half-band stage of ecog_halfband2_decimate: y[n] = c x[2n] + sum_i g_i (x[2n-2i-1] + x[2n+2i+1])."""
+    T = x32.shape[0]
+    dt = x32.dtype                  # float32 like the kernel, or float64 as the exact sums
+    n2 = 2 * np.arange(T // 2, dtype=np.int64)
+    y = dt.type(st[0]) * x32[n2]
+    for i, g in enumerate(st[1:]):
+        y = y + dt.type(g) * x32[(n2 - 2 * i - 1) % T] + dt.type(g) * x32[(n2 + 2 * i + 1) % T]
+    return y.astype(dt)
+
+
 def fir_decimate_model(x32: np.ndarray, pre) -> np.ndarray:
     """Model of csrc/firdecim.cu for one row: circular FIR + decimate, float32 accumulation."""
+    if pre.halfband is not None:
+        return halfband_stage_model(halfband_stage_model(x32, pre.halfband[0]), pre.halfband[1])
     T = x32.shape[0]
     T1 = T // pre.D
     y = np.zeros(T1, dtype=np.float32)

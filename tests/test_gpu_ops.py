@@ -292,6 +292,24 @@ def test_fir_decimate_matches_model(ops, T, D):
         assert y.shape == ref.shape and max_rel(y, ref64) < 2e-6
 
 
+@pytest.mark.parametrize("T", [12000, 8192 * 4, 8192 * 4 + 12, 200_004, 1_200_000])
+def test_halfband2_decimate_matches_model(ops, T):
+    """ecog_halfband2_decimate (two circular half-band stages, intermediate row in shared memory) against the float64
+    evaluation of the same two sums: arbitrary taps of every supported length, rows that end inside a CTA's tile,
+    a strided view."""
+    from helpers import emulate as EM
+    rng = np.random.default_rng(T)
+    big = (rng.standard_normal((3, T + 8)) * 10).astype(np.float32)
+    x = big[:, :T]
+    for k1, k2 in ((8, 21), (7, 20), (1, 1), (3, 12)):
+        s1 = (rng.standard_normal(1 + k1) / (1 + 2 * k1)).astype(np.float32)
+        s2 = (rng.standard_normal(1 + k2) / (1 + 2 * k2)).astype(np.float32)
+        y = host(ops.halfband2_decimate(dev(big)[:, :T], s1, s2))
+        ref = np.stack([EM.halfband_stage_model(EM.halfband_stage_model(r.astype(np.float64), s1.astype(np.float64)).astype(np.float64),
+                                                s2.astype(np.float64)) for r in x])
+        assert y.shape == (3, T // 4) and max_rel(y, ref) < 2e-6, (k1, k2)
+
+
 def test_resample_odd_golden(ops, golden):
     """Odd row length: the reference's own output for a 9001-sample row (chirp-z path)."""
     g = golden("steps")

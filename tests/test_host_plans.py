@@ -59,6 +59,10 @@ def test_two_stage_resample_model_vs_oracle(T, num):
     """FIR pre-decimation + gain-compensated brick wall == scipy.signal.resample of the whole row."""
     pre = FP.predecimation(T, num)
     assert pre is not None and T % pre.D == 0 and pre.offset % 4 == 0 and len(pre.taps) % 4 == 0
+    # ratios >= 5 with T % 4 == 0 take the two half-band stages (csrc/firdecim.cu: halfband2_decimate_kernel)
+    assert (pre.halfband is not None) == (T % 4 == 0 and num / T <= 0.2), (T, num)
+    if pre.halfband is not None:
+        assert pre.D == 4 and len(pre.halfband[0]) - 1 <= FP.HALFBAND_K[0] and len(pre.halfband[1]) - 1 <= FP.HALFBAND_K[1]
     rng = np.random.default_rng(T + num)
     x = rng.standard_normal(T).astype(np.float32) * 30          # white: worst case for aliasing
     x1 = EM.fir_decimate_model(x, pre)
