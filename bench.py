@@ -51,7 +51,9 @@ STEP_BYTES_PER_SAMPLE = {
 HILBERT_KEYS = ("car_rereference+frequency_filter[hilbert]", "frequency_filter[hilbert]")
 KERNEL_SOURCES = {"hilbert_env8_kernel": "decode_tonal_langauge_b200/csrc/hilbert.cu",
                   "sos_warm_kernel": "decode_tonal_langauge_b200/csrc/sos_common.cuh",
-                  "sos_warm_tma_kernel": "decode_tonal_langauge_b200/csrc/sosfilt_tma.cu"}
+                  "sos_warm_tma_kernel": "decode_tonal_langauge_b200/csrc/sosfilt_tma.cu",
+                  "sos_pair_ws_kernel": "decode_tonal_langauge_b200/csrc/sosfilt_pairws.cu",
+                  "halfband2_decimate_kernel": "decode_tonal_langauge_b200/csrc/firdecim.cu"}
 
 
 def source_sha(rel: str) -> str:
@@ -649,7 +651,7 @@ def run_ours(args):
                        "peak_source": rec.get("mix_ceiling_source", "4 schedulers x 1 warp instruction per clock"),
                        "source": rec["source"]}
         pair_key = "frequency_filter[butter_bandstop]+frequency_filter[butter_bandpass]"
-        rec_pair = ncu_record("sos_warm_tma_kernel")
+        rec_pair = ncu_record("sos_pair_ws_kernel") or ncu_record("sos_warm_tma_kernel")
         if pair_key in step_roofline and rec_pair and not rec_pair.get("stale"):
             # one sweep of the pair per capture entry; the group runs two (forward, backward)
             step_roofline[pair_key]["traffic_gb"] = 2 * rec_pair["dram_bytes_per_channel_sample"] * C * T / 1e9
