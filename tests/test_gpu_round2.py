@@ -61,7 +61,7 @@ def test_full6_full_length_default_plans_vs_oracle(C, T, fs):
     (y, f), kernels = _launched(lambda: preprocess_signal(x, FULL6_STEPS, Namespace(signal_freq=fs)))
     names = " ".join(kernels)
     assert "sos_pair_ws_fwd" in kernels and "sos_pair_ws_bwd" in kernels, names   # the fused pair (TMA tiles, notch and band-pass threads), not a fallback
-    assert "fir_decimate" in kernels, names                  # two-stage resampler
+    assert "halfband2_decimate" in kernels, names            # two-stage resampler (two half-band stages in front of the FFT)
     assert "hilbert_env8" in kernels and "car_colsum" in kernels and "car_fused" not in kernels, names
     rows = [0, C // 2 + 1, C - 1]
     no_car = [FULL6_STEPS[0]] + FULL6_STEPS[2:]
