@@ -1,5 +1,6 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-timeout 1200 python -m pytest tests -x -q -m gpu > gpurun_out/r4_t2.log 2>&1; tail -3 gpurun_out/r4_t2.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r4_smoke.log 2>&1; tail -3 gpurun_out/r4_smoke.log
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'hilbert_env8|halfband2' --launch-skip 4 -c 2 -o gpurun_out/prof_r4_hb_hil -f python scripts/prof_ops.py fir,hilbert_car 256 7200000 1 > gpurun_out/r4_ncu_full2.log 2>&1; tail -2 gpurun_out/r4_ncu_full2.log
+timeout 300 python scripts/prof_ops.py pair,pair,pair 256 7200000 10 > gpurun_out/r5_ops1.log 2>&1
+ECOG_PROF_FS=3000 timeout 300 python scripts/prof_ops.py pair,pair 128 10800000 10 >> gpurun_out/r5_ops1.log 2>&1
+cat gpurun_out/r5_ops1.log
+timeout 600 python -m pytest tests/test_gpu_round2.py -x -q -m gpu -s -k "float32_bandpass" > gpurun_out/r5_t1.log 2>&1; grep -n "pair @\|passed\|failed\|Error" gpurun_out/r5_t1.log
