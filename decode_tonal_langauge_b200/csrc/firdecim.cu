@@ -129,13 +129,12 @@ static int dispatch_taps(int nt4, const float* x, float* y, int64_t C, int64_t T
 //     y[n] = hc x[2n] + sum_{i < K} g_i (x[2n - 2i - 1] + x[2n + 2i + 1])              (2K + 1 products per output)
 // Stage 1 (T -> T/2: transition f_pass .. 1 - f_pass, wide) needs K1 = 8, stage 2 (T/2 -> T/4: 2 f_pass .. 1 - 2 f_pass)
 // K2 = 21 for 120 dB at f_pass = 0.2 (2 kHz -> 400 Hz): 17/2 + 43/4 = 19.25 products per input sample against the
-// 40 of the single 160-tap stage, which makes the step HBM-bound instead of FP32-bound.  The intermediate row lives
+// 40 of the single 160-tap stage, which takes the step off the FP32 pipe.  The intermediate row lives
 // in shared memory only.  Same circular indexing and the same exact compensation as above: the FFT stage divides the
 // kept bins by H1[k] H2[k] (fftplan.predecimation).
-// One tile = one channel x 1984 outputs (248 threads x 8): 4064 stage-1 values (254 tasks of 16, one per thread -- a
-// second round for a few stragglers would idle the CTA at the barrier) from 8160 staged inputs; both windows are read with conflict-free 128-bit loads (one pad word per
-// thread stride, as above).  A CTA walks eight consecutive tiles of its row and copies the next tile's inputs
-// (cp.async) while it filters the current one.
+// One CTA = one channel x 960 outputs (120 threads x 8): 2016 stage-1 values (126 tasks of 16, one per thread -- a
+// second round for a few stragglers would idle the CTA at the barrier) from 4064 staged inputs; both windows are
+// read with conflict-free 128-bit loads (one pad word per thread stride, as above).
 constexpr int kHbK1 = 8, kHbK2 = 21;
 struct HbTaps { float c1, g1[kHbK1], c2, g2[kHbK2]; };
 
@@ -168,30 +167,46 @@ __device__ __forceinline__ void hb_accumulate(const float4* __restrict__ win, fl
 }
 
 constexpr int kHbR2 = 8;                                   // outputs per thread
-constexpr int kHbT2 = 248;                                 // threads with stage-2 work: their stage-1 values are 254 <= 256 tasks
-constexpr int kHbM2 = kHbT2 * kHbR2;                       // 1984 outputs per tile
+constexpr int kHbThreads = 128;                            // threads per CTA: small CTAs, seven per SM -- the kernel's three
+                                                           // phases are separated by CTA barriers, and what hides them is other CTAs
+                                                           // (256 threads x 4 CTAs: 2.48 ms, 128 x 7: 2.35 ms, 64 x 16: 2.36 ms at C2;
+                                                           // double-buffered inputs at 256 x 2: 2.58 ms)
+constexpr int kHbT2 = kHbThreads - 8;                      // threads with stage-2 work: their stage-1 values are <= kHbThreads tasks of 16
+constexpr int kHbM2 = kHbT2 * kHbR2;                       // 960 outputs per tile
 constexpr int kHbL1 = (2 * kHbK1 - 1 + 3) / 4 * 4;         // window lead-ins: multiples of 4 >= 2K - 1 (16, 44)
 constexpr int kHbL2 = (2 * kHbK2 - 1 + 3) / 4 * 4;
 constexpr int kHbNW1 = (kHbL1 + 2 * 15 + 2 * kHbK1 - 1) / 4 + 1;               // window words of a stage-1 task (16)
 constexpr int kHbNW2 = (kHbL2 + 2 * (kHbR2 - 1) + 2 * kHbK2 - 1) / 4 + 1;      // window words of a stage-2 thread (25)
-constexpr int kHbTasks1 = (16 * (kHbT2 - 1) + 4 * kHbNW2 + 15) / 16;           // stage-1 tasks of 16 values (254)
-static_assert(kHbTasks1 <= kFirThreads, "one stage-1 task per thread: a second round would idle the CTA at the barrier");
-constexpr int kHbXW = 8 * (kHbTasks1 - 1) + kHbNW1;        // input words (float4) per CTA
+constexpr int kHbTasks1 = (16 * (kHbT2 - 1) + 4 * kHbNW2 + 15) / 16;           // stage-1 tasks of 16 values (126)
+static_assert(kHbTasks1 <= kHbThreads, "one stage-1 task per thread: a second round would idle the CTA at the barrier");
+constexpr int kHbXW = 8 * (kHbTasks1 - 1) + kHbNW1;        // input words (float4) per tile
 constexpr int kHbXS = kHbXW + kHbXW / 8 + 1;               // padded
 constexpr int kHbYW = 4 * kHbTasks1;                       // stage-1 words
 constexpr int kHbYS = kHbYW + kHbYW / 4 + 1;
+constexpr int kHbTilesPerCta = 8;
 
-constexpr int kHbTilesPerCta = 8;                          // consecutive tiles of one row per CTA (input double-buffered)
-
-// Stage the inputs of the tile whose first output is m0 into `xs`: asynchronous 16-byte copies for tiles inside the
-// row (one commit group; the caller waits), scalar circular loads for the first / last tiles of a row.
-__device__ __forceinline__ void hb_stage_inputs(float4* xs, const float* __restrict__ xr, int64_t m0, int64_t T, bool vec, int tid) {
+__global__ void __launch_bounds__(kHbThreads, 7)
+halfband2_decimate_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t T4, int64_t ldx,
+                          int64_t ldy, bool vec, const __grid_constant__ HbTaps taps) {
+    extern __shared__ __align__(16) float4 hsm[];
+    float4* xs = hsm;                                      // [kHbXS]  inputs, one pad word every 8
+    float4* ys = hsm + kHbXS;                              // [kHbYS]  stage-1 values, one pad word every 4
+    const int tid = threadIdx.x;
+    const int64_t ch = blockIdx.y;
+    const float* xr = x + ch * ldx;
+    const int64_t nTiles = (T4 + kHbM2 - 1) / kHbM2;
+    // a CTA walks kHbTilesPerCta consecutive tiles of its row (fewer, longer-lived CTAs: 2.35 against 2.41 ms at C2)
+    for (int64_t tile = (int64_t)blockIdx.x * kHbTilesPerCta; tile < nTiles && tile < (int64_t)(blockIdx.x + 1) * kHbTilesPerCta; ++tile) {
+    const int64_t m0 = tile * kHbM2;                       // first output of this tile
     const int64_t tin = 2 * (2 * m0 - kHbL2) - kHbL1;      // first input sample staged (may be < 0), multiple of 4
-    const bool interior = tin >= 0 && tin + 4 * (int64_t)kHbXW <= T;
-    if (vec && interior) {
-        for (int n = tid; n < kHbXW; n += kFirThreads) cp_async16(&xs[n + n / 8], xr + tin + 4 * (int64_t)n);
+
+    // ---- inputs: asynchronous 16-byte copies inside the row, scalar circular loads for the first / last tiles
+    if (vec && tin >= 0 && tin + 4 * (int64_t)kHbXW <= T) {
+        for (int n = tid; n < kHbXW; n += kHbThreads) cp_async16(&xs[n + n / 8], xr + tin + 4 * (int64_t)n);
+        cp_async_commit();
+        cp_async_wait<0>();
     } else {
-        for (int n = tid; n < kHbXW; n += kFirThreads) {
+        for (int n = tid; n < kHbXW; n += kHbThreads) {
             float v[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -202,64 +217,37 @@ __device__ __forceinline__ void hb_stage_inputs(float4* xs, const float* __restr
             xs[n + n / 8] = make_float4(v[0], v[1], v[2], v[3]);
         }
     }
-    cp_async_commit();
-}
+    __syncthreads();
 
-__global__ void __launch_bounds__(kFirThreads, 2)
-halfband2_decimate_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t T, int64_t T4, int64_t ldx,
-                          int64_t ldy, bool vec, const __grid_constant__ HbTaps taps) {
-    extern __shared__ __align__(16) float4 hsm[];
-    float4* xs0 = hsm;                                     // [2][kHbXS]  inputs of two tiles, one pad word every 8
-    float4* ys = hsm + 2 * kHbXS;                          // [kHbYS]     stage-1 values, one pad word every 4
-    const int tid = threadIdx.x;
-    const int64_t ch = blockIdx.y;
-    const float* xr = x + ch * ldx;
-    const int64_t tile0 = (int64_t)blockIdx.x * kHbTilesPerCta;
-    const int64_t nTiles = (T4 + kHbM2 - 1) / kHbM2;
-    const int nt = (int)(nTiles - tile0 < kHbTilesPerCta ? nTiles - tile0 : kHbTilesPerCta);
+    // ---- stage 1: task k -> stage-1 values 16 k .. 16 k + 15 (window: input words 8 k .. 8 k + 15, centre of value 0 at float kHbL1)
+    if (const int k = tid; k < kHbTasks1) {
+        float acc[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) acc[r] = 0.f;
+        hb_accumulate<kHbK1, 16, kHbL1, kHbNW1, 8>(xs + 9 * k, taps.c1, taps.g1, acc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ys[5 * k + j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    }
+    __syncthreads();
 
-    // the inputs of tile i + 1 travel while tile i is filtered: two CTAs per SM keep ~67 KB of loads in flight
-    hb_stage_inputs(xs0, xr, tile0 * kHbM2, T, vec, tid);
-    for (int i = 0; i < nt; ++i) {
-        const int64_t m0 = (tile0 + i) * kHbM2;            // first output of this tile
-        float4* xs = xs0 + (i & 1) * kHbXS;
-        if (i + 1 < nt) {
-            hb_stage_inputs(xs0 + ((i + 1) & 1) * kHbXS, xr, m0 + kHbM2, T, vec, tid);
-            cp_async_wait<1>();
+    // ---- stage 2: thread t -> outputs 8 t .. 8 t + 7 (window: stage-1 words 4 t .. 4 t + 24, centre of output 0 at float kHbL2)
+    if (tid < kHbT2) {
+        float acc[kHbR2];
+#pragma unroll
+        for (int r = 0; r < kHbR2; ++r) acc[r] = 0.f;
+        hb_accumulate<kHbK2, kHbR2, kHbL2, kHbNW2, 4>(ys + 5 * tid, taps.c2, taps.g2, acc);
+        const int64_t m = m0 + (int64_t)kHbR2 * tid;
+        float* yr = y + ch * ldy + m;
+        if (vec && m + kHbR2 <= T4) {
+            *reinterpret_cast<float4*>(yr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(yr + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
         } else {
-            cp_async_wait<0>();
+#pragma unroll
+            for (int r = 0; r < kHbR2; ++r)
+                if (m + r < T4) yr[r] = acc[r];
         }
-        __syncthreads();
-
-        // ---- stage 1: task k -> stage-1 values 16 k .. 16 k + 15 (window: input words 8 k .. 8 k + 15, centre of value 0 at float kHbL1)
-        if (const int k = tid; k < kHbTasks1) {
-            float acc[16];
-#pragma unroll
-            for (int r = 0; r < 16; ++r) acc[r] = 0.f;
-            hb_accumulate<kHbK1, 16, kHbL1, kHbNW1, 8>(xs + 9 * k, taps.c1, taps.g1, acc);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) ys[5 * k + j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-        }
-        __syncthreads();
-
-        // ---- stage 2: thread t -> outputs 8 t .. 8 t + 7 (window: stage-1 words 4 t .. 4 t + 24, centre of output 0 at float kHbL2)
-        if (tid < kHbT2) {
-            float acc[kHbR2];
-#pragma unroll
-            for (int r = 0; r < kHbR2; ++r) acc[r] = 0.f;
-            hb_accumulate<kHbK2, kHbR2, kHbL2, kHbNW2, 4>(ys + 5 * tid, taps.c2, taps.g2, acc);
-            const int64_t m = m0 + (int64_t)kHbR2 * tid;
-            float* yr = y + ch * ldy + m;
-            if (vec && m + kHbR2 <= T4) {
-                *reinterpret_cast<float4*>(yr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-                *reinterpret_cast<float4*>(yr + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
-            } else {
-#pragma unroll
-                for (int r = 0; r < kHbR2; ++r)
-                    if (m + r < T4) yr[r] = acc[r];
-            }
-        }
-        __syncthreads();        // this tile's reads of xs / ys are done before the next iteration refills xs[i & 1] and ys
+    }
+    __syncthreads();            // this tile's reads of xs / ys are done before the next tile refills them
     }
 }
 
@@ -374,10 +362,10 @@ extern "C" int ecog_halfband2_decimate(const float* d_x, float* d_y, int64_t C, 
     taps.c2 = h_stage2[0];
     for (int i = 0; i < k2; ++i) taps.g2[i] = h_stage2[1 + i];
     const bool vec = aligned16(d_x) && aligned16(d_y) && ldx % 4 == 0 && ldy % 4 == 0;
-    const size_t smem = (size_t)(2 * kHbXS + kHbYS) * sizeof(float4);
+    const size_t smem = (size_t)(kHbXS + kHbYS) * sizeof(float4);
     ECOG_TRY((smem_attr<halfband2_decimate_kernel>(smem)));
     dim3 grid((unsigned)ceil_div(ceil_div(T / 4, (int64_t)kHbM2), (int64_t)kHbTilesPerCta), (unsigned)C);
-    halfband2_decimate_kernel<<<grid, kFirThreads, smem, (cudaStream_t)stream>>>(d_x, d_y, T, T / 4, ldx, ldy, vec, taps);
+    halfband2_decimate_kernel<<<grid, kHbThreads, smem, (cudaStream_t)stream>>>(d_x, d_y, T, T / 4, ldx, ldy, vec, taps);
     return check_launch("halfband2_decimate");
 }
 
