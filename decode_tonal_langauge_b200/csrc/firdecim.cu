@@ -143,7 +143,7 @@ struct HbTaps { float c1, g1[kHbK1], c2, g2[kHbK2]; };
 // kernel's shared wavefronts were conflicts) where the padded 128-bit pattern has none
 __device__ __forceinline__ float4 lds128(const float4* p) {
     float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];"      // .volatile: ptxas narrows a plain v4 load whose components are dead
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((unsigned)__cvta_generic_to_shared(p)));
     return v;
 }

@@ -21,9 +21,9 @@
 
 namespace ecog {
 
-constexpr int kWsChunks = 256;        // chunks per CTA = box rows
+constexpr int kWsMaxChunks = 256;     // chunks per CTA = box rows: a run-time multiple of 32 (ecog_sos_plan.threads), chosen by
+                                      // the host so that the CTAs fill the SMs (125 CTAs of 256 chunks leave 23 of 148 SMs idle at C2)
 constexpr int kWsSub = 32;            // samples per stage
-constexpr int kWsTileBytes = kWsChunks * kWsSub * 4;
 
 // packed float32 pairs (sm_100 fma.rn.f32x2 / add.rn.f32x2): lane x = an even section, lane y = the next one
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
@@ -118,19 +118,21 @@ __device__ __forceinline__ void notch_block(const float (&x)[N], float (&y)[N], 
 // NA = 2: threads 0..255 run notch sections 0-1 (A1), 256..511 sections 2-3 (A2, float32 hand-over in the tile),
 //         512..767 the band-pass: four FP64 warps per scheduler instead of two.
 template <bool REV, int NUM, int NA>
-__global__ void __launch_bounds__(kWsChunks * (NA + 1), 1)
+__global__ void __launch_bounds__(kWsMaxChunks * (NA + 1), 1)
 sos_pair_ws_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
-                   int64_t nq, int L, int tail, int tail_b, int nChunks, SosCoef coef, float gain, Bp32Coef bpc) {
+                   int64_t nq, int L, int tail, int tail_b, int nChunks, SosCoef coef, float gain, Bp32Coef bpc, int P) {
+    const int tileFloats = P * kWsSub;             // one tile: P chunks x 32 samples
+    const uint32_t tileBytes = (uint32_t)tileFloats * 4u;
     constexpr int NR = NA + 1;                 // roles = pipeline depth in stages
     constexpr int SLOTS = NR + 2;
     extern __shared__ __align__(1024) unsigned char ws_smem[];
     unsigned char* base = ws_smem + ((1024u - (smem_u32(ws_smem) & 1023u)) & 1023u);    // SWIZZLE_128B repeats every 1024 B
-    float* tiles = reinterpret_cast<float*>(base);                                      // [SLOTS][256][32]
-    uint64_t* full = reinterpret_cast<uint64_t*>(base + SLOTS * kWsTileBytes);          // [SLOTS]
+    float* tiles = reinterpret_cast<float*>(base);                                      // [SLOTS][P][32]
+    uint64_t* full = reinterpret_cast<uint64_t*>(base + (size_t)SLOTS * tileBytes);     // [SLOTS]
     const int tid = threadIdx.x;
-    const int role = tid / kWsChunks;          // warp-uniform
-    const int ch = tid & (kWsChunks - 1);
-    const int64_t q0 = (int64_t)blockIdx.x * kWsChunks;
+    const int role = tid / P;                  // warp-uniform (P % 32 == 0)
+    const int ch = tid - role * P;
+    const int64_t q0 = (int64_t)blockIdx.x * P;
     const int64_t q = q0 + ch;
     const bool valid = q < nq;
     const int j = valid ? (int)(q % nChunks) : 0;
@@ -152,8 +154,8 @@ sos_pair_ws_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
             const int slot = (st - first) % SLOTS;
             int c0, c1;
             coords(st, c0, c1);
-            mbar_expect_tx(&full[slot], kWsTileBytes);
-            tma_load_2d(tiles + (size_t)slot * kWsChunks * kWsSub, &in_map, c0, c1, &full[slot]);
+            mbar_expect_tx(&full[slot], tileBytes);
+            tma_load_2d(tiles + (size_t)slot * tileFloats, &in_map, c0, c1, &full[slot]);
         }
     };
     if (tid == 0) {
@@ -197,7 +199,7 @@ sos_pair_ws_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
         if (sdone >= 0 && sdone < nStages) {
             int c0, c1;
             coords(sdone, c0, c1);
-            tma_store_2d(&out_map, c0, c1, tiles + (size_t)((it - NA) % SLOTS) * kWsChunks * kWsSub);
+            tma_store_2d(&out_map, c0, c1, tiles + (size_t)((it - NA) % SLOTS) * tileFloats);
             tma_commit();
             tma_wait_read<1>();         // the store of tile sdone - 1 has read its slot: refill it
         }
@@ -218,7 +220,7 @@ sos_pair_ws_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
             const int st = first + it - role;
             if (it >= role && st < nStages) {
                 const int slot = (it - role) % SLOTS;
-                float* mine = tiles + (size_t)slot * kWsChunks * kWsSub + ch * kWsSub;
+                float* mine = tiles + (size_t)slot * tileFloats + ch * kWsSub;
                 if (role == 0) mbar_wait(&full[slot], (uint32_t)(((it - role) / SLOTS) & 1));
                 if (st >= s_lo) {
                     float xs[kWsSub], ys[kWsSub];
@@ -257,7 +259,7 @@ sos_pair_ws_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
         for (int it = 0; it < nIter; ++it) {
             const int st = first + it - NA;
             if (it >= NA && st >= s_b) {
-                float* mine = tiles + (size_t)((it - NA) % SLOTS) * kWsChunks * kWsSub + ch * kWsSub;
+                float* mine = tiles + (size_t)((it - NA) % SLOTS) * tileFloats + ch * kWsSub;
                 float xs[kWsSub], ys[kWsSub];
                 rd(mine, xs);
                 bp32_block32(xs, ys, gain, bp);
@@ -274,15 +276,16 @@ sos_pair_ws_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_cons
 template <bool REV, int NUM, int NA>
 static int launch_ws(const float* in, float* out, int64_t C, const ecog_sos_plan& p, int nChunks, const SosCoef& coef,
                      float gain, const Bp32Coef& bpc, cudaStream_t st) {
+    const int P = p.threads;            // chunks per CTA (validated by the caller: 32 .. 256, multiple of 32)
     CUtensorMap in_map, out_map;
-    ECOG_TRY(make_chunk_map(&in_map, in, C * nChunks, p.chunk, kWsSub, kWsChunks));
-    ECOG_TRY(make_chunk_map(&out_map, out, C * nChunks, p.chunk, kWsSub, kWsChunks));
+    ECOG_TRY(make_chunk_map(&in_map, in, C * nChunks, p.chunk, kWsSub, P));
+    ECOG_TRY(make_chunk_map(&out_map, out, C * nChunks, p.chunk, kWsSub, P));
     constexpr int SLOTS = NA + 3;
-    const size_t smem = (size_t)SLOTS * kWsTileBytes + SLOTS * sizeof(uint64_t) + 1024;     // + alignment slack
+    const size_t smem = (size_t)SLOTS * P * kWsSub * 4 + SLOTS * sizeof(uint64_t) + 1024;     // + alignment slack
     ECOG_TRY((smem_attr<sos_pair_ws_kernel<REV, NUM, NA>>(smem)));
-    const unsigned grid = (unsigned)ceil_div(C * nChunks, kWsChunks);
-    sos_pair_ws_kernel<REV, NUM, NA><<<grid, kWsChunks * (NA + 1), smem, st>>>(in_map, out_map, C * nChunks, p.chunk, p.tail, p.tail_b, nChunks,
-                                                                 coef, gain, bpc);
+    const unsigned grid = (unsigned)ceil_div(C * nChunks, (int64_t)P);
+    sos_pair_ws_kernel<REV, NUM, NA><<<grid, P * (NA + 1), smem, st>>>(in_map, out_map, C * nChunks, p.chunk, p.tail, p.tail_b, nChunks,
+                                                                      coef, gain, bpc, P);
     return check_launch(REV ? "sos_pair_ws_bwd" : "sos_pair_ws_fwd");
 }
 
@@ -292,6 +295,8 @@ static int launch_ws(const float* in, float* out, int64_t C, const ecog_sos_plan
 int run_sos_pair_ws(const float* x, float* y, int64_t C, int64_t T, const ecog_sos_plan& p, const SosCoef& coef_in,
                     float* tmp, cudaStream_t st) {
     const int nChunks = (int)(T / p.chunk);
+    if (p.threads < 32 || p.threads > kWsMaxChunks || p.threads % 32)
+        return fail(ECOG_E_VALUE, "ecog_sosfilt (float32 band-pass half): plan.threads = chunks per CTA must be a multiple of 32 in 32..256 (got %d)", p.threads);
     SosCoef coef = coef_in;
     const int na = unit_form(coef, 0, 4, 0), nb = unit_form(coef, 4, 8, -1);
     if (!((na == 2 || na == 8) && nb == 5))

@@ -236,6 +236,30 @@ def tma_chunk(Cn: int, T: int, tail: int, max_per_sm: int = 2) -> Optional[int]:
     return None if best is None else best[1]
 
 
+PAIR_WS_CHUNKS = (256, 224, 192)      # chunks per CTA the warp-specialised pair may run with (csrc/sosfilt_pairws.cu)
+
+
+def pair_ws_shape(Cn: int, T: int, tail: int) -> Optional[Tuple[int, int]]:
+    """(chunks per CTA P, chunk length L) for the warp-specialised pair: one CTA per SM, so the sweep lasts
+    ceil(CTAs / 148) x P x (L + tail) FP64-bound thread-samples per SM.  With P fixed at 256 the divisors of T leave
+    125 CTAs for 148 SMs at C2; P = 224 makes it 143 CTAs of 7/8 the work each.  ECOG_PAIR_P pins P."""
+    pin = os.environ.get("ECOG_PAIR_P")
+    best = None
+    for P in ((int(pin),) if pin else PAIR_WS_CHUNKS):
+        for n in range(2, T // max(tail, 32) + 1):
+            if T % n:
+                continue
+            L = T // n
+            if L % 32 or L < tail:
+                continue
+            ctas = -(-Cn * n // P)
+            waves = -(-ctas // D.NUM_SMS)
+            cost = waves * P * (L + tail)
+            if best is None or cost < best[0]:
+                best = (cost, P, L)
+    return None if best is None else (best[1], best[2])
+
+
 def sosfilt(x: torch.Tensor, dsg: D.SosDesign, chunk: Optional[int] = None,
             out: Optional[torch.Tensor] = None, mode: Optional[str] = None, ws_tag: str = "sos") -> torch.Tensor:
     """Biquad cascade, zero-phase (filtfilt semantics) or causal.  ``mode``: "warm" (one kernel
@@ -360,12 +384,17 @@ def sosfilt_pair(x: torch.Tensor, A: D.SosDesign, B: D.SosDesign, out: Optional[
     dsg, plan, V = pp
     if _tma_enabled() and _ld(x) == T and _ld(y) == T:
         tail32 = -(-V // 32) * 32
-        L = tma_chunk(Cn, T, tail32, max_per_sm=1)       # the 8-section kernel keeps its coefficients in registers: one CTA per SM
-        if L is not None and T // L > 1:
-            # band-pass second half in float32 delta form when its poles allow it (12 of 29 FP64 operations per
-            # sample leave the FP64 pipe; <= ~1e-6 of the row maximum, ECOG_PAIR_F32=0 keeps everything in float64)
-            split = 4 | (nat.SOS_SPLIT_F32B if _pair_f32_enabled() and D.bandpass_f32_ok(B) else 0)
-            plan = nat.SosPlan(8, 1, dsg.padlen, L, tail32, nat.SOS_WARMUP_TMA, 256, split, -(-min(plan.tail_b, V) // 32) * 32)
+        # band-pass second half in float32 delta form when its poles allow it (12 of 29 FP64 operations per
+        # sample leave the FP64 pipe; <= ~1e-6 of the row maximum, ECOG_PAIR_F32=0 keeps everything in float64)
+        f32b = _pair_f32_enabled() and D.bandpass_f32_ok(B)
+        shape = pair_ws_shape(Cn, T, tail32) if f32b else None
+        if shape is None:
+            L = tma_chunk(Cn, T, tail32, max_per_sm=1)   # the 8-section kernel keeps its coefficients in registers: one CTA per SM
+            shape = None if L is None else (256, L)
+        if shape is not None and T // shape[1] > 1:
+            split = 4 | (nat.SOS_SPLIT_F32B if f32b else 0)
+            plan = nat.SosPlan(8, 1, dsg.padlen, shape[1], tail32, nat.SOS_WARMUP_TMA, shape[0], split,
+                               -(-min(plan.tail_b, V) // 32) * 32)
     if T <= dsg.padlen:
         raise ValueError(f"The length of the input vector x must be greater than padlen, which is {dsg.padlen}.")
     # exact edges (they only read x): rows 0..C-1 = left segments, C..2C-1 = right segments.  Twelve small
