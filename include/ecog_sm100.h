@@ -93,7 +93,8 @@ typedef struct {
     int32_t chunk;       /* samples per scan chunk, multiple of 16                    */
     int32_t tail;        /* multiple of 16; <= chunk in scan mode                     */
     int32_t mode;        /* ECOG_SOS_SCAN (exact carry scan) or ECOG_SOS_WARMUP        */
-    int32_t threads;     /* warm-up mode: threads per CTA, 256 or 512                 */
+    int32_t threads;     /* warm-up mode: threads per CTA, 256 or 512; with ECOG_SOS_SPLIT_F32B: chunks per CTA,
+                            a multiple of 32 in 32..256 (the CTA runs twice as many threads)            */
     int32_t split;       /* 0, or 4 (| ECOG_SOS_SPLIT_F32B): h_sos holds TWO 4-section unit-form cascades */
     int32_t tail_b;      /* split: warm-up samples of the second cascade (<= tail)     */
 } ecog_sos_plan;
