@@ -332,3 +332,41 @@ def test_bandpass_delta_form_is_the_same_filter():
     scale = np.max(np.abs(ref))
     assert np.max(np.abs(delta(np.float64) - ref)) / scale < 1e-12
     assert np.max(np.abs(delta(np.float32) - ref)) / scale < 1.5e-6
+
+
+@pytest.mark.parametrize("T,num", [(7_200_000, 1_440_000), (10_800_000, 1_440_000), (1_200_000, 120_000)])
+def test_halfband_predecimation_design(T, num):
+    """fftplan.predecimation for ratios >= 5: two half-band Kaiser stages that fit the kernel (csrc/firdecim.cu:
+    kHbK1 = 8, kHbK2 = 21), >= 120 dB where the decimation folds onto the kept band, and a compensation table that is
+    the reciprocal of the product of the two (float32) stage responses."""
+    pre = FP.predecimation(T, num)
+    assert pre is not None and pre.D == 4 and pre.halfband is not None
+    s1, s2 = pre.halfband
+    assert s1.dtype == np.float32 and s2.dtype == np.float32
+    assert len(s1) - 1 <= FP.HALFBAND_K[0] and len(s2) - 1 <= FP.HALFBAND_K[1]
+    f_pass = num / T
+
+    def resp(st, f):            # f in units of the stage's own Nyquist frequency
+        i = np.arange(len(st) - 1)
+        return float(st[0]) + 2 * np.sum(st[1:].astype(np.float64)[None] * np.cos(np.pi * f[:, None] * (2 * i + 1)[None]), axis=1)
+
+    for st, fp in ((s1, f_pass), (s2, 2 * f_pass)):
+        stop = np.abs(resp(st, np.linspace(1 - fp, 1, 2001)))
+        assert 20 * np.log10(stop.max()) <= -120.0
+        assert abs(resp(st, np.zeros(1))[0] - 1.0) < 1e-6          # DC gain 1
+    k = np.arange(0, num // 2 + 1, max(1, num // 2000), dtype=np.float64)
+    H = resp(s1, 2 * k / T) * resp(s2, 4 * k / T)
+    assert np.allclose(pre.bin_gain[k.astype(int)], 1.0 / H, rtol=2e-6)
+
+
+def test_pair_ws_shape_fills_the_sms():
+    """ops.pair_ws_shape: chunks per CTA and chunk length of the warp-specialised cascade pair -- the chunk length
+    divides the row, is a multiple of 32 and covers the warm-up; at C2 224 chunks per CTA give 143 CTAs for 148 SMs."""
+    ops = pytest.importorskip("decode_tonal_langauge_b200.ops")
+    for C, T, tail in ((256, 7_200_000, 10368), (128, 10_800_000, 16224), (21, 7_200_000, 10368), (8, 600_000, 10368)):
+        shape = ops.pair_ws_shape(C, T, tail)
+        assert shape is not None
+        P, L = shape
+        assert P in ops.PAIR_WS_CHUNKS and T % L == 0 and L % 32 == 0 and L >= tail
+    assert ops.pair_ws_shape(256, 7_200_000, 10368) == (224, 57600)
+    assert ops.pair_ws_shape(4, 7_200_002, 10368) is None          # no divisor that is a multiple of 32
