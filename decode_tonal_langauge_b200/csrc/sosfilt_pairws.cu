@@ -5,11 +5,12 @@
 // Replaces frequency_filter.py:218-229 twice (58-62 Hz band-stop, 70-150 Hz band-pass), like sosfilt_pair.cu.
 //
 // Data path = sosfilt_tma.cu: the (C, T) array is one 2-D tensor [C * nChunks][L]; a stage is a box of
-// 256 chunks x 32 samples (SWIZZLE_128B) brought in by one cp.async.bulk.tensor and completed on an mbarrier.
-// Iteration i:  threads   0..255 ("A") filter stage i   of their chunk through the notch, float32 result in place;
-//               threads 256..511 ("B") filter stage i-1 (the tile A finished one iteration earlier) through the
+// P chunks x 32 samples (SWIZZLE_128B; P = a run-time multiple of 32, 224 at C2) brought in by one
+// cp.async.bulk.tensor and completed on an mbarrier.
+// Iteration i:  threads 0..P-1   ("A") filter stage i   of their chunk through the notch, float32 result in place;
+//               threads P..2P-1  ("B") filter stage i-1 (the tile A finished one iteration earlier) through the
 //               band-pass, in place; after the CTA barrier one thread stores tile i-1 with cp.async.bulk.tensor
-//               and prefetches stage i+2 into the slot whose store (tile i-2) has been read.  Four 32 KB slots.
+//               and prefetches stage i+2 into the slot whose store (tile i-2) has been read.  Four slots of P x 128 bytes.
 // Row ends: every chunk starts from a ZERO state `tail` samples early (stages that would reach in front of the
 // row are skipped); there is no filtfilt start-up here -- the caller (ops.sosfilt_pair) overwrites the first /
 // last `tail` samples of every row with the exact sequential result, as it does for the other pair kernels.
@@ -114,9 +115,9 @@ __device__ __forceinline__ void notch_block(const float (&x)[N], float (&y)[N], 
     }
 }
 
-// NA = 1: threads 0..255 run the whole notch (A), 256..511 the band-pass (B).
-// NA = 2: threads 0..255 run notch sections 0-1 (A1), 256..511 sections 2-3 (A2, float32 hand-over in the tile),
-//         512..767 the band-pass: four FP64 warps per scheduler instead of two.
+// NA = 1: threads 0..P-1 run the whole notch (A), P..2P-1 the band-pass (B).
+// NA = 2 (measured slower, instantiated only with ECOG_PAIR_THREE_ROLES): threads 0..P-1 run notch sections 0-1 (A1),
+//         P..2P-1 sections 2-3 (A2, float32 hand-over in the tile), 2P..3P-1 the band-pass.
 template <bool REV, int NUM, int NA>
 __global__ void __launch_bounds__(kWsMaxChunks * (NA + 1), 1)
 sos_pair_ws_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
