@@ -57,9 +57,15 @@ KERNEL_SOURCES = {"hilbert_env8_kernel": "decode_tonal_langauge_b200/csrc/hilber
 
 
 def source_sha(rel: str) -> str:
+    """sha256 of a kernel source with comments and white space removed: a capture stays valid across comment
+    edits and goes stale with the first change of code."""
     import hashlib
-    with open(os.path.join(ROOT, rel), "rb") as f:
-        return hashlib.sha256(f.read()).hexdigest()[:16]
+    import re
+    with open(os.path.join(ROOT, rel), "r", encoding="utf-8") as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    return hashlib.sha256(re.sub(r"\s+", " ", src).strip().encode()).hexdigest()[:16]
 
 
 def ncu_record(kernel: str):

@@ -5,7 +5,7 @@
 For every kernel family bench.py knows (bench.KERNEL_SOURCES) the first matching launch in the report
 gives: DRAM bytes (dram__bytes_read.sum + dram__bytes_write.sum) and executed warp instructions
 (smsp__inst_executed.sum), both divided by channels x samples of that launch, plus the sha256 of the
-kernel's source file AS IT IS NOW -- run this right after the capture, on the tree that was captured.
+kernel's source file (comments and white space removed) AS IT IS NOW -- run this right after the capture, on the tree that was captured.
 bench.py refuses the record (prints traffic: null, "stale") once the source file changes.
 Writes profiles/r02_traffic.json (merging with what is there).
 """
