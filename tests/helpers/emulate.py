@@ -95,6 +95,48 @@ def sos_warm_model(x32: np.ndarray, design, chunk: int, tail: int) -> np.ndarray
     return out
 
 
+def pair_ws_model(x32: np.ndarray, A, B, chunk: int, tail: int, tail_b: int) -> np.ndarray:
+    """Model of csrc/sosfilt_pairws.cu for one row (float32 in, float32 out): ONE forward and ONE backward sweep of
+    notch (float64 sections of design A) -> float32 -> band-pass (design B in float32 delta form, the product of the
+    gains applied in float32 between the halves); every chunk starts from a ZERO state `tail` samples early (the
+    band-pass `tail_b` samples early), at the row ends from a zero state at the edge.  The caller of the kernel
+    overwrites the first / last `tail` samples of a row; the model leaves them as the kernel computes them."""
+    T = x32.shape[0]
+    sa = np.array(A.sos, dtype=np.float64)
+    sb = np.array(B.sos, dtype=np.float64)
+    gain = np.float32(np.prod(sa[:, 0]) * np.prod(sb[:, 0]))
+    sa_monic = sa.copy()
+    sa_monic[:, :3] /= sa[:, :1]
+    c1 = (-(1.0 + sb[:, 4] + sb[:, 5])).astype(np.float32)
+    e2 = (1.0 - sb[:, 5]).astype(np.float32)
+
+    def bandpass32(v):
+        w1 = np.zeros(4, dtype=np.float32)
+        d = np.zeros(4, dtype=np.float32)
+        y = np.empty(v.size, dtype=np.float32)
+        for n in range(v.size):
+            u = np.float32(v[n]) * gain
+            for j in range(4):
+                dn = np.float32(c1[j] * w1[j] + (u - e2[j] * d[j])) + d[j]
+                u = dn + d[j]
+                w1[j] = w1[j] + dn
+                d[j] = dn
+            y[n] = u
+        return y
+
+    def sweep(u):
+        y = np.empty(T, dtype=np.float32)
+        for a in range(0, T, chunk):
+            b = min(a + chunk, T)
+            lo = max(a - tail, 0)
+            notch = sp_signal.sosfilt(sa_monic, u[lo:b].astype(np.float64)).astype(np.float32)      # zero state at lo
+            lb = max(a - tail_b, lo)
+            y[a:b] = bandpass32(notch[lb - lo:])[a - lb:]
+        return y
+
+    return sweep(sweep(x32)[::-1])[::-1]
+
+
 # ----------------------------------------------------------------------------- FFT models
 def _c(t):  # (n, 2) float32 table -> complex128
     return t[:, 0].astype(np.float64) + 1j * t[:, 1].astype(np.float64)

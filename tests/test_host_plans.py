@@ -370,3 +370,28 @@ def test_pair_ws_shape_fills_the_sms():
         assert P in ops.PAIR_WS_CHUNKS and T % L == 0 and L % 32 == 0 and L >= tail
     assert ops.pair_ws_shape(256, 7_200_000, 10368) == (224, 57600)
     assert ops.pair_ws_shape(4, 7_200_002, 10368) is None          # no divisor that is a multiple of 32
+
+
+def test_pair_ws_model_matches_two_filtfilts():
+    """The algorithm of csrc/sosfilt_pairws.cu on the CPU (tests/helpers/emulate.py::pair_ws_model): one forward and
+    one backward sweep of notch (float64) -> band-pass (float32 delta form), zero-state warm-up per chunk, against
+    scipy's filtfilt(band-pass, filtfilt(notch, x)) away from the row ends (the product overwrites the ends)."""
+    from decode_tonal_langauge_b200 import design as D
+    from decode_tonal_langauge_b200 import synth
+    fs, T, L = 2000.0, 48_000, 12_000
+    A = D.butter_design([58, 62], fs, 4, False, "bandstop")
+    B = D.butter_design([70, 150], fs, 4, False, "bandpass")
+    comb = D.pair_design(A, B)
+    assert comb is not None and D.bandpass_f32_ok(B)
+    natural = D.SosDesign(np.ascontiguousarray(np.vstack([A.sos, B.sos])), None, comb[0].padlen, True)
+    tail = D.warm_tail(natural, T)
+    assert 0 < tail <= L
+    tail32 = -(-tail // 32) * 32
+    x = synth.session_channels(1, [5], T, fs, 256)[0]
+    got = EM.pair_ws_model(x, A, B, L, tail32, min(comb[1], tail32))
+    # the notch of the truth in long double: the float64 direct form of the reference is itself 8e-6 off at 2 kHz
+    n_ld = np.asarray(S.filtfilt_pad(A.b, A.a, x[None].astype(np.float64), dtype=np.longdouble, reference_edges=True), dtype=np.float64)
+    ref = S.filtfilt_pad(B.b, B.a, n_ld)[0]
+    inner = slice(tail32, T - tail32)
+    err = np.max(np.abs(got[inner] - ref[inner])) / np.max(np.abs(ref[inner]))
+    assert err < 2e-6, err
